@@ -1,0 +1,17 @@
+"""chainer-speech-recognition_b200 -- B200-native CTC / Gram-CTC loss (forward + backward).
+
+The directory name is not a Python identifier; import it with
+``importlib.import_module("chainer-speech-recognition_b200")`` or through the alias module
+``b200ctc`` at the repository root.  Layout mirrors the reference for the one path it replaces:
+
+    asr/loss/gram_ctc.py   gram_ctc(...)                                (reference: asr/loss/gram_ctc.py)
+    asr/loss/ctc.py        connectionist_temporal_classification(...)   (reference: Chainer's, via run/ctc/*)
+    csrc/                  sm_100a kernels + the C ABI (include/b200ctc.h)
+"""
+from . import _lib
+from ._build import build
+from .asr.loss import (gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
+                       ConnectionistTemporalClassification, greedy_argmax)
+
+__all__ = ["gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
+           "ConnectionistTemporalClassification", "greedy_argmax", "build"]

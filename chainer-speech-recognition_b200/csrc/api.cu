@@ -1,0 +1,131 @@
+// api.cu -- extern "C" entry points declared in include/b200ctc.h.
+//
+// Plain pointers and sizes in, status codes out; the caller (PyTorch via ctypes) owns every buffer.
+// Reference interface replaced: asr/loss/gram_ctc.py:219-315 (GramCTC / gram_ctc) and Chainer's
+// connectionist_temporal_classification as called from run/ctc/cnn/train.py:191.
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200ctc.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace b200ctc;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *a = "", long long x = 0, long long y = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, x, y);
+    return code;
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return B200CTC_OK;
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? B200CTC_OUT_OF_MEMORY : B200CTC_CUDA_ERROR;
+}
+
+int validate(int kind, int B, int T, int V, int Lmax, int blank, bool need_blank) {
+    if (kind != B200CTC_KIND_CTC && kind != B200CTC_KIND_GRAM) return fail(B200CTC_INVALID_ARGUMENT, "kind must be 0 (CTC) or 1 (Gram-CTC)%s");
+    if (B < 0 || T < 0 || V <= 0 || Lmax < 0)
+        return fail(B200CTC_INVALID_ARGUMENT, "negative or empty dimension%s (B=%lld ...)", "", B);
+    if (need_blank && (blank < 0 || blank >= V))
+        return fail(B200CTC_INVALID_ARGUMENT, "blank symbol %s%lld outside [0, V=%lld)", "", blank, V);
+    const int Nmax = (kind == 0 ? 2 : 3) * Lmax + 1;
+    if (Nmax > lattice_max_nodes(kind))
+        return fail(B200CTC_UNSUPPORTED, "lattice of %s%lld nodes exceeds the %lld this build instantiates", "", Nmax,
+                    lattice_max_nodes(kind));
+    return B200CTC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200ctc_version(void) { return B200CTC_VERSION; }
+
+const char *b200ctc_last_error(void) { return g_err; }
+
+int b200ctc_workspace_bytes(int kind, int B, int T, int V, int Lmax, size_t *bytes_out) {
+    if (!bytes_out) return fail(B200CTC_INVALID_ARGUMENT, "bytes_out is NULL%s");
+    int rc = validate(kind, B, T, V, Lmax, 0, false);
+    if (rc) return rc;
+    *bytes_out = make_layout(kind, B, T, V, Lmax).total;
+    return B200CTC_OK;
+}
+
+int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
+                    const int32_t *bigrams, const int32_t *input_lengths, const int32_t *label_lengths, int blank,
+                    int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_sum, int64_t *argmax_out,
+                    void *workspace, size_t workspace_bytes, unsigned flags, void *stream_) {
+    (void)flags;
+    int rc = validate(kind, B, T, V, Lmax, blank, true);
+    if (rc) return rc;
+    if (!acts && (size_t)B * T > 0) return fail(B200CTC_INVALID_ARGUMENT, "acts is NULL%s");
+    if (!labels && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "labels is NULL%s");
+    if (kind == B200CTC_KIND_GRAM && !bigrams && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "bigrams is NULL for Gram-CTC%s");
+    if (!loss_per_utt || !loss_sum || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "output or workspace pointer is NULL%s");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
+    if ((reinterpret_cast<uintptr_t>(acts) & 3) != 0) return fail(B200CTC_INVALID_ARGUMENT, "acts must be 4-byte aligned%s");
+    const WsLayout w = make_layout(kind, B, T, V, Lmax);
+    if (workspace_bytes < w.total)
+        return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s: %lld < %lld bytes", "", (long long)workspace_bytes,
+                    (long long)w.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0) return check_cuda(cudaMemsetAsync(loss_sum, 0, sizeof(float), stream), "memset");
+
+    ProblemDesc d;
+    d.kind = kind; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
+    d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
+    d.labels = labels; d.bigrams = kind == B200CTC_KIND_GRAM ? bigrams : nullptr;
+    d.input_lengths = input_lengths; d.label_lengths = label_lengths;
+
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    if ((rc = check_cuda(launch_prep(d, w, ws, stream), "prep kernel"))) return rc;
+    if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, stream), "softmax/gather kernel"))) return rc;
+
+    LatticeParams lp;
+    lp.labels = labels; lp.bigrams = d.bigrams;
+    lp.B = B; lp.T = T; lp.Lmax = Lmax; lp.W = w.W; lp.Np = w.Np; lp.C = 0;
+    lp.utt = reinterpret_cast<UttInfo *>(ws + w.off_utt);
+    lp.lp = reinterpret_cast<const float2 *>(ws + w.off_lp);
+    lp.fv = reinterpret_cast<float2 *>(ws + w.off_fv);
+    lp.gam = reinterpret_cast<float *>(ws + w.off_gam);
+    lp.loss_per_utt = loss_per_utt;
+    int st = 0;
+    if ((rc = check_cuda(launch_lattice(kind, lp, w.Nmax, stream, &st), "lattice kernel"))) return rc;
+    if (st) return fail(B200CTC_UNSUPPORTED, "lattice too large for the instantiated kernels%s");
+    return check_cuda(launch_loss_sum(loss_per_utt, B, loss_sum, stream), "loss sum kernel");
+}
+
+int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
+                     const int32_t *bigrams, int blank, int B, int T, int V, int Lmax, const float *grad_loss,
+                     int per_utterance, float scale, float *grad_out, int64_t gstride_t, int64_t gstride_b,
+                     const void *workspace, size_t workspace_bytes, void *stream_) {
+    int rc = validate(kind, B, T, V, Lmax, blank, true);
+    if (rc) return rc;
+    if ((size_t)B * T == 0) return B200CTC_OK;
+    if (!acts || !grad_loss || !grad_out || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    const WsLayout w = make_layout(kind, B, T, V, Lmax);
+    if (workspace_bytes < w.total) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
+    GradParams g;
+    g.d.kind = kind; g.d.B = B; g.d.T = T; g.d.V = V; g.d.Lmax = Lmax; g.d.blank = blank;
+    g.d.acts = acts; g.d.stride_t = stride_t; g.d.stride_b = stride_b;
+    g.d.labels = labels; g.d.bigrams = bigrams; g.d.input_lengths = nullptr; g.d.label_lengths = nullptr;
+    g.grad_loss = grad_loss; g.per_utterance = per_utterance; g.scale = scale;
+    g.grad_out = grad_out; g.gstride_t = gstride_t; g.gstride_b = gstride_b;
+    return check_cuda(launch_gradient(g, w, workspace, static_cast<cudaStream_t>(stream_)), "gradient kernel");
+}
+
+int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,
+                          int64_t *argmax_out, void *stream_) {
+    if (B < 0 || T < 0 || V <= 0) return fail(B200CTC_INVALID_ARGUMENT, "bad dimensions%s");
+    if ((size_t)B * T == 0) return B200CTC_OK;
+    if (!acts || !argmax_out) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    return check_cuda(launch_argmax(acts, stride_t, stride_b, B, T, V, argmax_out, static_cast<cudaStream_t>(stream_)),
+                      "argmax kernel");
+}
+
+}  // extern "C"

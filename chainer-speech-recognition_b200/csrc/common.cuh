@@ -1,0 +1,165 @@
+// common.cuh -- shared device helpers and the workspace layout of the B200 CTC / Gram-CTC library.
+//
+// Number format used by the lattice recursion ("split log2"): a log2-probability is carried as a
+// pair (hi, lo) of float32 with hi integer-valued and |lo| <~ 1.  Sums of hi parts are exact, so
+// alpha/beta values of magnitude 10^4 (T=800 frames x ~12 bits) keep an absolute resolution of
+// ~1e-7 without any per-frame renormalisation pass, and nothing can under/overflow the way a
+// linear-space recursion would.  SENT marks log(0) (the reference uses -1e10, gram_ctc.py:222).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200ctc {
+
+constexpr float SENT = -1.0e30f;              // "log 0" for hi parts
+constexpr float SENT_TEST = -1.0e29f;         // anything below this is treated as log 0
+constexpr float LOG2E_HI = 1.44269502162933349609375f;      // float(log2 e)
+constexpr float LOG2E_LO = 1.92596299112661746e-8f;         // log2 e - LOG2E_HI
+constexpr double LN2_D = 0.693147180559945309417232121458;
+constexpr float RINT_MAGIC = 12582912.0f;     // 1.5 * 2^23: (x + M) - M == rint(x) for |x| < 2^22
+
+// Per-utterance record written by the prep kernel and completed by the lattice kernel.
+struct UttInfo {
+    int Tb;        // clamped input length
+    int Lb;        // clamped label length
+    int Nb;        // lattice nodes: 2*Lb+1 (CTC) or 3*Lb+1 (Gram-CTC)
+    int Ub;        // number of distinct symbols among the non-blank-type nodes
+    float Ph;      // log2 P, integer part   (+1e30 when the alignment is infeasible)
+    float Pl;      // log2 P, fractional part
+    float loss;    // -ln P, or 1e10 when infeasible (reference quirk)
+    int flags;     // bit0: lengths were out of range and got clamped; bit1: infeasible
+};
+
+// Workspace carve-up (all offsets in bytes from a 16-byte aligned base).
+struct WsLayout {
+    int kind, B, T, V, Lmax;
+    int W;         // emission row width: [blank, label_0..label_{Lmax-1} (, bigram_0..)] padded to even
+    int Nmax;      // lattice nodes for Lmax
+    int Np;        // Nmax padded to a multiple of 4
+    size_t off_utt, off_lse, off_lp, off_fv, off_gam, off_usym, off_uoff, off_unode, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
+    WsLayout w;
+    w.kind = kind; w.B = B; w.T = T; w.V = V; w.Lmax = Lmax;
+    int width = 1 + (kind == 0 ? Lmax : 2 * Lmax);
+    w.W = (width + 1) & ~1;
+    w.Nmax = (kind == 0 ? 2 : 3) * Lmax + 1;
+    w.Np = (w.Nmax + 3) & ~3;
+    size_t o = 0;
+    const size_t BT = (size_t)B * (size_t)T;
+    w.off_utt = o;   o = align_up(o + sizeof(UttInfo) * (size_t)B, 256);
+    w.off_lse = o;   o = align_up(o + sizeof(float) * BT, 256);
+    w.off_lp = o;    o = align_up(o + sizeof(float2) * BT * w.W, 256);
+    w.off_fv = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);
+    w.off_gam = o;   o = align_up(o + sizeof(float) * BT * w.Np, 256);
+    w.off_usym = o;  o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
+    w.off_uoff = o;  o = align_up(o + sizeof(int) * (size_t)B * (w.Nmax + 1), 256);
+    w.off_unode = o; o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
+    w.total = o;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// rint for |x| < 2^22 on the FMA pipe (FRND would go through the slow conversion unit)
+__device__ __forceinline__ float rint_small(float x) {
+    return __fsub_rn(__fadd_rn(x, RINT_MAGIC), RINT_MAGIC);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (bulk-group completion)
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// order generic-proxy accesses against async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream4(float4 *p, const float4 &v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200ctc

@@ -1,0 +1,52 @@
+// kernels.h -- host-side launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace b200ctc {
+
+struct ProblemDesc {
+    int kind, B, T, V, Lmax, blank;
+    const float *acts;
+    int64_t stride_t, stride_b;
+    const int32_t *labels, *bigrams, *input_lengths, *label_lengths;
+};
+
+// kernel 0: per-utterance bookkeeping (lengths, distinct-symbol CSR for the gradient kernel)
+cudaError_t launch_prep(const ProblemDesc &d, const WsLayout &w, void *ws, cudaStream_t stream);
+
+// kernel 1: fused log-softmax statistics + label gather (+ optional greedy argmax)
+cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
+                                  cudaStream_t stream);
+cudaError_t launch_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,
+                          int64_t *argmax_out, cudaStream_t stream);
+
+// kernel 2: alpha/beta lattice recursion
+struct LatticeParams {
+    const int32_t *labels, *bigrams;
+    int B, T, Lmax, W, Np, C;
+    UttInfo *utt;
+    const float2 *lp;
+    float2 *fv;
+    float *gam;
+    float *loss_per_utt;
+};
+int lattice_max_nodes(int kind);
+cudaError_t launch_lattice(int kind, LatticeParams p, int Nmax, cudaStream_t stream, int *status);
+
+// loss_sum = sum_b loss_per_utt[b], fixed-order tree (deterministic)
+cudaError_t launch_loss_sum(const float *loss_per_utt, int B, float *loss_sum, cudaStream_t stream);
+
+// kernel 3: fused gradient
+struct GradParams {
+    ProblemDesc d;
+    const float *grad_loss;
+    int per_utterance;
+    float scale;
+    float *grad_out;
+    int64_t gstride_t, gstride_b;
+};
+cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream);
+
+}  // namespace b200ctc

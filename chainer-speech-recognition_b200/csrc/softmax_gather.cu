@@ -1,0 +1,360 @@
+// softmax_gather.cu -- kernel 0 (per-utterance bookkeeping) and kernel 1 (fused log-softmax
+// statistics + label gather + optional greedy argmax).
+//
+// Replaces, in the reference (asr/loss/gram_ctc.py):
+//   _softmax :18-21 and _log_matrix :48-57 over the whole (T,B,V) tensor (two extra 717 MB arrays at
+//   B=64,T=800,V=3500) and the per-frame `xp.take(y, index)` of loop 1/2 (:155,:175).
+// Kernel 1 reads each activation row exactly once and writes, per frame, ONE float (the log2
+// normaliser) plus the gathered log2-probabilities of the <= 1+2*Lmax symbols the lattice can emit.
+// No (T,B,V) log-probability tensor is ever materialised.
+//
+// One warp per frame, 128-bit loads, online (max, sum) per lane, warp-shuffle reduction.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200ctc {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kUnroll = 4;
+
+// ---------------------------------------------------------------------------------------------
+// kernel 0: lengths, lattice size and the distinct-symbol CSR used by the gradient kernel
+// (the merge of _compute_label_probability, gram_ctc.py:180-217, needs "which nodes share a symbol").
+// One CTA per utterance.  Only non-blank-type nodes go into the CSR; the blank-type nodes (every
+// 2nd / 3rd node) are summed directly by the gradient kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prep_kernel(ProblemDesc d, WsLayout w, unsigned char *ws) {
+    extern __shared__ int sm[];
+    const int b = blockIdx.x;
+    UttInfo *ui = reinterpret_cast<UttInfo *>(ws + w.off_utt) + b;
+    int *usym = reinterpret_cast<int *>(ws + w.off_usym) + (size_t)b * w.Nmax;
+    int *uoff = reinterpret_cast<int *>(ws + w.off_uoff) + (size_t)b * (w.Nmax + 1);
+    int *unode = reinterpret_cast<int *>(ws + w.off_unode) + (size_t)b * w.Nmax;
+
+    int Tb = d.input_lengths ? d.input_lengths[b] : d.T;
+    int Lb = d.label_lengths ? d.label_lengths[b] : d.Lmax;
+    int flags = 0;
+    if (Tb < 0 || Tb > d.T) { flags |= 1; Tb = max(0, min(Tb, d.T)); }
+    if (Lb < 0 || Lb > d.Lmax) { flags |= 1; Lb = max(0, min(Lb, d.Lmax)); }
+    const int per = d.kind == 0 ? 2 : 3;
+    const int Nb = per * Lb + 1;
+    // entries: the non-blank-type nodes in node order.  CTC: label i -> node 2i+1.
+    // Gram: unigram i -> node 3i+1, bigram i -> node 3i+2.
+    const int M = (per - 1) * Lb;
+    int *esym = sm;               // [M] symbol (or -1)
+    int *efirst = sm + M;         // [M] index of the first entry with the same symbol
+    int *epos = sm + 2 * M;       // [M] how many earlier entries share the symbol
+    int *rank = sm + 3 * M;       // [M] distinct-symbol index of a first entry
+    int *cnt = sm + 4 * M;        // [M] list length per distinct symbol
+    const int32_t *lab = d.labels + (size_t)b * d.Lmax;
+    const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)b * d.Lmax : nullptr;
+    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        int s;
+        if (d.kind == 0) s = lab[e];
+        else s = (e & 1) ? big[e >> 1] : lab[e >> 1];
+        if (s < 0 || s >= d.V) s = -1;                     // dead bigram (or an id outside the vocabulary)
+        esym[e] = s;
+        cnt[e] = 0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        const int s = esym[e];
+        int first = e, pos = 0;
+        if (s >= 0) {
+            for (int e2 = 0; e2 < e; ++e2)
+                if (esym[e2] == s) { if (pos == 0) first = e2; ++pos; }
+        }
+        efirst[e] = first;
+        epos[e] = pos;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int u = 0;
+        for (int e = 0; e < M; ++e) {
+            if (esym[e] >= 0 && efirst[e] == e) { rank[e] = u; usym[u] = esym[e]; ++u; }
+        }
+        ui->Tb = Tb; ui->Lb = Lb; ui->Nb = Nb; ui->Ub = u;
+        ui->Ph = 0.f; ui->Pl = 0.f; ui->loss = 0.f; ui->flags = flags;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < M; e += blockDim.x)
+        if (esym[e] >= 0) atomicAdd(&cnt[rank[efirst[e]]], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int U = ui->Ub;
+        int acc = 0;
+        for (int u = 0; u < U; ++u) { uoff[u] = acc; acc += cnt[u]; }
+        uoff[U] = acc;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+        if (esym[e] < 0) continue;
+        const int node = d.kind == 0 ? (2 * e + 1) : (3 * (e >> 1) + 1 + (e & 1));
+        unode[uoff[rank[efirst[e]]] + epos[e]] = node;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 1
+// ---------------------------------------------------------------------------------------------
+struct RowStat {
+    float m;      // running max (raw activation units)
+    float s;      // running sum of 2^((x - m) * log2 e)
+    float bv;     // best value for argmax (NaN-aware)
+    int bi;       // its index
+};
+
+template <bool ARGMAX>
+__device__ __forceinline__ void fold(RowStat &st, float x, int idx) {
+    if (ARGMAX) {
+        // numpy.argmax: first maximum wins, NaN is maximal
+        const bool better = (x > st.bv) || ((x != x) && (st.bv == st.bv)) || (st.bi == 0x7fffffff);
+        if (better) { st.bv = x; st.bi = idx; }
+    }
+}
+
+template <bool ARGMAX>
+__device__ __forceinline__ void fold4(RowStat &st, const float4 &v, int idx) {
+    const float cm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (cm > st.m) {
+        st.s *= ex2_approx((st.m - cm) * LOG2E_HI);
+        st.m = cm;
+    }
+    const float c = -st.m * LOG2E_HI;
+    st.s += ex2_approx(fmaf(v.x, LOG2E_HI, c)) + ex2_approx(fmaf(v.y, LOG2E_HI, c)) +
+            ex2_approx(fmaf(v.z, LOG2E_HI, c)) + ex2_approx(fmaf(v.w, LOG2E_HI, c));
+    fold<ARGMAX>(st, v.x, idx);
+    fold<ARGMAX>(st, v.y, idx + 1);
+    fold<ARGMAX>(st, v.z, idx + 2);
+    fold<ARGMAX>(st, v.w, idx + 3);
+}
+
+template <bool ARGMAX>
+__device__ __forceinline__ void fold1(RowStat &st, float x, int idx) {
+    if (x > st.m) {
+        st.s *= ex2_approx((st.m - x) * LOG2E_HI);
+        st.m = x;
+    }
+    st.s += ex2_approx((x - st.m) * LOG2E_HI);
+    fold<ARGMAX>(st, x, idx);
+}
+
+// Scan one row with the whole warp.  Returns warp-uniform (max, log2 normaliser, argmax).
+template <bool ARGMAX, bool SOFTMAX>
+__device__ __forceinline__ void scan_row(const float *__restrict__ row, int V, int lane, float &row_max,
+                                         float &lse2, int &amax) {
+    RowStat st;
+    st.m = -INFINITY; st.s = 0.f; st.bv = -INFINITY; st.bi = 0x7fffffff;
+    // a row that is not 16-byte aligned starts with up to 3 scalar elements
+    const int mis = (int)((reinterpret_cast<uintptr_t>(row) >> 2) & 3);
+    const int head = mis ? min(V, 4 - mis) : 0;
+    if (lane < head) {
+        if (SOFTMAX) fold1<ARGMAX>(st, row[lane], lane);
+        else fold<ARGMAX>(st, row[lane], lane);
+    }
+    const float4 *row4 = reinterpret_cast<const float4 *>(row + head);
+    const int n4 = (V - head) >> 2;
+    int i = lane;
+    for (; i + 32 * (kUnroll - 1) < n4; i += 32 * kUnroll) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = __ldg(row4 + i + 32 * u);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (SOFTMAX) fold4<ARGMAX>(st, v[u], head + 4 * (i + 32 * u));
+            else {
+                fold<ARGMAX>(st, v[u].x, head + 4 * (i + 32 * u));
+                fold<ARGMAX>(st, v[u].y, head + 4 * (i + 32 * u) + 1);
+                fold<ARGMAX>(st, v[u].z, head + 4 * (i + 32 * u) + 2);
+                fold<ARGMAX>(st, v[u].w, head + 4 * (i + 32 * u) + 3);
+            }
+        }
+    }
+    for (; i < n4; i += 32) {
+        const float4 v = __ldg(row4 + i);
+        if (SOFTMAX) fold4<ARGMAX>(st, v, head + 4 * i);
+        else {
+            fold<ARGMAX>(st, v.x, head + 4 * i);
+            fold<ARGMAX>(st, v.y, head + 4 * i + 1);
+            fold<ARGMAX>(st, v.z, head + 4 * i + 2);
+            fold<ARGMAX>(st, v.w, head + 4 * i + 3);
+        }
+    }
+    const int tail0 = head + 4 * n4;
+    if (tail0 + lane < V) {
+        if (SOFTMAX) fold1<ARGMAX>(st, row[tail0 + lane], tail0 + lane);
+        else fold<ARGMAX>(st, row[tail0 + lane], tail0 + lane);
+    }
+    if (SOFTMAX) {
+        const float m = warp_max(st.m);
+        float s = st.s * ex2_approx((st.m - m) * LOG2E_HI);     // lanes that saw nothing: 0 * 2^-inf = 0
+        if (st.m == -INFINITY) s = 0.f;
+        s = warp_sum(s);
+        row_max = m;
+        lse2 = s;                                                // caller finishes with split_lse2(row_max, lse2)
+    }
+    if (ARGMAX) {
+        // lane order is not index order: reduce on (value, index) with "NaN beats all, then larger value,
+        // then smaller index"
+        float bv = st.bv; int bi = st.bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const bool onan = (ov != ov), mnan = (bv != bv);
+            bool take;
+            if (onan || mnan) take = onan && (!mnan || oi < bi);
+            else take = (ov > bv) || (ov == bv && oi < bi);
+            if (take) { bv = ov; bi = oi; }
+        }
+        amax = bi;
+    }
+}
+
+// log2 p = x*log2(e) - lse2 as a split value (integer hi, small lo); exact to ~1e-7 between symbols.
+// lse2 itself comes as an unevaluated sum (la + lb) so that its own rounding does not enter.
+__device__ __forceinline__ float2 split_log2p(float x, float la, float lb) {
+    const float ph = x * LOG2E_HI;
+    float pl = fmaf(x, LOG2E_HI, -ph);
+    pl = fmaf(x, LOG2E_LO, pl);
+    const float dd = ph - la;                                 // TwoSum(ph, -la)
+    const float bb = dd - ph;
+    const float err = (ph - (dd - bb)) + (-la - bb);
+    const float lo_full = (err + pl) - lb;
+    const float hi = rintf(dd);
+    const float lo = (dd - hi) + lo_full;
+    if (dd < SENT_TEST) return make_float2(SENT, 0.f);        // -inf activation: log 0 (a NaN still propagates)
+    return make_float2(hi, lo);
+}
+
+// log2 normaliser of a row, max*log2(e) + log2(sum), as an unevaluated float pair
+__device__ __forceinline__ void split_lse2(float m, float s, float &la, float &lb) {
+    const float mh = m * LOG2E_HI;
+    float ml = fmaf(m, LOG2E_HI, -mh);
+    ml = fmaf(m, LOG2E_LO, ml);
+    const float lg = log2f(s);
+    const float a = mh + lg;                                  // TwoSum(mh, lg)
+    const float bb = a - mh;
+    const float err = (mh - (a - bb)) + (lg - bb);
+    la = a;
+    lb = err + ml;
+}
+
+template <bool ARGMAX>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(ProblemDesc d, WsLayout w,
+                                                                          unsigned char *ws, int64_t *argmax_out,
+                                                                          int b_major) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * kWarpsPerCta;
+    const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
+    float *lse_out = reinterpret_cast<float *>(ws + w.off_lse);
+    float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
+    const long long frames = (long long)d.B * d.T;
+    for (long long f = warp_global; f < frames; f += warps_total) {
+        // walk frames in memory order of the activations
+        int b, t;
+        if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
+        else { t = (int)(f / d.B); b = (int)(f % d.B); }
+        const int Tb = utt[b].Tb;
+        const bool valid = t < Tb;
+        if (!valid && !ARGMAX) continue;
+        const float *row = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
+        float row_max = 0.f, lse2 = 0.f;
+        int amax = 0;
+        if (valid) scan_row<ARGMAX, true>(row, d.V, lane, row_max, lse2, amax);
+        else scan_row<ARGMAX, false>(row, d.V, lane, row_max, lse2, amax);
+        if (ARGMAX && lane == 0) argmax_out[(size_t)b * d.T + t] = amax;
+        if (!valid) continue;
+        float la, lb;
+        split_lse2(row_max, lse2, la, lb);
+        if (lane == 0) lse_out[(size_t)b * d.T + t] = la + lb;
+        // gather: column 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams (gram_ctc.py:24-32, :155)
+        const int Lb = utt[b].Lb;
+        float2 *lprow = lp_out + ((size_t)b * d.T + t) * w.W;
+        const int32_t *lab = d.labels + (size_t)b * d.Lmax;
+        const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)b * d.Lmax : nullptr;
+        const int ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
+        for (int c = lane; c < ncol; c += 32) {
+            int sym;
+            if (c == 0) sym = d.blank;
+            else if (c <= d.Lmax) sym = (c - 1 < Lb) ? lab[c - 1] : -1;
+            else sym = big[c - 1 - d.Lmax];
+            float2 v = make_float2(SENT, 0.f);
+            if (sym >= 0 && sym < d.V) v = split_log2p(__ldg(row + sym), la, lb);
+            lprow[c] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) argmax_kernel(const float *acts, int64_t stride_t,
+                                                                  int64_t stride_b, int B, int T, int V,
+                                                                  int64_t *argmax_out, int b_major) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * kWarpsPerCta;
+    const long long frames = (long long)B * T;
+    for (long long f = warp_global; f < frames; f += warps_total) {
+        int b, t;
+        if (b_major) { b = (int)(f / T); t = (int)(f % T); }
+        else { t = (int)(f / B); b = (int)(f % B); }
+        const float *row = acts + (int64_t)t * stride_t + (int64_t)b * stride_b;
+        float row_max, lse2;
+        int amax = 0;
+        scan_row<true, false>(row, V, lane, row_max, lse2, amax);
+        if (lane == 0) argmax_out[(size_t)b * T + t] = amax;
+    }
+}
+
+int grid_for_frames(long long frames) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long cap = (long long)sms * 8;       // 8 CTAs x 8 warps = 64 resident warps per SM
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    return (int)ctas;
+}
+
+}  // namespace
+
+cudaError_t launch_prep(const ProblemDesc &d, const WsLayout &w, void *ws, cudaStream_t stream) {
+    const int per = d.kind == 0 ? 1 : 2;
+    const size_t smem = sizeof(int) * 5 * (size_t)per * (size_t)(d.Lmax > 0 ? d.Lmax : 1);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    prep_kernel<<<d.B, 128, smem, stream>>>(d, w, static_cast<unsigned char *>(ws));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
+                                  cudaStream_t stream) {
+    const long long frames = (long long)d.B * d.T;
+    if (frames == 0) return cudaSuccess;
+    const int grid = grid_for_frames(frames);
+    const int b_major = d.stride_b > d.stride_t ? 1 : 0;
+    if (argmax_out)
+        softmax_gather_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, static_cast<unsigned char *>(ws),
+                                                                            argmax_out, b_major);
+    else
+        softmax_gather_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, static_cast<unsigned char *>(ws),
+                                                                             nullptr, b_major);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,
+                          int64_t *argmax_out, cudaStream_t stream) {
+    const long long frames = (long long)B * T;
+    if (frames == 0) return cudaSuccess;
+    const int grid = grid_for_frames(frames);
+    const int b_major = stride_b > stride_t ? 1 : 0;
+    argmax_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(acts, stride_t, stride_b, B, T, V, argmax_out, b_major);
+    return cudaGetLastError();
+}
+
+}  // namespace b200ctc

@@ -1,0 +1,104 @@
+/*
+ * b200ctc.h -- C ABI of the B200-native CTC / Gram-CTC loss (forward + backward).
+ *
+ * This is the drop-in boundary for the loss path of musyoku/chainer-speech-recognition:
+ *   asr/loss/gram_ctc.py:300      gram_ctc(xs, label_unigram, label_bigram, blank_symbol,
+ *                                          input_length, length_unigram, reduce)
+ *   run/ctc/cnn/train.py:191      F.connectionist_temporal_classification(y, t, blank, x_len, t_len)
+ *   run/ctc/cnn/train.py:232      xp.argmax(y.data, axis=2)            (greedy path)
+ * The reference's binding for it is Python (a chainer.Function subclass); the replacement binding
+ * is a ctypes stub that calls the functions below.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a CUDA *device* pointer unless the name ends in _host;
+ *   - the caller owns every buffer, including the workspace; the library keeps no device memory
+ *     and no global state besides a thread-local last-error string;
+ *   - every function returns a status code (B200CTC_OK == 0) and never throws;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
+ *     except the *_host convenience entry points;
+ *   - activations are float32, element (t, b, v) at acts[t*stride_t + b*stride_b + v] (vocabulary
+ *     stride is 1), which covers the reference's stacked (T,B,V) layout (gram_ctc.py:272-273) and
+ *     the decoder's (B,T,V) layout (asr/model/cnn.py:45-47) without a copy;
+ *   - labels are int32, (B, Lmax) row-major, padded with any value (the data layer pads with the
+ *     blank id, asr/data/processing.py:125-126); a Gram-CTC bigram id of -1 marks a bigram that is
+ *     not in the inventory (asr/data/processing.py:139-146, gram_ctc.py:94-98);
+ *   - input_lengths / label_lengths are int32 (B) or NULL for "full length" (gram_ctc.py:310-313).
+ */
+#ifndef B200CTC_H_
+#define B200CTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CTC_VERSION 100
+
+enum {
+    B200CTC_OK = 0,
+    B200CTC_INVALID_ARGUMENT = 1,   /* -> ValueError / TypeError in the Python shim              */
+    B200CTC_UNSUPPORTED = 2,        /* shape outside what the kernels are instantiated for       */
+    B200CTC_CUDA_ERROR = 3,         /* launch / runtime failure; message in b200ctc_last_error() */
+    B200CTC_WORKSPACE_TOO_SMALL = 4,
+    B200CTC_OUT_OF_MEMORY = 5       /* host entry points only -> torch.cuda.OutOfMemoryError     */
+};
+
+enum { B200CTC_KIND_CTC = 0, B200CTC_KIND_GRAM = 1 };
+
+/* flags for b200ctc_forward */
+enum {
+    B200CTC_FLAG_NONE = 0
+};
+
+int b200ctc_version(void);
+const char *b200ctc_last_error(void);
+
+/* Bytes of device workspace the forward/backward pair needs (replaces the reference's saved
+ * `yseq` + `prob_trans`, gram_ctc.py:273,276).  16-byte aligned base required. */
+int b200ctc_workspace_bytes(int kind, int B, int T, int V, int Lmax, size_t *bytes_out);
+
+/*
+ * Forward: replaces GramCTC.forward (gram_ctc.py:246-282) / Chainer's CTC forward.
+ *   loss_per_utt  (B) float32, out: -log P(labels_b | x_b); exactly 1e10 for an infeasible
+ *                 alignment (what the reference returns).
+ *   loss_sum      (1) float32, out: sum_b loss_per_utt[b] (the caller divides by the GLOBAL batch
+ *                 size for reduce='mean', gram_ctc.py:281, after its all-reduce across ranks).
+ *   argmax_out    (B,T) int64 or NULL: greedy indices over the raw activations, first maximum
+ *                 wins, NaN counts as maximal (numpy.argmax semantics, run/ctc/cnn/train.py:232).
+ *   bigrams       NULL for kind == B200CTC_KIND_CTC.
+ */
+int b200ctc_forward(int kind,
+                    const float *acts, int64_t stride_t, int64_t stride_b,
+                    const int32_t *labels, const int32_t *bigrams,
+                    const int32_t *input_lengths, const int32_t *label_lengths,
+                    int blank, int B, int T, int V, int Lmax,
+                    float *loss_per_utt, float *loss_sum, int64_t *argmax_out,
+                    void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+
+/*
+ * Backward: replaces GramCTC.backward (gram_ctc.py:284-297).  Must follow a b200ctc_forward on the
+ * same workspace and activations.
+ *   grad_loss        device pointer: 1 float (per_utterance == 0, reduce='mean') or (B) floats
+ *                    (per_utterance == 1, reduce='no'), the upstream gradient gy (gram_ctc.py:291-294).
+ *   scale            extra factor applied to every element: 1/B_global for 'mean' (:292), 1 for 'no'.
+ *   grad_out         float32, element (t,b,v) at grad_out[t*gstride_t + b*gstride_b + v]; every one of
+ *                    the B*T*V elements is written, zeros for t >= input_lengths[b] (:296).
+ */
+int b200ctc_backward(int kind,
+                     const float *acts, int64_t stride_t, int64_t stride_b,
+                     const int32_t *labels, const int32_t *bigrams,
+                     int blank, int B, int T, int V, int Lmax,
+                     const float *grad_loss, int per_utterance, float scale,
+                     float *grad_out, int64_t gstride_t, int64_t gstride_b,
+                     const void *workspace, size_t workspace_bytes, void *stream);
+
+/* Greedy path alone (run/ctc/cnn/train.py:232 and its 9 sibling call sites): out (B,T) int64. */
+int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b,
+                          int B, int T, int V, int64_t *argmax_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CTC_H_ */

@@ -1,0 +1,114 @@
+"""Run the reference's own ``asr/loss/gram_ctc.py`` UNMODIFIED on its NumPy path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Works only where ``/root/reference`` is
+mounted (the build container); the GPU box never has it, so nothing under ``-m gpu`` tests,
+``smoke()`` or ``bench.py`` calls this.  It exists to (1) pin oracle/lattice.py and
+oracle/ctc_oracle.c and (2) generate the committed golden vectors (tests/golden/generate_golden.py).
+
+The reference file needs only a handful of Chainer symbols:
+``chainer.is_debug`` (gram_ctc.py:255), ``chainer.cuda.get_array_module`` (:247,285,311),
+``chainer.function.Function`` (:219), ``chainer.utils.force_array`` (:281),
+``chainer.utils.type_check`` (import only) and ``chainer.variable.Variable`` (:312-313).
+Chainer and CuPy are not installable here (no network), so a tiny stand-in for exactly those
+symbols is registered in ``sys.modules`` before the file is loaded with importlib.
+"""
+import collections
+import collections.abc
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("B200CTC_REFERENCE_ROOT", "/root/reference")
+_REF_FILE = os.path.join(REFERENCE_ROOT, "asr", "loss", "gram_ctc.py")
+_module = None
+
+
+def available():
+    return os.path.isfile(_REF_FILE)
+
+
+def _install_chainer_stub():
+    if "chainer" in sys.modules and getattr(sys.modules["chainer"], "_b200ctc_stub", False):
+        return
+    if not hasattr(collections, "Sequence"):          # gram_ctc.py:301 (removed in Python 3.10)
+        collections.Sequence = collections.abc.Sequence
+
+    class Variable(object):
+        def __init__(self, data):
+            self.data = data
+
+        @property
+        def shape(self):
+            return self.data.shape
+
+    class Function(object):
+        def __call__(self, *inputs):
+            arrays = tuple(i.data if isinstance(i, Variable) else np.asarray(i) for i in inputs)
+            return Variable(self.forward(arrays)[0])
+
+    chainer = types.ModuleType("chainer")
+    chainer._b200ctc_stub = True
+    chainer.is_debug = lambda: False
+    cuda = types.ModuleType("chainer.cuda")
+    cuda.get_array_module = lambda *a: np
+    cuda.cupy = None
+    function = types.ModuleType("chainer.function")
+    function.Function = Function
+    utils = types.ModuleType("chainer.utils")
+    utils.force_array = lambda x, dtype=None: np.asarray(x)
+    type_check = types.ModuleType("chainer.utils.type_check")
+    utils.type_check = type_check
+    variable = types.ModuleType("chainer.variable")
+    variable.Variable = Variable
+    chainer.cuda, chainer.function, chainer.utils, chainer.variable = cuda, function, utils, variable
+    for name, mod in (("chainer", chainer), ("chainer.cuda", cuda), ("chainer.function", function),
+                      ("chainer.utils", utils), ("chainer.utils.type_check", type_check),
+                      ("chainer.variable", variable)):
+        sys.modules[name] = mod
+
+
+def load():
+    """Return the reference module object (cached)."""
+    global _module
+    if _module is None:
+        if not available():
+            raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
+        _install_chainer_stub()
+        spec = importlib.util.spec_from_file_location("_ref_gram_ctc", _REF_FILE)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _module = mod
+    return _module
+
+
+def run_gram_ctc(x_tbv, unigram, bigram, input_length, label_length, blank=0, reduce="no", gy=None):
+    """Reference forward+backward.  x_tbv: (T,B,V) float32.  Returns (loss, grad (T,B,V), prob_trans).
+
+    Inputs are passed in the Function's own order (gram_ctc.py:248-253).  A fresh GramCTC object is
+    used per call because backward mutates the saved softmax in place (gram_ctc.py:290-296).
+    """
+    ref = load()
+    x_tbv = np.ascontiguousarray(x_tbv, dtype=np.float32)
+    T, B, V = x_tbv.shape
+    xs = tuple(x_tbv[t].copy() for t in range(T))
+    f = ref.GramCTC(int(blank), reduce)
+    inputs = (np.asarray(input_length, np.int32), np.asarray(label_length, np.int32),
+              np.asarray(unigram, np.int32), np.asarray(bigram, np.int32)) + xs
+    loss = np.array(f.forward(inputs)[0], copy=True)
+    prob_trans = np.array(f.prob_trans, copy=True)
+    if gy is None:
+        gy = np.ones((B,), np.float32) if reduce == "no" else np.float32(1.0)
+    grads = f.backward(inputs, (gy,))
+    assert all(g is None for g in grads[:4])          # gram_ctc.py:297
+    grad = np.stack(grads[4:]).astype(np.float32)
+    return loss, grad, prob_trans
+
+
+def run_ctc(x_tbv, labels, input_length, label_length, blank=0, reduce="no", gy=None):
+    """Plain CTC through the reference: every bigram node dead (gram_ctc.py:95-98)."""
+    labels = np.asarray(labels, np.int32)
+    return run_gram_ctc(x_tbv, labels, np.full_like(labels, -1), input_length, label_length,
+                        blank=blank, reduce=reduce, gy=gy)

@@ -1,0 +1,140 @@
+"""-m gpu: the CUDA path (through the Python shim -> ctypes -> C ABI) against the float64 oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: loss 1e-5 relative, gradient 1e-5
+absolute, greedy indices bit-exact.
+"""
+import numpy as np
+import pytest
+
+from util import run_cuda, run_oracle, assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def synth():
+    import importlib
+    return importlib.import_module("chainer-speech-recognition_b200.synth")
+
+
+CTC_SHAPES = [
+    # B, T, V, L
+    (3, 12, 9, 3),
+    (4, 50, 40, 8),
+    (2, 33, 37, 5),        # V not a multiple of 4: unaligned rows
+    (5, 64, 130, 17),
+    (2, 7, 5, 1),          # Lmax = 1 crashes the reference; must simply work here
+    (8, 200, 3500, 40),    # BASELINE configs[0]
+    (2, 300, 64, 100),     # K = 8 slots per lane
+    (2, 500, 32, 150),     # K = 12
+    (1, 900, 16, 250),     # K = 16
+    (1, 1000, 16, 380),    # K = 24
+]
+
+
+@pytest.mark.parametrize("shape", CTC_SHAPES)
+@pytest.mark.parametrize("trained", [False, True])
+def test_ctc_matches_oracle(pkg, shape, trained):
+    B, T, V, L = shape
+    prob = synth().ctc_problem(B, T, V, L, seed=1, trained=trained)
+    loss, grad, _ = run_cuda(pkg, prob, "ctc")
+    loss_ref, grad_ref, _ = run_oracle(prob, "ctc")
+    assert_parity(loss, grad, loss_ref, grad_ref, "ctc %r" % (shape,))
+
+
+GRAM_SHAPES = [
+    (3, 12, 9, 3),
+    (4, 50, 40, 8),
+    (2, 33, 37, 5),
+    (2, 9, 11, 1),
+    (4, 120, 300, 30),
+    (2, 400, 200, 100),    # K = 12
+    (1, 700, 150, 190),    # K = 18
+    (1, 900, 150, 250),    # K = 24
+    (1, 1200, 150, 380),   # K = 36
+]
+
+
+@pytest.mark.parametrize("shape", GRAM_SHAPES)
+@pytest.mark.parametrize("trained", [False, True])
+def test_gram_ctc_matches_oracle(pkg, shape, trained):
+    B, T, V, L = shape
+    prob = synth().gram_problem(B, T, V, L, seed=2, trained=trained, n_unigram=max(3, min(119, V // 3)))
+    loss, grad, _ = run_cuda(pkg, prob, "gram")
+    loss_ref, grad_ref, _ = run_oracle(prob, "gram")
+    assert_parity(loss, grad, loss_ref, grad_ref, "gram %r" % (shape,))
+
+
+def test_reduce_mean_and_upstream_gradient(pkg):
+    prob = synth().ctc_problem(4, 40, 30, 6, seed=3)
+    loss_ref, grad_ref, _ = run_oracle(prob, "ctc")
+    loss, grad, _ = run_cuda(pkg, prob, "ctc", reduce="mean", gy=2.5)
+    assert abs(loss - loss_ref.mean()) <= 1e-5 * abs(loss_ref.mean())
+    assert np.abs(grad - grad_ref * (2.5 / 4)).max() <= 1e-5            # gram_ctc.py:292
+    gy = np.array([1.0, -2.0, 0.5, 3.0], np.float32)
+    loss, grad, _ = run_cuda(pkg, prob, "ctc", reduce="no", gy=gy)
+    assert np.abs(grad - grad_ref * gy[None, :, None]).max() <= 3e-5    # gram_ctc.py:294 (|gy| up to 3)
+
+
+@pytest.mark.parametrize("kind", ["ctc", "gram"])
+def test_layouts_agree_bitwise(pkg, kind):
+    s = synth()
+    prob = s.ctc_problem(3, 30, 24, 5, seed=4) if kind == "ctc" else s.gram_problem(3, 30, 24, 5, seed=4, n_unigram=8)
+    base = run_cuda(pkg, prob, kind)
+    as_list = run_cuda(pkg, prob, kind, as_list=True)
+    btv = run_cuda(pkg, prob, kind, batch_first=True)
+    for other in (as_list, btv):
+        assert np.array_equal(base[0], other[0])
+        assert np.array_equal(base[1], other[1])
+
+
+def test_default_lengths_are_full(pkg):
+    prob = synth().ctc_problem(3, 25, 12, 4, seed=5, variable=False)
+    a = run_cuda(pkg, prob, "ctc")
+    prob2 = dict(prob, input_length=None, label_length=None)
+    b = run_cuda(pkg, prob2, "ctc")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_padded_frames_get_exact_zero_and_batch_independence(pkg):
+    prob = synth().ctc_problem(4, 60, 20, 6, seed=6)
+    loss, grad, _ = run_cuda(pkg, prob, "ctc")
+    for b in range(4):
+        Tb = int(prob["input_length"][b])
+        assert not grad[Tb:, b].any()                                   # gram_ctc.py:296
+        solo = {k: (v[:, b:b + 1] if k == "x" else (v[b:b + 1] if isinstance(v, np.ndarray) else v))
+                for k, v in prob.items()}
+        l1, g1, _ = run_cuda(pkg, solo, "ctc")
+        assert np.array_equal(l1[0], loss[b]) and np.array_equal(g1[:, 0], grad[:, b])   # bit-identical
+
+
+def test_infeasible_alignment_and_empty_label(pkg):
+    rs = np.random.RandomState(7)
+    x = rs.randn(5, 3, 8).astype(np.float32)
+    prob = {"x": x, "labels": np.array([[1, 1, 1, 1], [1, 2, 3, 0], [0, 0, 0, 0]], np.int32),
+            "input_length": np.array([5, 5, 5], np.int32), "label_length": np.array([4, 3, 0], np.int32), "blank": 0}
+    loss, grad, _ = run_cuda(pkg, prob, "ctc")
+    loss_ref, grad_ref, _ = run_oracle(prob, "ctc")
+    assert loss[0] == 1e10                                              # reference quirk: exactly 1e10
+    assert np.isfinite(grad).all()
+    assert_parity(loss[1:], grad[:, 1:], loss_ref[1:], grad_ref[:, 1:])
+    assert np.abs(grad[:, 0] - grad_ref[:, 0]).max() <= 1e-5
+
+
+def test_greedy_argmax_bit_exact(pkg):
+    import torch
+    rs = np.random.RandomState(8)
+    y = rs.randn(6, 70, 3500).astype(np.float32)                        # (B,T,V), asr/model/cnn.py:45-47
+    y[0, 3, 10] = y[0, 3, 200] = 9.0                                    # tie -> first index
+    y[1, 5, :] = -np.inf
+    y[2, 7, 100] = np.nan; y[2, 7, 50] = np.nan                         # NaN is maximal, first one wins
+    y[3, 9, 3499] = 50.0
+    out = pkg.greedy_argmax(torch.tensor(y, device="cuda:0")).cpu().numpy()
+    assert out.dtype == np.int64
+    assert np.array_equal(out, np.argmax(y, axis=2))
+    y2 = rs.randn(3, 11, 37).astype(np.float32)                         # unaligned rows
+    out2 = pkg.greedy_argmax(torch.tensor(y2, device="cuda:0")).cpu().numpy()
+    assert np.array_equal(out2, np.argmax(y2, axis=2))
+    # the loss kernel's fused argmax agrees with the standalone one
+    prob = synth().ctc_problem(4, 50, 40, 8, seed=1)
+    _, _, am = run_cuda(pkg, prob, "ctc", want_argmax=True)
+    assert np.array_equal(am, np.argmax(prob["x"], axis=2).T)
