@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- CTC loss forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (loss forward + gradient) over one batch of synthetic
+input: BASELINE.json configs[1], CTC B=64, T=800, V=3500, label length <= 80, variable lengths,
+PER GPU (weak scaling: N GPUs = configs[3]'s B=512 at N=8, batch-sharded, one scalar all-reduce).
+
+Printed JSON (rank 0, one line):
+  value     padded utterance-frames/s = N*B*T*K / max-over-ranks device time, inputs resident in HBM
+  e2e       the same through the public API with HOST (pinned) buffers: activations H2D, gradient and
+            loss D2H inside the timed region
+  roofline  dominant kernel (the fused gradient kernel: 2/3 of the algorithmic bytes) against the
+            measured HBM copy bandwidth in MEASURED_PEAKS.json; whole-step figure in "step_roofline"
+  cpu_baseline  the oracle's C port (oracle/ctc_oracle.c, OpenMP) on this box's host cores, rank 0, N=1
+
+--impl reference times the CPU implementation alone (the reference itself is Python/Chainer and
+cannot travel to the GPU box, so this is the oracle port -- kind "port").
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = {"B": 64, "T": 800, "V": 3500, "L": 80}
+METRIC = "CTC fwd+bwd utterance-frames/sec at B=64,T=800,V=3500"
+UNIT = "frames/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def synth():
+    return importlib.import_module("chainer-speech-recognition_b200.synth")
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons sampled while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load": keep the upper half of the samples (idle samples before/after the region read low)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(V, in_len, B, T):
+    """read activations once (softmax), once more (gradient), write the gradient once."""
+    valid = int(np.sum(in_len))
+    k1 = 4 * V * valid                       # kernel 1: one read of the valid frames
+    k3 = 4 * V * valid + 4 * V * B * T       # kernel 3: re-read valid frames + write every frame
+    return k1, k3
+
+
+def cpu_baseline(prob, sample_b, threads, repeats=2):
+    """Oracle C port, forward+backward, on the first `sample_b` utterances of the workload."""
+    from oracle import c_oracle
+    x = np.ascontiguousarray(prob["x"][:, :sample_b])
+    args = (0, x, prob["labels"][:sample_b], None, prob["input_length"][:sample_b],
+            prob["label_length"][:sample_b], prob["blank"])
+    c_oracle.run(*args, nthreads=threads)                      # warm-up: page in, spin up the thread pool
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        c_oracle.run(*args, nthreads=threads)
+        best = min(best, time.perf_counter() - t0)
+    T = x.shape[0]
+    return sample_b * T / best, best
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU implementation alone, all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    threads = c_oracle.max_threads()
+    W = WORKLOAD
+    sample_b = 16
+    prob = synth().ctc_problem(sample_b, W["T"], W["V"], W["L"], seed=0)
+    xargs = (0, prob["x"], prob["labels"], None, prob["input_length"], prob["label_length"], prob["blank"])
+    for _ in range(max(args.warmup, 1)):
+        c_oracle.run(*xargs, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.run(*xargs, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = sample_b * W["T"] * args.steps / dt
+    sample = "oracle C port (oracle/ctc_oracle.c, float64, OpenMP x%d), %d of the 64 utterances per step" % (threads, sample_b)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CTC fwd+bwd B=64,T=800,V=3500,L<=80, variable lengths (BASELINE configs[1]); "
+                               "CPU arm runs a %d-utterance sample per step" % sample_b},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import b200ctc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    W = WORKLOAD
+    B, T, V, L = W["B"], W["T"], W["V"], W["L"]
+    prob = synth().ctc_problem(B, T, V, L, seed=rank)            # each rank owns its own shard of utterances
+    x = torch.tensor(prob["x"], device=dev).requires_grad_(True)  # (T,B,V), the reference's stacked layout
+    labels = torch.tensor(prob["labels"], device=dev)
+    in_len = torch.tensor(prob["input_length"], device=dev)
+    lab_len = torch.tensor(prob["label_length"], device=dev)
+    kw = {"group": group} if group is not None else {}
+
+    def step():
+        x.grad = None
+        loss = b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean", **kw)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region: device time, CUDA events on the stream the kernels are launched on ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        x.grad = None
+        ev[k][0].record()
+        loss = b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean", **kw)
+        ev[k][1].record()
+        loss.backward()
+        ev[k][2].record()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    fwd_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
+    bwd_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]))
+    t = torch.tensor([elapsed_ms, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, fwd_ms, bwd_ms = [float(v) for v in t.tolist()]
+    loss_value = float(loss.item())
+
+    # ---- end to end: host (pinned) buffers, H2D + D2H inside the timed region ----
+    x_host = torch.from_numpy(prob["x"]).pin_memory()
+    g_host = torch.empty_like(x_host).pin_memory()
+    x_dev = torch.empty_like(x_host, device=dev).requires_grad_(True)
+
+    def e2e_step():
+        x_dev.grad = None
+        with torch.no_grad():
+            x_dev.copy_(x_host, non_blocking=True)
+        l = b200ctc.connectionist_temporal_classification(x_dev, labels, 0, in_len, lab_len, reduce="mean", **kw)
+        l.backward()
+        g_host.copy_(x_dev.grad, non_blocking=True)
+        return float(l.item())                                    # D2H read of the loss: synchronises
+
+    e2e_step()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    s1.record()
+    barrier()
+    t2 = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = measured_peak()
+    k1_bytes, k3_bytes = algorithmic_bytes(V, prob["input_length"], B, T)
+    step_bytes = k1_bytes + k3_bytes
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B * T * args.steps / (elapsed_ms * 1e-3)
+    achieved = k3_bytes / (bwd_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CTC fwd+bwd B=64,T=800,V=3500,L<=80 per GPU, variable lengths "
+                               "(BASELINE configs[1]; N GPUs = batch-sharded configs[3])",
+                   "global_batch": world * B, "parallelism": "batch-sharded dp%d, 1 scalar all-reduce" % world,
+                   "layout": "(T,B,V) float32", "l2": "inputs (717 MB) and outputs exceed the 126 MB L2; no flush needed",
+                   "valid_frames_per_step": int(np.sum(prob["input_length"])), "loss": loss_value},
+        "valid_frames_per_s": world * int(np.sum(prob["input_length"])) * args.steps / (elapsed_ms * 1e-3),
+        "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+        "roofline": {"bound": "hbm", "kernel": "gradient_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": k3_bytes},
+        "step_roofline": {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                          "algorithmic_bytes_per_step": step_bytes},
+        "e2e": {"value": world * B * T * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4),
+                "ms_per_step": e2e_ms / args.e2e_steps},
+        "gpu_launches": 5 * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+        threads = c_oracle.max_threads()
+        sample_b = 16
+        v, secs = cpu_baseline(prob, sample_b, threads)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": "oracle C port (float64, OpenMP), first %d of the 64 utterances, best of 2 "
+                                         "(%.2f s per pass)" % (sample_b, secs)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,8 @@ int validate(int kind, int B, int T, int V, int Lmax, int blank, bool need_blank
     if (kind != B200CTC_KIND_CTC && kind != B200CTC_KIND_GRAM) return fail(B200CTC_INVALID_ARGUMENT, "kind must be 0 (CTC) or 1 (Gram-CTC)%s");
     if (B < 0 || T < 0 || V <= 0 || Lmax < 0)
         return fail(B200CTC_INVALID_ARGUMENT, "negative or empty dimension%s (B=%lld ...)", "", B);
+    if ((long long)B * (long long)T >= (1ll << 31))
+        return fail(B200CTC_UNSUPPORTED, "B*T = %s%lld frames exceeds 2^31", "", (long long)B * T);
     if (need_blank && (blank < 0 || blank >= V))
         return fail(B200CTC_INVALID_ARGUMENT, "blank symbol %s%lld outside [0, V=%lld)", "", blank, V);
     const int Nmax = (kind == 0 ? 2 : 3) * Lmax + 1;
@@ -83,8 +85,9 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
     d.input_lengths = input_lengths; d.label_lengths = label_lengths;
 
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    if ((rc = check_cuda(launch_prep(d, w, ws, stream), "prep kernel"))) return rc;
+    if ((rc = check_cuda(cudaMemsetAsync(ws + w.off_hdr, 0, sizeof(WsHeader), stream), "workspace header memset"))) return rc;
     if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, stream), "softmax/gather kernel"))) return rc;
+    if ((rc = check_cuda(launch_prep(d, w, ws, stream), "prep kernel"))) return rc;
 
     LatticeParams lp;
     lp.labels = labels; lp.bigrams = d.bigrams;

@@ -23,11 +23,21 @@ struct UttInfo {
     int Tb;        // clamped input length
     int Lb;        // clamped label length
     int Nb;        // lattice nodes: 2*Lb+1 (CTC) or 3*Lb+1 (Gram-CTC)
-    int Ub;        // number of distinct symbols among the non-blank-type nodes
+    int Ub;        // number of distinct symbols the lattice can emit (blank included), sorted by id
     float Ph;      // log2 P, integer part   (+1e30 when the alignment is infeasible)
     float Pl;      // log2 P, fractional part
     float loss;    // -ln P, or 1e10 when infeasible (reference quirk)
     int flags;     // bit0: lengths were out of range and got clamped; bit1: infeasible
+    int ublank;    // position of the blank id in the sorted distinct-symbol list
+    int pad;
+};
+
+// Header at the start of the workspace: work-queue tickets for the row-streaming kernels.
+struct WsHeader {
+    unsigned int k1_ticket;    // next frame for the softmax/gather kernel
+    unsigned int k3_ticket;    // next frame for the gradient kernel
+    unsigned int k3_done;      // gradient warps that ran out of work (last one re-arms the queue)
+    unsigned int pad;
 };
 
 // Workspace carve-up (all offsets in bytes from a 16-byte aligned base).
@@ -36,7 +46,9 @@ struct WsLayout {
     int W;         // emission row width: [blank, label_0..label_{Lmax-1} (, bigram_0..)] padded to even
     int Nmax;      // lattice nodes for Lmax
     int Np;        // Nmax padded to a multiple of 4
-    size_t off_utt, off_lse, off_lp, off_fv, off_gam, off_usym, off_uoff, off_unode, total;
+    int Umax;      // upper bound on distinct symbols per utterance (blank + every non-blank-type node)
+    int nwords;    // ceil(V / 32): words of the per-utterance "is a lattice symbol" bitmap
+    size_t off_hdr, off_utt, off_lse, off_lp, off_fv, off_gam, off_usym, off_uoff, off_unode, off_bm, off_pc, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -48,8 +60,11 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     w.W = (width + 1) & ~1;
     w.Nmax = (kind == 0 ? 2 : 3) * Lmax + 1;
     w.Np = (w.Nmax + 3) & ~3;
+    w.Umax = w.Nmax - Lmax;                 // blank + (per-1)*Lmax entries
+    w.nwords = (V + 31) / 32;
     size_t o = 0;
     const size_t BT = (size_t)B * (size_t)T;
+    w.off_hdr = o;   o = align_up(o + sizeof(WsHeader), 256);
     w.off_utt = o;   o = align_up(o + sizeof(UttInfo) * (size_t)B, 256);
     w.off_lse = o;   o = align_up(o + sizeof(float) * BT, 256);
     w.off_lp = o;    o = align_up(o + sizeof(float2) * BT * w.W, 256);
@@ -58,6 +73,8 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     w.off_usym = o;  o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
     w.off_uoff = o;  o = align_up(o + sizeof(int) * (size_t)B * (w.Nmax + 1), 256);
     w.off_unode = o; o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
+    w.off_bm = o;    o = align_up(o + sizeof(unsigned) * (size_t)B * w.nwords, 256);
+    w.off_pc = o;    o = align_up(o + sizeof(int) * (size_t)B * w.nwords, 256);
     w.total = o;
     return w;
 }

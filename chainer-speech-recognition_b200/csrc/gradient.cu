@@ -8,10 +8,12 @@
 // recomputed from the saved per-frame normaliser, and the <= L+1 non-zero posteriors of a frame are
 // merged from gamma on the fly.  One read + one write of (T,B,V), nothing else of that size.
 //
-// One warp per frame; 128-bit streaming loads/stores; the few label columns are patched after the
-// row has been written (same warp, ordered by __syncwarp).
+// One warp per frame, frames handed out by a ticket counter; 128-bit streaming loads/stores.  Which
+// columns carry a posterior is looked up in a per-utterance V-bit bitmap (1 word per 32 columns, L1
+// resident), so the correction happens in registers and every gradient element is written once.
 #include "common.cuh"
 #include "kernels.h"
+#include "row_ring.cuh"
 
 namespace b200ctc {
 
@@ -32,26 +34,50 @@ __device__ __forceinline__ void zero_row(float *__restrict__ g, int V, int lane)
     if (tail0 + lane < V) g[tail0 + lane] = 0.f;
 }
 
+// softmax * sc for 4 consecutive columns, minus the (pre-scaled) posterior of the columns the lattice emits
+__device__ __forceinline__ float4 grad4(const float4 &v, float c, float sc, unsigned word, int bit0, int pc,
+                                        const float *__restrict__ post_sm) {
+    float4 o;
+    o.x = ex2_approx(fmaf(v.x, LOG2E_HI, c)) * sc;
+    o.y = ex2_approx(fmaf(v.y, LOG2E_HI, c)) * sc;
+    o.z = ex2_approx(fmaf(v.z, LOG2E_HI, c)) * sc;
+    o.w = ex2_approx(fmaf(v.w, LOG2E_HI, c)) * sc;
+    const unsigned nib = (word >> bit0) & 0xfu;
+    if (nib) {                                              // ~2% of the columns: label/blank ids of this utterance
+        int slot = pc + __popc(word & ((1u << bit0) - 1u));
+        if (nib & 1u) o.x -= post_sm[slot++];
+        if (nib & 2u) o.y -= post_sm[slot++];
+        if (nib & 4u) o.z -= post_sm[slot++];
+        if (nib & 8u) o.w -= post_sm[slot];
+    }
+    return o;
+}
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams gp, WsLayout w,
-                                                                     const unsigned char *ws, int b_major,
+                                                                     unsigned char *ws, int b_major,
                                                                      int sm_floats_per_warp) {
     extern __shared__ float sm_all[];
     const ProblemDesc &d = gp.d;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;        // [Np] exp2(gamma) of this frame
-    const int warp_global = blockIdx.x * kWarpsPerCta + warp;
-    const int warps_total = gridDim.x * kWarpsPerCta;
+    float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;        // [Np]   2^gamma of this frame
+    float *post_sm = e_sm + w.Np;                                    // [Umax] merged posterior * sc, by sorted id
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
     const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
     const float *gam_all = reinterpret_cast<const float *>(ws + w.off_gam);
-    const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
     const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
     const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
+    const unsigned *bm_all = reinterpret_cast<const unsigned *>(ws + w.off_bm);
+    const int *pc_all = reinterpret_cast<const int *>(ws + w.off_pc);
     const int per = d.kind == 0 ? 2 : 3;
-    const long long frames = (long long)d.B * d.T;
+    const unsigned frames = (unsigned)d.B * (unsigned)d.T;
 
-    for (long long f = warp_global; f < frames; f += warps_total) {
+    for (;;) {
+        unsigned f = 0;
+        if (lane == 0) f = atomicAdd(&hdr->k3_ticket, 1u);
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (f >= frames) break;
         int b, t;
         if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
         else { t = (int)(f / d.B); b = (int)(f % d.B); }
@@ -65,7 +91,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         const float sc = gy * gp.scale;                                      // :291-294
         const float c = -lse2;
 
-        // ---- posteriors of this frame: e[j] = 2^gamma[t][j] ----
+        // ---- posteriors of this frame: e[j] = 2^gamma[t][j], merged per emitted id (:180-217) ----
         const float *gam = gam_all + ((size_t)b * d.T + t) * w.Np;
         float blank_part = 0.f;
         for (int j = lane; j < ui.Nb; j += 32) {
@@ -75,70 +101,208 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         }
         blank_part = warp_sum(blank_part);
         __syncwarp();
+        const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
+        const int *unode = unode_all + (size_t)b * w.Nmax;
+        for (int u = lane; u < ui.Ub; u += 32) {
+            const int n0 = __ldg(uoff + u), n1 = __ldg(uoff + u + 1);
+            float post = (u == ui.ublank) ? blank_part : 0.f;
+            for (int n = n0; n < n1; ++n) {
+                const int j = __ldg(unode + n);
+                if (j < ui.Nb) post += e_sm[j];
+            }
+            post_sm[u] = post * sc;
+        }
+        __syncwarp();
 
-        // ---- stream the row: grad = softmax * sc ----
-        const int mis = (int)((reinterpret_cast<uintptr_t>(row) >> 2) & 3);
-        const int gmis = (int)((reinterpret_cast<uintptr_t>(grow) >> 2) & 3);
-        if (mis == gmis) {
-            const int head = mis ? min(d.V, 4 - mis) : 0;
-            if (lane < head) grow[lane] = ex2_approx(fmaf(row[lane], LOG2E_HI, c)) * sc;
-            const float4 *row4 = reinterpret_cast<const float4 *>(row + head);
-            float4 *g4 = reinterpret_cast<float4 *>(grow + head);
-            const int n4 = (d.V - head) >> 2;
+        // ---- stream the row: grad = (softmax - posterior) * sc, one read and one write ----
+        const unsigned *bm = bm_all + (size_t)b * w.nwords;
+        const int *pc = pc_all + (size_t)b * w.nwords;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(grow)) & 15) == 0;
+        if (aligned) {
+            const float4 *row4 = reinterpret_cast<const float4 *>(row);
+            float4 *g4 = reinterpret_cast<float4 *>(grow);
+            const int n4 = d.V >> 2;
             int i = lane;
             for (; i + 32 * (kUnroll - 1) < n4; i += 32 * kUnroll) {
                 float4 v[kUnroll];
+                unsigned wd[kUnroll];
+                int pcw[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) v[u] = ldg_stream4(row4 + i + 32 * u);
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    float4 o;
-                    o.x = ex2_approx(fmaf(v[u].x, LOG2E_HI, c)) * sc;
-                    o.y = ex2_approx(fmaf(v[u].y, LOG2E_HI, c)) * sc;
-                    o.z = ex2_approx(fmaf(v[u].z, LOG2E_HI, c)) * sc;
-                    o.w = ex2_approx(fmaf(v[u].w, LOG2E_HI, c)) * sc;
-                    stg_stream4(g4 + i + 32 * u, o);
+                    const int wi = (i + 32 * u) >> 3;                        // column 4*(i+32u) lives in word col/32
+                    wd[u] = __ldg(bm + wi);
+                    pcw[u] = __ldg(pc + wi);
                 }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    stg_stream4(g4 + i + 32 * u, grad4(v[u], c, sc, wd[u], ((i + 32 * u) & 7) << 2, pcw[u], post_sm));
             }
             for (; i < n4; i += 32) {
                 const float4 v = ldg_stream4(row4 + i);
-                float4 o;
-                o.x = ex2_approx(fmaf(v.x, LOG2E_HI, c)) * sc;
-                o.y = ex2_approx(fmaf(v.y, LOG2E_HI, c)) * sc;
-                o.z = ex2_approx(fmaf(v.z, LOG2E_HI, c)) * sc;
-                o.w = ex2_approx(fmaf(v.w, LOG2E_HI, c)) * sc;
-                stg_stream4(g4 + i, o);
+                const int wi = i >> 3;
+                stg_stream4(g4 + i, grad4(v, c, sc, __ldg(bm + wi), (i & 7) << 2, __ldg(pc + wi), post_sm));
             }
-            const int tail0 = head + 4 * n4;
-            if (tail0 + lane < d.V) grow[tail0 + lane] = ex2_approx(fmaf(row[tail0 + lane], LOG2E_HI, c)) * sc;
-        } else {
-            for (int k = lane; k < d.V; k += 32) grow[k] = ex2_approx(fmaf(row[k], LOG2E_HI, c)) * sc;
-        }
-        __syncwarp();
-
-        // ---- patch the label columns: subtract the merged posterior (:180-217, :290) ----
-        if (lane == 0) {
-            const float p = ex2_approx(fmaf(__ldg(row + d.blank), LOG2E_HI, c));
-            grow[d.blank] = (p - blank_part) * sc;
-        }
-        __syncwarp();
-        const int *usym = usym_all + (size_t)b * w.Nmax;
-        const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
-        const int *unode = unode_all + (size_t)b * w.Nmax;
-        for (int u = lane; u < ui.Ub; u += 32) {
-            const int sym = usym[u];
-            const int n0 = uoff[u], n1 = uoff[u + 1];
-            float post = 0.f;
-            for (int n = n0; n < n1; ++n) {
-                const int j = unode[n];
-                if (j < ui.Nb) post += e_sm[j];
+            for (int k = 4 * n4 + lane; k < d.V; k += 32) {
+                float o = ex2_approx(fmaf(row[k], LOG2E_HI, c)) * sc;
+                const unsigned word = __ldg(bm + (k >> 5));
+                if ((word >> (k & 31)) & 1u) o -= post_sm[__ldg(pc + (k >> 5)) + __popc(word & ((1u << (k & 31)) - 1u))];
+                grow[k] = o;
             }
-            if (sym == d.blank) post += blank_part;               // a label equal to the blank id
-            const float p = ex2_approx(fmaf(__ldg(row + sym), LOG2E_HI, c));
-            grow[sym] = (p - post) * sc;
+        } else {                                                             // unaligned rows (V % 4 != 0 ...)
+            for (int k = lane; k < d.V; k += 32) {
+                float o = ex2_approx(fmaf(row[k], LOG2E_HI, c)) * sc;
+                const unsigned word = __ldg(bm + (k >> 5));
+                if ((word >> (k & 31)) & 1u) o -= post_sm[__ldg(pc + (k >> 5)) + __popc(word & ((1u << (k & 31)) - 1u))];
+                grow[k] = o;
+            }
         }
         __syncwarp();
     }
+    // re-arm the queue for a possible second backward over the same workspace
+    if (lane == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&hdr->k3_done, 1u) + 1u;
+        if (done == gridDim.x * kWarpsPerCta) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 3, TMA row-ring variant (see row_ring.cuh).  The producer bulk-copies the activation row AND
+// the frame's gamma row into a ring slot; a consumer warp turns the row into the gradient in place
+// (softmax * sc, then subtracts the merged posteriors at the <= L+1 label columns -- a plain scatter in
+// shared memory, no bitmap needed) and hands it back to the TMA engine as one bulk store.  Padded frames
+// never touch a consumer: the producer bulk-stores a zero row for them.
+// Slot layout: [V floats row][Np floats gamma].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradParams gp, WsLayout w, unsigned char *ws,
+                                                                       int b_major, RingLayout rl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ring ring = ring_setup(smem_raw, rl);
+    const ProblemDesc &d = gp.d;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
+    const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
+    const unsigned frames = (unsigned)d.B * (unsigned)d.T;
+    const uint32_t row_bytes = (uint32_t)d.V * 4u;
+    const uint32_t gam_bytes = (uint32_t)w.Np * 4u;
+    // extra region: [V floats of zeros][per consumer: Umax floats posterior]
+    float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
+    float *post_all = zero_row + d.V;
+    for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== producer (lane i owns frame i of the current batch) =====
+        const float *gam_all = reinterpret_cast<const float *>(ws + w.off_gam);
+        unsigned q = 0, pend;
+        ring_first_ticket(&hdr->k3_ticket, pend, lane, ring.batch);
+        for (;;) {
+            const unsigned base = ring_take_batch(&hdr->k3_ticket, pend, lane, ring.batch, frames);
+            if (base >= frames) break;
+            const unsigned f = base + (unsigned)lane;
+            int b = 0, t = 0;
+            bool need = false;
+            if (lane < ring.batch && f < frames) {
+                if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
+                else { t = (int)(f / d.B); b = (int)(f % d.B); }
+                if (t >= utt[b].Tb) {                                                // :296 -- zeros, straight from smem
+                    bulk_s2g(gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b, zero_row, row_bytes);
+                    bulk_commit();
+                } else {
+                    need = true;
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (need) {
+                const int s = ring_claim(ring, q + (unsigned)__popc(mask & ((1u << lane) - 1u)));
+                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0;
+                mbar_arrive_expect_tx(&ring.full[s], row_bytes + gam_bytes);
+                bulk_g2s(ring.slot(s), d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b, row_bytes,
+                         &ring.full[s]);
+                bulk_g2s(ring.slot(s) + row_bytes, gam_all + ((size_t)b * d.T + t) * w.Np, gam_bytes, &ring.full[s]);
+            }
+            q += (unsigned)__popc(mask);
+        }
+        ring_stop(ring, q, lane);
+        bulk_wait_all<0>();
+        // re-arm the queue for a possible second backward over the same workspace
+        if (lane == 0) {
+            __threadfence();
+            const unsigned done = atomicAdd(&hdr->k3_done, 1u) + 1u;
+            if (done == gridDim.x) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
+    const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
+    const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
+    const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
+    float *post_sm = post_all + (size_t)(warp - 1) * ((w.Umax + 3) & ~3);
+    const int per = d.kind == 0 ? 2 : 3;
+    const int n4 = d.V >> 2;
+    for (unsigned q = (unsigned)(warp - 1);; q += kRingConsumers) {
+        const int s = (int)(q % (unsigned)ring.slots);
+        mbar_wait(&ring.full[s], (q / (unsigned)ring.slots) & 1u);
+        const RowMeta m = ring.meta[s];
+        if (m.kind < 0) break;
+        const int b = m.b, t = m.t;
+        float *row = reinterpret_cast<float *>(ring.slot(s));
+        float *e_sm = row + d.V;                                             // gamma row, turned into 2^gamma in place
+        const UttInfo ui = utt[b];
+        const float lse2 = __ldg(lse_all + (size_t)b * d.T + t);
+        const float gy = gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss);
+        const float sc = gy * gp.scale;                                      // :291-294
+        const float c = -lse2;
+
+        float blank_part = 0.f;
+        for (int j = lane; j < ui.Nb; j += 32) {
+            const float e = ex2_approx(e_sm[j]);
+            e_sm[j] = e;
+            if (j % per == 0) blank_part += e;
+        }
+        blank_part = warp_sum(blank_part);
+        __syncwarp();
+        const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
+        const int *unode = unode_all + (size_t)b * w.Nmax;
+        const int *usym = usym_all + (size_t)b * w.Nmax;
+        for (int u = lane; u < ui.Ub; u += 32) {                             // merge per emitted id (:180-217)
+            const int n0 = __ldg(uoff + u), n1 = __ldg(uoff + u + 1);
+            float post = (u == ui.ublank) ? blank_part : 0.f;
+            for (int n = n0; n < n1; ++n) {
+                const int j = __ldg(unode + n);
+                if (j < ui.Nb) post += e_sm[j];
+            }
+            post_sm[u] = post * sc;
+        }
+        // softmax * sc in place
+        float4 *row4 = reinterpret_cast<float4 *>(row);
+#pragma unroll 4
+        for (int i = lane; i < n4; i += 32) {
+            float4 v = row4[i];
+            v.x = ex2_approx(fmaf(v.x, LOG2E_HI, c)) * sc;
+            v.y = ex2_approx(fmaf(v.y, LOG2E_HI, c)) * sc;
+            v.z = ex2_approx(fmaf(v.z, LOG2E_HI, c)) * sc;
+            v.w = ex2_approx(fmaf(v.w, LOG2E_HI, c)) * sc;
+            row4[i] = v;
+        }
+        __syncwarp();
+        for (int u = lane; u < ui.Ub; u += 32) row[__ldg(usym + u)] -= post_sm[u];     // distinct columns (:290)
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b, row, row_bytes);
+            bulk_commit();
+            bulk_wait_read<0>();                 // the TMA engine has read the slot: hand it back to the producer
+            mbar_arrive(&ring.empty[s]);
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();
 }
 
 __global__ void __launch_bounds__(256) loss_sum_kernel(const float *loss, int B, float *out) {
@@ -164,21 +328,29 @@ cudaError_t launch_loss_sum(const float *loss_per_utt, int B, float *loss_sum, c
 cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream) {
     const long long frames = (long long)g.d.B * g.d.T;
     if (frames == 0) return cudaSuccess;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_warp = w.Np;
+    unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
+    const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
+    const size_t extra = sizeof(float) * ((size_t)g.d.V + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
+    const RingLayout rl = make_ring(sizeof(float) * ((size_t)g.d.V + (size_t)w.Np), extra);
+    if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
+        ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl)) {
+        long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
+        if (ctas > sm_count()) ctas = sm_count();
+        cudaError_t e = cudaFuncSetAttribute(gradient_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+        if (e != cudaSuccess) return e;
+        gradient_ring_kernel<<<(int)ctas, kRingThreads, rl.total, stream>>>(g, w, wsb, b_major, rl);
+        return cudaGetLastError();
+    }
+    const int per_warp = w.Np + ((w.Umax + 3) & ~3);
     const size_t smem = sizeof(float) * (size_t)per_warp * kWarpsPerCta;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     long long ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
-    const long long cap = (long long)sms * 8;
+    const long long cap = (long long)sm_count() * 8;
     if (ctas > cap) ctas = cap;
-    const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
-    gradient_kernel<<<(int)ctas, kWarpsPerCta * 32, smem, stream>>>(g, w, static_cast<const unsigned char *>(ws),
-                                                                    b_major, per_warp);
+    gradient_kernel<<<(int)ctas, kWarpsPerCta * 32, smem, stream>>>(g, w, wsb, b_major, per_warp);
     return cudaGetLastError();
 }
 

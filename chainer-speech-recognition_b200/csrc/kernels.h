@@ -22,6 +22,11 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
 cudaError_t launch_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,
                           int64_t *argmax_out, cudaStream_t stream);
 
+// shared by the two row-streaming kernels (defined in softmax_gather.cu)
+struct RingLayout;
+bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl);
+int sm_count();
+
 // kernel 2: alpha/beta lattice recursion
 struct LatticeParams {
     const int32_t *labels, *bigrams;

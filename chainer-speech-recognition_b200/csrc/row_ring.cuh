@@ -1,0 +1,124 @@
+// row_ring.cuh -- shared-memory ring of activation rows fed by the TMA engine.
+//
+// Both row-streaming kernels (softmax/gather and gradient) use the same structure: one CTA per SM,
+// warp 0 is the producer, the other warps are consumers.
+//   producer  draws frame tickets from a global counter (batches of kTicketBatch consecutive frames,
+//             next batch prefetched); lane i of the producer warp owns frame i of the batch: the lanes
+//             whose frame needs work are ranked by ballot, each claims the next ring slot in sequence
+//             order, arms its mbarrier and issues a 1-D bulk async copy (cp.async.bulk, SASS UBLKCP) of
+//             the whole V-float row -- several rows ahead of the consumers, so DRAM latency is covered by
+//             the copy queue instead of by resident warps;
+//   consumer  warp c handles row sequence numbers c, c+NC, c+2NC, ...: waits for the slot's "full"
+//             barrier, works on the row out of shared memory, then releases the slot ("empty").
+// Requirements (checked by the host dispatcher, which otherwise uses the plain LDG kernels):
+// rows 16-byte aligned, V % 4 == 0, and at least kMinSlots rows fit in shared memory.
+#pragma once
+#include "common.cuh"
+
+namespace b200ctc {
+
+constexpr int kRingConsumers = 8;
+constexpr int kRingThreads = 32 * (1 + kRingConsumers);
+constexpr int kTicketBatch = 8;       // frames per ticket; one producer lane per frame of the batch
+constexpr int kMinSlots = 4;
+constexpr int kMaxSlots = 16;
+constexpr size_t kRingSmemBudget = 200 * 1024;
+
+struct RowMeta {
+    int b, t;
+    int kind;      // 0: full work, 1: argmax only (padded frame), -1: stop
+    int pad;
+};
+
+struct RingLayout {
+    int slots;             // R
+    size_t slot_bytes;     // row (+ per-row extras), multiple of 128
+    size_t off_meta, off_full, off_empty, off_extra, total;
+};
+
+__host__ __device__ inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes) {
+    RingLayout r;
+    r.slot_bytes = align_up(slot_payload, 128);
+    const size_t fixed = (size_t)kMaxSlots * (sizeof(RowMeta) + 16) + extra_bytes + 256;
+    long long n = ((long long)kRingSmemBudget - (long long)fixed) / (long long)r.slot_bytes;
+    if (n > kMaxSlots) n = kMaxSlots;
+    r.slots = (int)(n < 0 ? 0 : n);
+    size_t o = r.slot_bytes * (size_t)r.slots;
+    r.off_meta = o;  o += sizeof(RowMeta) * kMaxSlots;
+    r.off_full = o;  o += 8 * kMaxSlots;
+    r.off_empty = o; o += 8 * kMaxSlots;
+    r.off_extra = align_up(o, 128);
+    r.total = r.off_extra + extra_bytes;
+    return r;
+}
+
+#ifdef __CUDACC__
+
+struct Ring {
+    unsigned char *base;
+    RowMeta *meta;
+    uint64_t *full, *empty;
+    int slots;
+    int batch;             // frames per ticket = min(kTicketBatch, slots): a batch never waits on its own rows
+    size_t slot_bytes;
+    __device__ __forceinline__ unsigned char *slot(int s) const { return base + (size_t)s * slot_bytes; }
+};
+
+__device__ __forceinline__ Ring ring_setup(unsigned char *smem, const RingLayout &rl) {
+    Ring r;
+    r.base = smem;
+    r.meta = reinterpret_cast<RowMeta *>(smem + rl.off_meta);
+    r.full = reinterpret_cast<uint64_t *>(smem + rl.off_full);
+    r.empty = reinterpret_cast<uint64_t *>(smem + rl.off_empty);
+    r.slots = rl.slots;
+    r.batch = rl.slots < kTicketBatch ? rl.slots : kTicketBatch;
+    r.slot_bytes = rl.slot_bytes;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < rl.slots; ++i) {
+            mbar_init(&r.full[i], 1);
+            mbar_init(&r.empty[i], 1);
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Producer side: claim the slot for row sequence number q (waits until its previous occupant was released).
+__device__ __forceinline__ int ring_claim(const Ring &r, unsigned q) {
+    const int s = (int)(q % (unsigned)r.slots);
+    const unsigned n = q / (unsigned)r.slots;
+    if (n > 0) mbar_wait(&r.empty[s], (n - 1) & 1u);
+    return s;
+}
+
+// Producer side (whole warp): tell every consumer to stop -- one stop record per consumer, in sequence order.
+__device__ __forceinline__ void ring_stop(const Ring &r, unsigned q, int lane) {
+    if (lane < kRingConsumers) {
+        const int s = ring_claim(r, q + (unsigned)lane);
+        r.meta[s].kind = -1;
+        mbar_arrive(&r.full[s]);
+    }
+}
+
+// Producer side (whole warp): ticket handling.  Lane 0 keeps the *next* batch's ticket in flight in `pend`
+// (the atomic's latency hides behind the batch being issued); ring_take_batch broadcasts the batch that
+// is due now and immediately requests the following one.
+__device__ __forceinline__ void ring_first_ticket(unsigned *ticket, unsigned &pend, int lane, int batch) {
+    pend = 0;
+    if (lane == 0) pend = atomicAdd(ticket, (unsigned)batch);
+}
+__device__ __forceinline__ unsigned ring_take_batch(unsigned *ticket, unsigned &pend, int lane, int batch,
+                                                    unsigned frames) {
+    const unsigned base = __shfl_sync(0xffffffffu, pend, 0);
+    if (base < frames && lane == 0) pend = atomicAdd(ticket, (unsigned)batch);
+    return base;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200ctc

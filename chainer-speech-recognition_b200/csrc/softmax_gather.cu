@@ -9,8 +9,10 @@
 // No (T,B,V) log-probability tensor is ever materialised.
 //
 // One warp per frame, 128-bit loads, online (max, sum) per lane, warp-shuffle reduction.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "row_ring.cuh"
 
 namespace b200ctc {
 
@@ -20,18 +22,25 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kUnroll = 4;
 
 // ---------------------------------------------------------------------------------------------
-// kernel 0: lengths, lattice size and the distinct-symbol CSR used by the gradient kernel
-// (the merge of _compute_label_probability, gram_ctc.py:180-217, needs "which nodes share a symbol").
-// One CTA per utterance.  Only non-blank-type nodes go into the CSR; the blank-type nodes (every
-// 2nd / 3rd node) are summed directly by the gradient kernel.
+// kernel 0: per-utterance bookkeeping for the gradient kernel -- which vocabulary ids can the lattice
+// emit, and which nodes share an id (the merge of _compute_label_probability, gram_ctc.py:180-217).
+// One CTA per utterance.  Output, per utterance:
+//   usym[u]            distinct emitted ids, sorted ascending, blank included (Ub of them)
+//   uoff[u]..uoff[u+1] range in unode[] listing the non-blank-type nodes that carry id usym[u]
+//                      (the blank-type nodes -- every 2nd / 3rd node -- are summed directly)
+//   bm[], pc[]         V-bit bitmap of emitted ids and, per 32-bit word, the number of set bits before it,
+//                      so that "posterior slot of column k" = pc[k/32] + popc(bm[k/32] & low bits).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) prep_kernel(ProblemDesc d, WsLayout w, unsigned char *ws) {
     extern __shared__ int sm[];
+    __shared__ int s_U;
     const int b = blockIdx.x;
     UttInfo *ui = reinterpret_cast<UttInfo *>(ws + w.off_utt) + b;
     int *usym = reinterpret_cast<int *>(ws + w.off_usym) + (size_t)b * w.Nmax;
     int *uoff = reinterpret_cast<int *>(ws + w.off_uoff) + (size_t)b * (w.Nmax + 1);
     int *unode = reinterpret_cast<int *>(ws + w.off_unode) + (size_t)b * w.Nmax;
+    unsigned *bm_g = reinterpret_cast<unsigned *>(ws + w.off_bm) + (size_t)b * w.nwords;
+    int *pc_g = reinterpret_cast<int *>(ws + w.off_pc) + (size_t)b * w.nwords;
 
     int Tb = d.input_lengths ? d.input_lengths[b] : d.T;
     int Lb = d.label_lengths ? d.label_lengths[b] : d.Lmax;
@@ -40,59 +49,78 @@ __global__ void __launch_bounds__(128) prep_kernel(ProblemDesc d, WsLayout w, un
     if (Lb < 0 || Lb > d.Lmax) { flags |= 1; Lb = max(0, min(Lb, d.Lmax)); }
     const int per = d.kind == 0 ? 2 : 3;
     const int Nb = per * Lb + 1;
-    // entries: the non-blank-type nodes in node order.  CTC: label i -> node 2i+1.
-    // Gram: unigram i -> node 3i+1, bigram i -> node 3i+2.
+    // entry 0 = the blank id itself; entries 1..M = the non-blank-type nodes in node order
+    // (CTC: label i -> node 2i+1; Gram: unigram i -> node 3i+1, bigram i -> node 3i+2).
     const int M = (per - 1) * Lb;
-    int *esym = sm;               // [M] symbol (or -1)
-    int *efirst = sm + M;         // [M] index of the first entry with the same symbol
-    int *epos = sm + 2 * M;       // [M] how many earlier entries share the symbol
-    int *rank = sm + 3 * M;       // [M] distinct-symbol index of a first entry
-    int *cnt = sm + 4 * M;        // [M] list length per distinct symbol
+    const int E = M + 1;
+    int *esym = sm;               // [E] symbol (or -1)
+    int *efirst = sm + E;         // [E] first entry with the same symbol
+    int *epos = sm + 2 * E;       // [E] number of earlier node entries with the same symbol
+    int *erank = sm + 3 * E;      // [E] sorted position of a first entry's symbol
+    int *cnt = sm + 4 * E;        // [E] node-list length per distinct symbol
+    unsigned *bm = reinterpret_cast<unsigned *>(sm + 5 * E);   // [nwords]
     const int32_t *lab = d.labels + (size_t)b * d.Lmax;
     const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)b * d.Lmax : nullptr;
-    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+    if (threadIdx.x == 0) s_U = 0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
         int s;
-        if (d.kind == 0) s = lab[e];
-        else s = (e & 1) ? big[e >> 1] : lab[e >> 1];
+        if (e == 0) s = d.blank;
+        else if (d.kind == 0) s = lab[e - 1];
+        else s = ((e - 1) & 1) ? big[(e - 1) >> 1] : lab[(e - 1) >> 1];
         if (s < 0 || s >= d.V) s = -1;                     // dead bigram (or an id outside the vocabulary)
         esym[e] = s;
         cnt[e] = 0;
     }
+    for (int i = threadIdx.x; i < w.nwords; i += blockDim.x) bm[i] = 0u;
     __syncthreads();
-    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
         const int s = esym[e];
         int first = e, pos = 0;
+        bool found = false;
         if (s >= 0) {
             for (int e2 = 0; e2 < e; ++e2)
-                if (esym[e2] == s) { if (pos == 0) first = e2; ++pos; }
+                if (esym[e2] == s) {
+                    if (!found) { first = e2; found = true; }
+                    if (e2 >= 1) ++pos;
+                }
         }
         efirst[e] = first;
         epos[e] = pos;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int u = 0;
-        for (int e = 0; e < M; ++e) {
-            if (esym[e] >= 0 && efirst[e] == e) { rank[e] = u; usym[u] = esym[e]; ++u; }
-        }
-        ui->Tb = Tb; ui->Lb = Lb; ui->Nb = Nb; ui->Ub = u;
-        ui->Ph = 0.f; ui->Pl = 0.f; ui->loss = 0.f; ui->flags = flags;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const int s = esym[e];
+        if (s < 0 || efirst[e] != e) continue;
+        int r = 0;
+        for (int e2 = 0; e2 < E; ++e2)
+            if (esym[e2] >= 0 && efirst[e2] == e2 && esym[e2] < s) ++r;
+        erank[e] = r;
+        usym[r] = s;
+        atomicAdd(&s_U, 1);
+        atomicOr(&bm[s >> 5], 1u << (s & 31));
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < M; e += blockDim.x)
-        if (esym[e] >= 0) atomicAdd(&cnt[rank[efirst[e]]], 1);
+    for (int e = 1 + threadIdx.x; e < E; e += blockDim.x)
+        if (esym[e] >= 0) atomicAdd(&cnt[erank[efirst[e]]], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int U = ui->Ub;
+        const int U = s_U;
         int acc = 0;
         for (int u = 0; u < U; ++u) { uoff[u] = acc; acc += cnt[u]; }
         uoff[U] = acc;
+        ui->Tb = Tb; ui->Lb = Lb; ui->Nb = Nb; ui->Ub = U;
+        ui->flags = flags; ui->ublank = erank[0]; ui->pad = 0;
+    }
+    if (threadIdx.x == 32) {
+        int acc = 0;
+        for (int i = 0; i < w.nwords; ++i) { pc_g[i] = acc; bm_g[i] = bm[i]; acc += __popc(bm[i]); }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < M; e += blockDim.x) {
+    for (int e = 1 + threadIdx.x; e < E; e += blockDim.x) {
         if (esym[e] < 0) continue;
-        const int node = d.kind == 0 ? (2 * e + 1) : (3 * (e >> 1) + 1 + (e & 1));
-        unode[uoff[rank[efirst[e]]] + epos[e]] = node;
+        const int en = e - 1;
+        const int node = d.kind == 0 ? (2 * en + 1) : (3 * (en >> 1) + 1 + (en & 1));
+        unode[uoff[erank[efirst[e]]] + epos[e]] = node;
     }
 }
 
@@ -247,18 +275,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
                                                                           unsigned char *ws, int64_t *argmax_out,
                                                                           int b_major) {
     const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const int warps_total = gridDim.x * kWarpsPerCta;
-    const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     float *lse_out = reinterpret_cast<float *>(ws + w.off_lse);
     float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
-    const long long frames = (long long)d.B * d.T;
-    for (long long f = warp_global; f < frames; f += warps_total) {
-        // walk frames in memory order of the activations
+    const unsigned frames = (unsigned)d.B * (unsigned)d.T;
+    for (;;) {
+        // work queue: one ticket per frame, handed out in memory order of the activations, so that the
+        // (variable-length) valid frames spread evenly over the warps whatever the batch layout is
+        unsigned f = 0;
+        if (lane == 0) f = atomicAdd(&hdr->k1_ticket, 1u);
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (f >= frames) break;
         int b, t;
         if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
         else { t = (int)(f / d.B); b = (int)(f % d.B); }
-        const int Tb = utt[b].Tb;
+        int Tb = d.input_lengths ? d.input_lengths[b] : d.T;
+        Tb = max(0, min(Tb, d.T));
         const bool valid = t < Tb;
         if (!valid && !ARGMAX) continue;
         const float *row = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
@@ -272,7 +304,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
         split_lse2(row_max, lse2, la, lb);
         if (lane == 0) lse_out[(size_t)b * d.T + t] = la + lb;
         // gather: column 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams (gram_ctc.py:24-32, :155)
-        const int Lb = utt[b].Lb;
+        int Lb = d.label_lengths ? d.label_lengths[b] : d.Lmax;
+        Lb = max(0, min(Lb, d.Lmax));
         float2 *lprow = lp_out + ((size_t)b * d.T + t) * w.W;
         const int32_t *lab = d.labels + (size_t)b * d.Lmax;
         const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)b * d.Lmax : nullptr;
@@ -286,6 +319,130 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
             if (sym >= 0 && sym < d.V) v = split_log2p(__ldg(row + sym), la, lb);
             lprow[c] = v;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 1, TMA row-ring variant (see row_ring.cuh): the row sits in shared memory, so the statistics
+// take two cheap passes (max/argmax, then sum of exponentials) and the label gather reads shared
+// memory instead of going back to L2.
+// ---------------------------------------------------------------------------------------------
+template <bool ARGMAX>
+__global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(ProblemDesc d, WsLayout w,
+                                                                              unsigned char *ws,
+                                                                              int64_t *argmax_out, int b_major,
+                                                                              RingLayout rl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ring ring = ring_setup(smem_raw, rl);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
+    const unsigned frames = (unsigned)d.B * (unsigned)d.T;
+    const uint32_t row_bytes = (uint32_t)d.V * 4u;
+
+    if (warp == 0) {
+        // ===== producer (lane i owns frame i of the current batch) =====
+        unsigned q = 0, pend;
+        ring_first_ticket(&hdr->k1_ticket, pend, lane, ring.batch);
+        for (;;) {
+            const unsigned base = ring_take_batch(&hdr->k1_ticket, pend, lane, ring.batch, frames);
+            if (base >= frames) break;
+            const unsigned f = base + (unsigned)lane;
+            int b = 0, t = 0;
+            bool valid = false, need = false;
+            if (lane < ring.batch && f < frames) {
+                if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
+                else { t = (int)(f / d.B); b = (int)(f % d.B); }
+                int Tb = d.input_lengths ? __ldg(d.input_lengths + b) : d.T;
+                Tb = max(0, min(Tb, d.T));
+                valid = t < Tb;
+                need = valid || ARGMAX;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (need) {
+                const int s = ring_claim(ring, q + (unsigned)__popc(mask & ((1u << lane) - 1u)));
+                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = valid ? 0 : 1;
+                mbar_arrive_expect_tx(&ring.full[s], row_bytes);
+                bulk_g2s(ring.slot(s), d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b, row_bytes,
+                         &ring.full[s]);
+            }
+            q += (unsigned)__popc(mask);
+        }
+        ring_stop(ring, q, lane);
+        return;
+    }
+
+    // ===== consumers =====
+    float *lse_out = reinterpret_cast<float *>(ws + w.off_lse);
+    float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
+    const int n4 = d.V >> 2;
+    for (unsigned q = (unsigned)(warp - 1);; q += kRingConsumers) {
+        const int s = (int)(q % (unsigned)ring.slots);
+        mbar_wait(&ring.full[s], (q / (unsigned)ring.slots) & 1u);
+        const RowMeta m = ring.meta[s];
+        if (m.kind < 0) break;
+        const float *row = reinterpret_cast<const float *>(ring.slot(s));
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        // pass 1: maximum (and greedy index)
+        RowStat st;
+        st.m = -INFINITY; st.s = 0.f; st.bv = -INFINITY; st.bi = 0x7fffffff;
+#pragma unroll 4
+        for (int i = lane; i < n4; i += 32) {
+            const float4 v = row4[i];
+            st.m = fmaxf(st.m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+            fold<ARGMAX>(st, v.x, 4 * i);
+            fold<ARGMAX>(st, v.y, 4 * i + 1);
+            fold<ARGMAX>(st, v.z, 4 * i + 2);
+            fold<ARGMAX>(st, v.w, 4 * i + 3);
+        }
+        if (ARGMAX) {
+            float bv = st.bv; int bi = st.bi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const bool onan = (ov != ov), mnan = (bv != bv);
+                bool take;
+                if (onan || mnan) take = onan && (!mnan || oi < bi);
+                else take = (ov > bv) || (ov == bv && oi < bi);
+                if (take) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) argmax_out[(size_t)m.b * d.T + m.t] = bi;
+        }
+        if (m.kind == 0) {
+            const float mx = warp_max(st.m);
+            // pass 2: sum of 2^((x - max) * log2 e)
+            const float c = -mx * LOG2E_HI;
+            float sum = 0.f;
+#pragma unroll 4
+            for (int i = lane; i < n4; i += 32) {
+                const float4 v = row4[i];
+                sum += (ex2_approx(fmaf(v.x, LOG2E_HI, c)) + ex2_approx(fmaf(v.y, LOG2E_HI, c))) +
+                       (ex2_approx(fmaf(v.z, LOG2E_HI, c)) + ex2_approx(fmaf(v.w, LOG2E_HI, c)));
+            }
+            sum = warp_sum(sum);
+            float la, lb;
+            split_lse2(mx, sum, la, lb);
+            if (lane == 0) lse_out[(size_t)m.b * d.T + m.t] = la + lb;
+            // gather from the staged row: column 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams
+            int Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
+            Lb = max(0, min(Lb, d.Lmax));
+            float2 *lprow = lp_out + ((size_t)m.b * d.T + m.t) * w.W;
+            const int32_t *lab = d.labels + (size_t)m.b * d.Lmax;
+            const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)m.b * d.Lmax : nullptr;
+            const int ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
+            for (int cidx = lane; cidx < ncol; cidx += 32) {
+                int sym;
+                if (cidx == 0) sym = d.blank;
+                else if (cidx <= d.Lmax) sym = (cidx - 1 < Lb) ? __ldg(lab + cidx - 1) : -1;
+                else sym = __ldg(big + cidx - 1 - d.Lmax);
+                float2 v = make_float2(SENT, 0.f);
+                if (sym >= 0 && sym < d.V) v = split_log2p(row[sym], la, lb);
+                lprow[cidx] = v;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[s]);
     }
 }
 
@@ -323,7 +480,7 @@ int grid_for_frames(long long frames) {
 
 cudaError_t launch_prep(const ProblemDesc &d, const WsLayout &w, void *ws, cudaStream_t stream) {
     const int per = d.kind == 0 ? 1 : 2;
-    const size_t smem = sizeof(int) * 5 * (size_t)per * (size_t)(d.Lmax > 0 ? d.Lmax : 1);
+    const size_t smem = sizeof(int) * (5 * ((size_t)per * d.Lmax + 1) + (size_t)w.nwords);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -332,18 +489,46 @@ cudaError_t launch_prep(const ProblemDesc &d, const WsLayout &w, void *ws, cudaS
     return cudaGetLastError();
 }
 
+bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl) {
+    if (getenv("B200CTC_NO_TMA")) return false;
+    return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride_t & 3) == 0 && (stride_b & 3) == 0 &&
+           (V & 3) == 0 && rl.slots >= kMinSlots;
+}
+
+int sm_count() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
 cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
                                   cudaStream_t stream) {
     const long long frames = (long long)d.B * d.T;
     if (frames == 0) return cudaSuccess;
-    const int grid = grid_for_frames(frames);
     const int b_major = d.stride_b > d.stride_t ? 1 : 0;
+    unsigned char *wsb = static_cast<unsigned char *>(ws);
+    const RingLayout rl = make_ring((size_t)d.V * 4, 0);
+    if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl)) {
+        long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
+        if (ctas > sm_count()) ctas = sm_count();
+        cudaError_t e;
+        if (argmax_out) {
+            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+            if (e != cudaSuccess) return e;
+            softmax_gather_ring_kernel<true><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, argmax_out, b_major, rl);
+        } else {
+            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+            if (e != cudaSuccess) return e;
+            softmax_gather_ring_kernel<false><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, nullptr, b_major, rl);
+        }
+        return cudaGetLastError();
+    }
+    const int grid = grid_for_frames(frames);
     if (argmax_out)
-        softmax_gather_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, static_cast<unsigned char *>(ws),
-                                                                            argmax_out, b_major);
+        softmax_gather_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, argmax_out, b_major);
     else
-        softmax_gather_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, static_cast<unsigned char *>(ws),
-                                                                             nullptr, b_major);
+        softmax_gather_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, nullptr, b_major);
     return cudaGetLastError();
 }
 
