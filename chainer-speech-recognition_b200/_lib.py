@@ -27,7 +27,7 @@ def _bind(lib):
     lib.b200ctc_forward.restype = c.c_int
     lib.b200ctc_forward.argtypes = [
         c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
-        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_float, c.c_void_p,
         c.c_void_p, c.c_size_t, c.c_uint, c.c_void_p]
     lib.b200ctc_backward.restype = c.c_int
     lib.b200ctc_backward.argtypes = [

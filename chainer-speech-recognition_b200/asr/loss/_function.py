@@ -69,7 +69,8 @@ class LatticeLossFunction(torch.autograd.Function):
         nbytes = _lib.workspace_bytes(kind, B, T, V, Lmax)
         workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
         loss_b = torch.empty(B, dtype=torch.float32, device=dev)
-        loss_sum = torch.empty((), dtype=torch.float32, device=dev)
+        loss_red = torch.empty((), dtype=torch.float32, device=dev)
+        loss_scale = 1.0 / float(batch_global) if reduce == "mean" else 1.0     # gram_ctc.py:280-281
         argmax = torch.empty((B, T), dtype=torch.int64, device=dev) if want_argmax else None
         with torch.cuda.device(dev):
             _lib.check(lib.b200ctc_forward(
@@ -77,7 +78,7 @@ class LatticeLossFunction(torch.autograd.Function):
                 labels.data_ptr(), bigrams.data_ptr() if bigrams is not None else None,
                 input_length.data_ptr() if input_length is not None else None,
                 label_length.data_ptr() if label_length is not None else None,
-                blank, B, T, V, Lmax, loss_b.data_ptr(), loss_sum.data_ptr(),
+                blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(), loss_scale,
                 argmax.data_ptr() if argmax is not None else None,
                 workspace.data_ptr(), workspace.numel(), 0, _stream_ptr(dev)))
         ctx.kind, ctx.blank, ctx.reduce, ctx.dims = kind, blank, reduce, (B, T, V, Lmax)
@@ -85,8 +86,8 @@ class LatticeLossFunction(torch.autograd.Function):
         ctx.save_for_backward(acts, labels, bigrams if bigrams is not None else labels, workspace)
         ctx.has_bigrams = bigrams is not None
         ctx.argmax = argmax
-        if reduce == "mean":                                     # gram_ctc.py:280-281
-            loss = loss_sum / float(batch_global)
+        if reduce == "mean":                                     # gram_ctc.py:280-281 (scaled in-kernel)
+            loss = loss_red
             if group is not None:
                 import torch.distributed as dist
                 dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)

@@ -44,7 +44,11 @@ int validate(int kind, int B, int T, int V, int Lmax, int blank, bool need_blank
 
 }  // namespace
 
+namespace b200ctc { void lattice_set_debug(long long *p); }
+
 extern "C" {
+
+void b200ctc_debug_lattice(long long *p) { b200ctc::lattice_set_debug(p); }
 
 int b200ctc_version(void) { return B200CTC_VERSION; }
 
@@ -60,15 +64,15 @@ int b200ctc_workspace_bytes(int kind, int B, int T, int V, int Lmax, size_t *byt
 
 int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
                     const int32_t *bigrams, const int32_t *input_lengths, const int32_t *label_lengths, int blank,
-                    int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_sum, int64_t *argmax_out,
-                    void *workspace, size_t workspace_bytes, unsigned flags, void *stream_) {
+                    int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_reduced, float loss_scale,
+                    int64_t *argmax_out, void *workspace, size_t workspace_bytes, unsigned flags, void *stream_) {
     (void)flags;
     int rc = validate(kind, B, T, V, Lmax, blank, true);
     if (rc) return rc;
     if (!acts && (size_t)B * T > 0) return fail(B200CTC_INVALID_ARGUMENT, "acts is NULL%s");
     if (!labels && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "labels is NULL%s");
     if (kind == B200CTC_KIND_GRAM && !bigrams && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "bigrams is NULL for Gram-CTC%s");
-    if (!loss_per_utt || !loss_sum || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "output or workspace pointer is NULL%s");
+    if (!loss_per_utt || !loss_reduced || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "output or workspace pointer is NULL%s");
     if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
     if ((reinterpret_cast<uintptr_t>(acts) & 3) != 0) return fail(B200CTC_INVALID_ARGUMENT, "acts must be 4-byte aligned%s");
     const WsLayout w = make_layout(kind, B, T, V, Lmax);
@@ -76,7 +80,7 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
         return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s: %lld < %lld bytes", "", (long long)workspace_bytes,
                     (long long)w.total);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (B == 0) return check_cuda(cudaMemsetAsync(loss_sum, 0, sizeof(float), stream), "memset");
+    if (B == 0) return check_cuda(cudaMemsetAsync(loss_reduced, 0, sizeof(float), stream), "memset");
 
     ProblemDesc d;
     d.kind = kind; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
@@ -87,20 +91,15 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     if ((rc = check_cuda(cudaMemsetAsync(ws + w.off_hdr, 0, sizeof(WsHeader), stream), "workspace header memset"))) return rc;
     if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, stream), "softmax/gather kernel"))) return rc;
-    if ((rc = check_cuda(launch_prep(d, w, ws, stream), "prep kernel"))) return rc;
 
     LatticeParams lp;
-    lp.labels = labels; lp.bigrams = d.bigrams;
-    lp.B = B; lp.T = T; lp.Lmax = Lmax; lp.W = w.W; lp.Np = w.Np; lp.C = 0;
-    lp.utt = reinterpret_cast<UttInfo *>(ws + w.off_utt);
-    lp.lp = reinterpret_cast<const float2 *>(ws + w.off_lp);
-    lp.fv = reinterpret_cast<float2 *>(ws + w.off_fv);
-    lp.gam = reinterpret_cast<float *>(ws + w.off_gam);
-    lp.loss_per_utt = loss_per_utt;
+    lp.d = d; lp.w = w; lp.ws = ws;
+    lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
+    lp.W = 0; lp.S = 0;
     int st = 0;
-    if ((rc = check_cuda(launch_lattice(kind, lp, w.Nmax, stream, &st), "lattice kernel"))) return rc;
-    if (st) return fail(B200CTC_UNSUPPORTED, "lattice too large for the instantiated kernels%s");
-    return check_cuda(launch_loss_sum(loss_per_utt, B, loss_sum, stream), "loss sum kernel");
+    if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
+    if (st) return fail(B200CTC_UNSUPPORTED, "lattice of %s%lld nodes does not fit the kernel's shared-memory pipeline", "", w.Nmax);
+    return B200CTC_OK;
 }
 
 int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,

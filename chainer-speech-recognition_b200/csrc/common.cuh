@@ -27,9 +27,9 @@ struct UttInfo {
     float Ph;      // log2 P, integer part   (+1e30 when the alignment is infeasible)
     float Pl;      // log2 P, fractional part
     float loss;    // -ln P, or 1e10 when infeasible (reference quirk)
-    int flags;     // bit0: lengths were out of range and got clamped; bit1: infeasible
+    int flags;     // bit0: lengths were out of range and got clamped
     int ublank;    // position of the blank id in the sorted distinct-symbol list
-    int pad;
+    int infeasible;  // written by the lattice CTA: 1 when no alignment exists
 };
 
 // Header at the start of the workspace: work-queue tickets for the row-streaming kernels.
@@ -37,7 +37,7 @@ struct WsHeader {
     unsigned int k1_ticket;    // next frame for the softmax/gather kernel
     unsigned int k3_ticket;    // next frame for the gradient kernel
     unsigned int k3_done;      // gradient warps that ran out of work (last one re-arms the queue)
-    unsigned int pad;
+    unsigned int k2_done;      // lattice CTAs that have published their loss (last one reduces the batch)
 };
 
 // Workspace carve-up (all offsets in bytes from a 16-byte aligned base).
@@ -48,7 +48,7 @@ struct WsLayout {
     int Np;        // Nmax padded to a multiple of 4
     int Umax;      // upper bound on distinct symbols per utterance (blank + every non-blank-type node)
     int nwords;    // ceil(V / 32): words of the per-utterance "is a lattice symbol" bitmap
-    size_t off_hdr, off_utt, off_lse, off_lp, off_fv, off_gam, off_usym, off_uoff, off_unode, off_bm, off_pc, total;
+    size_t off_hdr, off_utt, off_lse, off_lp, off_av, off_bv, off_usym, off_uoff, off_unode, off_bm, off_pc, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -68,8 +68,8 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     w.off_utt = o;   o = align_up(o + sizeof(UttInfo) * (size_t)B, 256);
     w.off_lse = o;   o = align_up(o + sizeof(float) * BT, 256);
     w.off_lp = o;    o = align_up(o + sizeof(float2) * BT * w.W, 256);
-    w.off_fv = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);
-    w.off_gam = o;   o = align_up(o + sizeof(float) * BT * w.Np, 256);
+    w.off_av = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // alpha_t[j], split log2
+    w.off_bv = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // beta_t[j] (excludes emission at t)
     w.off_usym = o;  o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
     w.off_uoff = o;  o = align_up(o + sizeof(int) * (size_t)B * (w.Nmax + 1), 256);
     w.off_unode = o; o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
@@ -125,6 +125,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -139,6 +142,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
+}
+// same, but backs off between polls: for waits that are expected to block for a while, so that the
+// polling does not compete with the warps it is waiting for
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

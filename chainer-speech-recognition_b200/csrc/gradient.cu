@@ -1,4 +1,4 @@
-// gradient.cu -- kernel 3: fused gradient, plus the deterministic loss sum.
+// gradient.cu -- kernel 3: fused gradient.
 //
 // Replaces GramCTC.backward (asr/loss/gram_ctc.py:284-297) and _compute_label_probability (:180-217):
 //   grad[t,b,k] = ( softmax[t,b,k] - exp( LSE_{j: symbol_j = k} (alpha_t[j]+beta_t[j]) - log P_b ) ) * gy * scale
@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
     const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
-    const float *gam_all = reinterpret_cast<const float *>(ws + w.off_gam);
+    const float2 *av_all = reinterpret_cast<const float2 *>(ws + w.off_av);
+    const float2 *bv_all = reinterpret_cast<const float2 *>(ws + w.off_bv);
     const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
     const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
     const unsigned *bm_all = reinterpret_cast<const unsigned *>(ws + w.off_bm);
@@ -92,10 +93,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         const float c = -lse2;
 
         // ---- posteriors of this frame: e[j] = 2^gamma[t][j], merged per emitted id (:180-217) ----
-        const float *gam = gam_all + ((size_t)b * d.T + t) * w.Np;
+        const float2 *arow = av_all + ((size_t)b * d.T + t) * w.Np;
+        const float2 *brow = bv_all + ((size_t)b * d.T + t) * w.Np;
         float blank_part = 0.f;
         for (int j = lane; j < ui.Nb; j += 32) {
-            const float e = ex2_approx(__ldg(gam + j));
+            const float2 a = __ldg(arow + j), bb = __ldg(brow + j);
+            const float e = ex2_approx(((a.x + bb.x) - ui.Ph) + ((a.y + bb.y) - ui.Pl));    // 2^gamma
             e_sm[j] = e;
             if (j % per == 0) blank_part += e;
         }
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
 // (softmax * sc, then subtracts the merged posteriors at the <= L+1 label columns -- a plain scatter in
 // shared memory, no bitmap needed) and hands it back to the TMA engine as one bulk store.  Padded frames
 // never touch a consumer: the producer bulk-stores a zero row for them.
-// Slot layout: [V floats row][Np floats gamma].
+// Slot layout: [V floats row][Np float2 alpha row][Np float2 beta row].
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradParams gp, WsLayout w, unsigned char *ws,
                                                                        int b_major, RingLayout rl) {
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
     const uint32_t row_bytes = (uint32_t)d.V * 4u;
-    const uint32_t gam_bytes = (uint32_t)w.Np * 4u;
+    const uint32_t ab_bytes = (uint32_t)w.Np * 8u;
     // extra region: [V floats of zeros][per consumer: Umax floats posterior]
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
     float *post_all = zero_row + d.V;
@@ -197,7 +200,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
 
     if (warp == 0) {
         // ===== producer (lane i owns frame i of the current batch) =====
-        const float *gam_all = reinterpret_cast<const float *>(ws + w.off_gam);
+        const float2 *av_all = reinterpret_cast<const float2 *>(ws + w.off_av);
+        const float2 *bv_all = reinterpret_cast<const float2 *>(ws + w.off_bv);
         unsigned q = 0, pend;
         ring_first_ticket(&hdr->k3_ticket, pend, lane, ring.batch);
         for (;;) {
@@ -220,10 +224,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             if (need) {
                 const int s = ring_claim(ring, q + (unsigned)__popc(mask & ((1u << lane) - 1u)));
                 ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0;
-                mbar_arrive_expect_tx(&ring.full[s], row_bytes + gam_bytes);
+                mbar_arrive_expect_tx(&ring.full[s], row_bytes + 2 * ab_bytes);
                 bulk_g2s(ring.slot(s), d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b, row_bytes,
                          &ring.full[s]);
-                bulk_g2s(ring.slot(s) + row_bytes, gam_all + ((size_t)b * d.T + t) * w.Np, gam_bytes, &ring.full[s]);
+                bulk_g2s(ring.slot(s) + row_bytes, av_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
+                bulk_g2s(ring.slot(s) + row_bytes + ab_bytes, bv_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
             }
             q += (unsigned)__popc(mask);
         }
@@ -253,7 +258,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         if (m.kind < 0) break;
         const int b = m.b, t = m.t;
         float *row = reinterpret_cast<float *>(ring.slot(s));
-        float *e_sm = row + d.V;                                             // gamma row, turned into 2^gamma in place
+        const float2 *a_sm = reinterpret_cast<const float2 *>(row + d.V);       // alpha row
+        const float2 *b_sm = a_sm + w.Np;                                    // beta row
+        float *e_sm = reinterpret_cast<float *>(row + d.V);                  // 2^gamma, written over the alpha row
         const UttInfo ui = utt[b];
         const float lse2 = __ldg(lse_all + (size_t)b * d.T + t);
         const float gy = gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss);
@@ -261,10 +268,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         const float c = -lse2;
 
         float blank_part = 0.f;
-        for (int j = lane; j < ui.Nb; j += 32) {
-            const float e = ex2_approx(e_sm[j]);
-            e_sm[j] = e;
-            if (j % per == 0) blank_part += e;
+        for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
+            const int j = j0 + lane;
+            float e = 0.f;
+            if (j < ui.Nb) {
+                const float2 a = a_sm[j], bb = b_sm[j];
+                e = ex2_approx(((a.x + bb.x) - ui.Ph) + ((a.y + bb.y) - ui.Pl));         // 2^gamma
+            }
+            __syncwarp();                                                    // e_sm aliases the alpha row: reads first
+            if (j < ui.Nb) e_sm[j] = e;
+            if (j < ui.Nb && j % per == 0) blank_part += e;
         }
         blank_part = warp_sum(blank_part);
         __syncwarp();
@@ -305,25 +318,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     if (lane == 0) bulk_wait_all<0>();
 }
 
-__global__ void __launch_bounds__(256) loss_sum_kernel(const float *loss, int B, float *out) {
-    __shared__ double part[256];
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < B; i += 256) acc += (double)loss[i];
-    part[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *out = (float)part[0];
-}
-
 }  // namespace
-
-cudaError_t launch_loss_sum(const float *loss_per_utt, int B, float *loss_sum, cudaStream_t stream) {
-    loss_sum_kernel<<<1, 256, 0, stream>>>(loss_per_utt, B, loss_sum);
-    return cudaGetLastError();
-}
 
 cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream) {
     const long long frames = (long long)g.d.B * g.d.T;
@@ -331,7 +326,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
     unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
     const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
     const size_t extra = sizeof(float) * ((size_t)g.d.V + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
-    const RingLayout rl = make_ring(sizeof(float) * ((size_t)g.d.V + (size_t)w.Np), extra);
+    const RingLayout rl = make_ring(sizeof(float) * ((size_t)g.d.V + 4 * (size_t)w.Np), extra);
     if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
         ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl)) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;

@@ -13,9 +13,6 @@ struct ProblemDesc {
     const int32_t *labels, *bigrams, *input_lengths, *label_lengths;
 };
 
-// kernel 0: per-utterance bookkeeping (lengths, distinct-symbol CSR for the gradient kernel)
-cudaError_t launch_prep(const ProblemDesc &d, const WsLayout &w, void *ws, cudaStream_t stream);
-
 // kernel 1: fused log-softmax statistics + label gather (+ optional greedy argmax)
 cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
                                   cudaStream_t stream);
@@ -27,21 +24,19 @@ struct RingLayout;
 bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl);
 int sm_count();
 
-// kernel 2: alpha/beta lattice recursion
+// kernel 2: alpha/beta lattice recursion (+ symbol-table CTAs, + batch loss reduction by the last CTA)
 struct LatticeParams {
-    const int32_t *labels, *bigrams;
-    int B, T, Lmax, W, Np, C;
-    UttInfo *utt;
-    const float2 *lp;
-    float2 *fv;
-    float *gam;
-    float *loss_per_utt;
+    ProblemDesc d;
+    WsLayout w;
+    unsigned char *ws;
+    float *loss_per_utt;     // (B)
+    float *loss_reduced;     // (1): loss_scale * sum_b loss_b
+    float loss_scale;
+    int W;                   // warps per direction
+    int S;                   // pipeline stages
 };
 int lattice_max_nodes(int kind);
-cudaError_t launch_lattice(int kind, LatticeParams p, int Nmax, cudaStream_t stream, int *status);
-
-// loss_sum = sum_b loss_per_utt[b], fixed-order tree (deterministic)
-cudaError_t launch_loss_sum(const float *loss_per_utt, int B, float *loss_sum, cudaStream_t stream);
+cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status);
 
 // kernel 3: fused gradient
 struct GradParams {

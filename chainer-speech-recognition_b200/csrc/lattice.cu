@@ -10,65 +10,110 @@
 //            reversed type 0 (blank): q, q-1, q-5        type 1 (bigram): q, q-1, q-2, q-6*
 //                     type 2 (unigram): q, q-2, q-3*, q-7          (* = only if the two ids differ)
 //
-// Mapping: one CTA per utterance, two warps.  Warp 0 runs alpha forward in time, warp 1 runs beta
-// backward in time on the reversed lattice; each lane owns K consecutive nodes in registers, so a
-// step needs no barrier and no shared-memory round trip for the state: only the 2 (CTC) or 7
-// (Gram-CTC) boundary values come from the neighbouring lane by warp shuffle.  The per-frame rows
-// of gathered label log-probs are staged in shared memory by 1-D bulk async copies (TMA engine)
-// several frames ahead, completion tracked by mbarriers.
+// Mapping.  One CTA per utterance, 2*W warps: warps [0,W) run alpha forward in time, warps [W,2W)
+// run beta backward in time on the reversed lattice.  Within a direction warp w owns nodes
+// [w*32K, (w+1)*32K), K consecutive nodes per lane, all state in registers.  The recursion is a chain
+// of dependent instructions per node, so it is bound by the issue rate of a single warp (ncu: IPC 0.5,
+// stall = fixed-latency "wait"); K is therefore kept small (2 for CTC, 3 for Gram-CTC) and the lattice is
+// spread over several warps, i.e. several SM sub-partitions issue in parallel.
+//   * inside a warp the 2 (CTC) / 7 (Gram) boundary values come from the lower lanes by warp shuffle;
+//   * between warps they travel through shared memory, and the warps run as a systolic pipeline at
+//     chunk granularity (8 frames): warp w works on chunk c while warp w+1 works on chunk c-1 or c-2,
+//     reading the per-frame boundary values warp w left behind.  Hand-over is by mbarrier, once per
+//     chunk, so no step ever waits on a CTA-wide barrier;
+//   * the per-frame rows of gathered label log-probs are staged in shared memory by 1-D bulk async
+//     copies (TMA engine) issued by the direction's first warp two chunks ahead.
 //
-// Meet in the middle: alpha visits frames 0..mid first, beta visits frames T-1..mid first, each
-// writing its values ("first visitor", array fv).  After one CTA barrier log P is known
-// (sum over nodes of alpha_mid * beta_mid) and each warp continues over the other half as "second
-// visitor": it reads the first visitor's row (again staged by bulk copy) and writes
-// gamma[t][j] = alpha_t[j] + beta_t[j] - log P directly.  Every (frame, node) cell is therefore
-// written once by each direction and the gradient kernel reads one float per cell.
+// Both directions run the full utterance: alpha writes av[t][j] = alpha_t[j], beta writes bv[t][j] = beta_t[j],
+// as split-log2 pairs.  log P is read off alpha at the last frame.  The gradient kernel forms
+// gamma = alpha + beta - log P itself while it merges the per-symbol posteriors, so the recursion carries no
+// "combine" work at all (an earlier meet-in-the-middle version that wrote gamma directly spent 40-90% more
+// cycles per step on the second half).
 //
 // beta convention as in the reference (:171-175): beta_t EXCLUDES the emission at t, so
 // alpha_t + beta_t sums (in the log-sum-exp sense) to log P at every valid frame.
+//
+// The same launch carries B extra CTAs that build the gradient kernel's symbol tables (prep.cuh) while
+// the recursion runs, and the last lattice CTA to finish reduces the batch loss in a fixed order.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "prep.cuh"
 
 namespace b200ctc {
 
+__device__ long long *g_lat_dbg = nullptr;   // profiling hook (tools/lattice_timeline.py): per-warp cycle breakdown
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
 namespace {
 
-constexpr int kStages = 3;
+constexpr int kChunk = 8;        // frames per pipeline chunk
+constexpr int kMaxAhead = 2;     // chunks of emission rows in flight ahead of the first warp
+constexpr int kMaxStages = 8;
+constexpr int kMaxWarpsPerDir = 16;
+
+// CTC, reversed direction: the lattice is indexed with one phantom node in front (q = 0 <-> j = Nb, never
+// reachable), i.e. q <-> j = Nb - q.  That flips the slot parity (slot 0 = label, slot 1 = blank) and makes each
+// lane's two nodes an ALIGNED pair (j even, j+1) in memory, so the beta rows are written with the same single
+// 16-byte store per lane as the alpha rows.
+template <int K, bool GRAM, bool REV>
+struct Shifted {
+    static constexpr bool value = REV && !GRAM && K == 2;
+};
+
+template <int K, bool GRAM>
+struct Geo {
+    static constexpr int PAD = GRAM ? 7 : 2;                 // how far back a node's predecessors reach
+    static constexpr int EXT = K + PAD;
+};
 
 template <int K, bool GRAM>
 struct LaneState {
     float h[K], l[K];        // split-log2 value of the K nodes this lane owns
     int ci[K];               // column of each node's symbol in the emission row (0 = blank)
-    uint64_t flag;           // bit r: the "ids differ" edge into slot r is open
-    uint64_t dead;           // bit r: dead node (bigram id -1, gram_ctc.py:94-98)
-    uint64_t valid;          // bit r: node index < Nb
+    uint32_t flag;           // bit r: the "ids differ" edge into slot r is open
+    uint32_t dead;           // bit r: dead node (bigram id -1, gram_ctc.py:94-98)
+    uint32_t valid;          // bit r: node index < Nb
 };
 
-struct Pipe {
-    uint64_t *bar;           // [kStages]
-    float2 *lp;              // [kStages][C][W]
-    float2 *fv;              // [kStages][C][Np]
-    uint32_t parity;         // bit s: parity to wait for on stage s
+// shared-memory view of one direction's pipeline (32-bit shared-space addresses: no generic-pointer
+// conversion inside the recursion loop)
+struct DirPipe {
+    uint32_t lp;             // [S][kChunk][Wlp] float2   staged emission rows
+    uint32_t bnd;            // [W-1][S][kChunk][PAD] float2 boundary values handed from warp w to warp w+1;
+                             //   as deep as the stage ring, so a buffer is free by the time it comes round again
+                             //   (a warp can only be at chunk c once every warp has consumed chunk c-S)
+    uint64_t *full;          // [S]     emission rows of a chunk have landed (tx count)
+    uint64_t *consumed;      // [S]     all W warps are done with the stage
+    uint64_t *ready;         // [W-1][S] warp w finished the chunk: its boundary values can be read
 };
+
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
 
 struct UttCtx {
-    const float2 *lp_g;      // this utterance's emission rows   [T][W]
-    float2 *fv_g;            // first-visitor rows               [T][Np]
-    float *gam_g;            // gamma rows                       [T][Np]
-    int W, Np, C, Nb;
-    float Ph, Pl;
+    const float2 *lp_g;      // this utterance's emission rows   [T][Wlp]
+    float2 *out_g;           // this direction's output rows     [T][Np]
+    int Wlp, Np, Nb, W, S;
 };
 
-// ---- one lattice step: new (pre-emission) value of slot r from the extended old array ----
-// eh/el hold nodes [K*lane - PAD, K*lane + K); index PAD + r is slot r itself.
+// ---- one lattice step: new (pre-emission) value of slot R from the extended old array ----
+// eh/el hold nodes [K*gl - PAD, K*gl + K) for this lane; index PAD + R is slot R itself.
 template <int K, bool GRAM, bool REV, int R>
-__device__ __forceinline__ void slot_update(const float (&eh)[K + (GRAM ? 7 : 2)], const float (&el)[K + (GRAM ? 7 : 2)],
-                                            uint64_t flag, uint64_t dead, float &pre_h, float &pre_l) {
-    constexpr int PAD = GRAM ? 7 : 2;
+__device__ __forceinline__ void slot_update(const float (&eh)[Geo<K, GRAM>::EXT], const float (&el)[Geo<K, GRAM>::EXT],
+                                            uint32_t flag, uint32_t dead, float &pre_h, float &pre_l) {
+    constexpr int PAD = Geo<K, GRAM>::PAD;
     constexpr int I = PAD + R;
-    const bool open = (flag >> R) & 1ull;
+    const bool open = (flag >> R) & 1u;
     if constexpr (!GRAM) {
-        if constexpr ((R & 1) == 0) {                         // blank node: self, q-1
+        constexpr bool SH = Shifted<K, GRAM, REV>::value;
+        if constexpr (((R & 1) == 0) != SH) {                 // blank node: self, q-1
             const float hm = fmaxf(eh[I], eh[I - 1]);
             const float d0 = (eh[I] - hm) + el[I];
             const float d1 = (eh[I - 1] - hm) + el[I - 1];
@@ -82,6 +127,9 @@ __device__ __forceinline__ void slot_update(const float (&eh)[K + (GRAM ? 7 : 2)
             const float d2 = (h2 - hm) + el[I - 2];
             pre_h = hm;
             pre_l = lg2_approx(ex2_approx(d0) + ex2_approx(d1) + ex2_approx(d2));
+            if constexpr (SH && R == 0) {                     // the phantom node in front of the reversed lattice
+                if (dead & 1u) { pre_h = SENT; pre_l = 0.f; }
+            }
         }
     } else {
         constexpr int TYPE = R % 3;
@@ -106,58 +154,28 @@ __device__ __forceinline__ void slot_update(const float (&eh)[K + (GRAM ? 7 : 2)
         // a bigram node sits at type 2 forward / type 1 reversed
         constexpr bool CAN_BE_DEAD = (!REV && TYPE == 2) || (REV && TYPE == 1);
         if constexpr (CAN_BE_DEAD) {
-            if ((dead >> R) & 1ull) { pre_h = SENT; pre_l = 0.f; }
+            if ((dead >> R) & 1u) { pre_h = SENT; pre_l = 0.f; }
         }
     }
 }
 
-template <int K, bool GRAM, bool REV, bool SECOND, int R>
-struct SlotLoop {
-    __device__ __forceinline__ static void run(LaneState<K, GRAM> &st, const float (&eh)[K + (GRAM ? 7 : 2)],
-                                               const float (&el)[K + (GRAM ? 7 : 2)], const float2 *lprow,
-                                               const float2 *fvrow, float2 *fv_out, float *gam_out, int jbase,
-                                               float Ph, float Pl, bool store) {
-        float ph, pl;
-        slot_update<K, GRAM, REV, R>(eh, el, st.flag, st.dead, ph, pl);
-        const float2 e = lprow[st.ci[R]];
-        // post-emission value, renormalised so that hi stays integer-valued and |lo| <= 0.5
-        float nl = pl + e.y;
-        float nh = ph + e.x;
-        const float rr = rint_small(nl);
-        nh += rr;
-        nl -= rr;
-        st.h[R] = nh;
-        st.l[R] = nl;
-        // node index in forward coordinates
-        const int j = REV ? (jbase - R) : (jbase + R);
-        const bool ok = (st.valid >> R) & 1ull;
-        // alpha keeps the emission at t, beta excludes it (gram_ctc.py:171-175)
-        const float vh = REV ? ph : nh;
-        const float vl = REV ? pl : nl;
-        if constexpr (!SECOND) {
-            if (ok && store) fv_out[j] = make_float2(vh, vl);
-        } else {
-            if (ok) {
-                const float2 o = fvrow[j];
-                gam_out[j] = ((vh + o.x) - Ph) + ((vl + o.y) - Pl);
-            }
-        }
-        if constexpr (R + 1 < K)
-            SlotLoop<K, GRAM, REV, SECOND, R + 1>::run(st, eh, el, lprow, fvrow, fv_out, gam_out, jbase, Ph, Pl, store);
-    }
-};
-
+// Old values of the PAD nodes below this lane's first node: from lower lanes by shuffle, or -- for the first
+// BACK lanes of a warp -- from the previous warp's boundary record (SENT if there is no previous warp).
+// Branch-free: every lane reads a (clamped) boundary slot and the right source is picked by select.
 template <int K, bool GRAM>
-__device__ __forceinline__ void gather_neighbours(const LaneState<K, GRAM> &st, float (&eh)[K + (GRAM ? 7 : 2)],
-                                                  float (&el)[K + (GRAM ? 7 : 2)], int lane) {
-    constexpr int PAD = GRAM ? 7 : 2;
+__device__ __forceinline__ void gather_ext(const LaneState<K, GRAM> &st, float (&eh)[Geo<K, GRAM>::EXT],
+                                           float (&el)[Geo<K, GRAM>::EXT], int lane, bool has_prev, uint32_t bnd_in) {
+    constexpr int PAD = Geo<K, GRAM>::PAD;
 #pragma unroll
-    for (int k = 0; k < PAD; ++k) {
-        // node K*lane - PAD + k lives in the previous lane's slot K - PAD + k
-        float nh = __shfl_up_sync(0xffffffffu, st.h[K - PAD + k], 1);
-        float nl = __shfl_up_sync(0xffffffffu, st.l[K - PAD + k], 1);
-        eh[k] = (lane == 0) ? SENT : nh;
-        el[k] = (lane == 0) ? 0.f : nl;
+    for (int e = 0; e < PAD; ++e) {
+        const int delta = (PAD - e + K - 1) / K;              // lanes back (compile-time after unrolling)
+        const int slot = e - PAD + K * delta;
+        const float2 bv = lds_f2(bnd_in + 8u * (uint32_t)min(K * lane + e, PAD - 1));
+        const float nh = __shfl_up_sync(0xffffffffu, st.h[slot], delta);
+        const float nl = __shfl_up_sync(0xffffffffu, st.l[slot], delta);
+        const bool edge = lane < delta;
+        eh[e] = edge ? (has_prev ? bv.x : SENT) : nh;
+        el[e] = edge ? (has_prev ? bv.y : 0.f) : nl;
     }
 #pragma unroll
     for (int r = 0; r < K; ++r) {
@@ -166,72 +184,173 @@ __device__ __forceinline__ void gather_neighbours(const LaneState<K, GRAM> &st, 
     }
 }
 
-// Visit n frames starting at f0 (ascending for alpha, descending for beta).
-template <int K, bool GRAM, bool REV, bool SECOND>
-__device__ __forceinline__ void run_phase(LaneState<K, GRAM> &st, Pipe &pipe, const UttCtx &c, int f0, int n,
-                                       bool store_last, int lane) {
+template <int K, bool GRAM, bool REV, int R>
+struct SlotLoop {
+    __device__ __forceinline__ static void run(LaneState<K, GRAM> &st, const float (&eh)[Geo<K, GRAM>::EXT],
+                                               const float (&el)[Geo<K, GRAM>::EXT], uint32_t lprow, float2 (&outv)[K]) {
+        float ph, pl;
+        slot_update<K, GRAM, REV, R>(eh, el, st.flag, st.dead, ph, pl);
+        const float2 e = lds_f2(lprow + 8u * (uint32_t)st.ci[R]);
+        // post-emission value, renormalised so that hi stays integer-valued and |lo| <= 0.5
+        float nl = pl + e.y;
+        float nh = ph + e.x;
+        const float rr = rint_small(nl);
+        nh += rr;
+        nl -= rr;
+        st.h[R] = nh;
+        st.l[R] = nl;
+        // alpha keeps the emission at t, beta excludes it (gram_ctc.py:171-175)
+        outv[R] = REV ? make_float2(ph, pl) : make_float2(nh, nl);
+        if constexpr (R + 1 < K) SlotLoop<K, GRAM, REV, R + 1>::run(st, eh, el, lprow, outv);
+    }
+};
+
+// Write this lane's K results of one frame.  out points at the lane's first node (REV: walks downwards).
+// Partial 32-byte sectors are poison here: the output lines are never resident in L2 when first written, so a
+// half-written sector costs a DRAM fill.  For the CTC layout (K = 2) every lane therefore writes one aligned
+// 16-byte pair (see Shifted<> for how the reversed direction gets aligned pairs too).
+template <int K, bool GRAM, bool REV>
+__device__ __forceinline__ void store_results(const float2 (&outv)[K], float2 *out, uint32_t store_mask, int lane) {
+    if constexpr (!GRAM && K == 2) {
+        if constexpr (!REV) {
+            // nodes (2gl, 2gl+1): aligned; the odd partner of the last valid node falls into the row padding
+            if (store_mask & 1u) *reinterpret_cast<float4 *>(out) = make_float4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
+        } else {
+            // shifted reversed indexing: slot 1 = node j (even), slot 0 = node j+1; out points at node j
+            if (store_mask & 2u) *reinterpret_cast<float4 *>(out) = make_float4(outv[1].x, outv[1].y, outv[0].x, outv[0].y);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < K; ++r)
+            if ((store_mask >> r) & 1u) out[REV ? -r : r] = outv[r];
+    }
+}
+
+// one frame of the recursion for this lane
+template <int K, bool GRAM, bool REV>
+__device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, bool has_prev, bool has_next,
+                                             uint32_t bin, uint32_t bout, uint32_t lprow, float2 *out) {
+    constexpr int PAD = Geo<K, GRAM>::PAD;
+    float eh[Geo<K, GRAM>::EXT], el[Geo<K, GRAM>::EXT];
+    gather_ext<K, GRAM>(st, eh, el, lane, has_prev, bin);
+    // leave my last PAD nodes' old values for warp w+1 (predicated stores, no branch)
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        const int idx = K * lane + r - (32 * K - PAD);
+        if (has_next && idx >= 0) sts_f2(bout + 8u * (uint32_t)idx, st.h[r], st.l[r]);
+    }
+    float2 outv[K];
+    SlotLoop<K, GRAM, REV, 0>::run(st, eh, el, lprow, outv);
+    store_results<K, GRAM, REV>(outv, out, st.valid, lane);
+}
+
+// Visit n frames starting at f0 (ascending for alpha, descending for beta) with warp w of W.
+template <int K, bool GRAM, bool REV>
+__device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirPipe &pp, const UttCtx &c, int f0, int n,
+                                              int w, int lane) {
+    constexpr int PAD = Geo<K, GRAM>::PAD;
     if (n <= 0) return;
-    const int C = c.C;
-    const int nchunks = (n + C - 1) / C;
-    const uint32_t row_lp_bytes = (uint32_t)c.W * 8u;
-    const uint32_t row_fv_bytes = (uint32_t)c.Np * 8u;
+    const int W = c.W, S = c.S;
+    const int kAhead = min(kMaxAhead, S - 1);
+    const int nchunks = (n + kChunk - 1) / kChunk;
+    const bool leader = (w == 0);
+    const bool has_prev = (w > 0), has_next = (w + 1 < W);
+    const uint32_t row_bytes = (uint32_t)c.Wlp * 8u;
+    const uint32_t stage_bytes = row_bytes * kChunk;
+    const uint32_t bnd_chunk_bytes = kChunk * PAD * 8u;
+    const int gl = 32 * w + lane;                             // lane index within the direction
+    const int jbase = REV ? (c.Nb - 1 - K * gl) : (K * gl);
+    const int64_t frame_step = REV ? -(int64_t)c.Np : (int64_t)c.Np;
+    float2 *out_ptr = c.out_g + (size_t)f0 * c.Np + jbase;    // this lane's first node in frame f0
 
-    auto issue = [&](int chunk) {
-        const int s = chunk % kStages;
-        const int i0 = chunk * C;
-        const int cnt = min(C, n - i0);
+    // leader bookkeeping: next chunk to issue, its stage and how often that stage has been used
+    int is_chunk = 0, is_stage = 0;
+    uint32_t is_wrap = 0;
+    auto issue = [&]() {                                      // leader, lane 0
+        const int i0 = is_chunk * kChunk;
+        const int cnt = min(kChunk, n - i0);
         const int flo = REV ? (f0 - i0 - cnt + 1) : (f0 + i0);
-        if (lane == 0) {
-            const uint32_t bl = row_lp_bytes * cnt;
-            const uint32_t bf = SECOND ? row_fv_bytes * cnt : 0u;
-            mbar_arrive_expect_tx(&pipe.bar[s], bl + bf);
-            bulk_g2s(pipe.lp + (size_t)s * C * c.W, c.lp_g + (size_t)flo * c.W, bl, &pipe.bar[s]);
-            if (SECOND) bulk_g2s(pipe.fv + (size_t)s * C * c.Np, c.fv_g + (size_t)flo * c.Np, bf, &pipe.bar[s]);
-        }
+        if (is_wrap > 0) mbar_wait(&pp.consumed[is_stage], (is_wrap - 1) & 1u);
+        mbar_arrive_expect_tx(&pp.full[is_stage], row_bytes * cnt);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pp.lp + (uint32_t)is_stage * stage_bytes),
+                     "l"(c.lp_g + (size_t)flo * c.Wlp), "r"(row_bytes * cnt), "r"(smem_u32(&pp.full[is_stage]))
+                     : "memory");
+        ++is_chunk;
+        if (++is_stage == S) { is_stage = 0; ++is_wrap; }
     };
+    if (leader && lane == 0)
+        for (int ch = 0; ch < min(kAhead, nchunks); ++ch) issue();
 
-    for (int ch = 0; ch < min(kStages, nchunks); ++ch) issue(ch);
-
-    const int jbase = REV ? (c.Nb - 1 - K * lane) : (K * lane);
+    int stage = 0;
+    uint32_t wrap = 0;
+    long long acc_ready = 0, acc_issue = 0, acc_full = 0, acc_work = 0, acc_tail = 0;
+    const bool prof = (g_lat_dbg != nullptr) && lane == 0 && blockIdx.x < 64;
     for (int ch = 0; ch < nchunks; ++ch) {
-        const int s = ch % kStages;
-        const int i0 = ch * C;
-        const int cnt = min(C, n - i0);
-        mbar_wait(&pipe.bar[s], (pipe.parity >> s) & 1u);
-        pipe.parity ^= (1u << s);
-        const float2 *lp_s = pipe.lp + (size_t)s * C * c.W;
-        const float2 *fv_s = pipe.fv + (size_t)s * C * c.Np;
-        for (int i = 0; i < cnt; ++i) {
-            const int row = REV ? (cnt - 1 - i) : i;
-            const int f = REV ? (f0 - i0 - i) : (f0 + i0 + i);
-            float eh[K + (GRAM ? 7 : 2)], el[K + (GRAM ? 7 : 2)];
-            gather_neighbours<K, GRAM>(st, eh, el, lane);
-            const bool store = store_last || (i0 + i + 1 < n);
-            SlotLoop<K, GRAM, REV, SECOND, 0>::run(st, eh, el, lp_s + (size_t)row * c.W, fv_s + (size_t)row * c.Np,
-                                                   c.fv_g + (size_t)f * c.Np, c.gam_g + (size_t)f * c.Np, jbase, c.Ph,
-                                                   c.Pl, store);
+        const int cnt = min(kChunk, n - ch * kChunk);
+        long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+        if (prof) tq0 = clock64();
+        if (has_prev) mbar_wait_backoff(&pp.ready[(w - 1) * S + stage], wrap & 1u);
+        if (prof) tq1 = clock64();
+        if (leader && lane == 0 && is_chunk < nchunks) issue();
+        if (prof) tq2 = clock64();
+        mbar_wait(&pp.full[stage], wrap & 1u);
+        if (prof) { tq3 = clock64(); acc_ready += tq1 - tq0; acc_issue += tq2 - tq1; acc_full += tq3 - tq2; }
+
+        const uint32_t lp_s = pp.lp + (uint32_t)stage * stage_bytes;
+        const uint32_t bin = pp.bnd + (uint32_t)((has_prev ? w - 1 : 0) * S + stage) * bnd_chunk_bytes;
+        const uint32_t bout = pp.bnd + (uint32_t)((has_next ? w : 0) * S + stage) * bnd_chunk_bytes;
+        if (cnt == kChunk) {                                  // full chunk: straight-line code, no per-step branch
+#pragma unroll
+            for (int i = 0; i < kChunk; ++i) {
+                const int row = REV ? (kChunk - 1 - i) : i;
+                lattice_step<K, GRAM, REV>(st, lane, has_prev, has_next, bin + i * PAD * 8u, bout + i * PAD * 8u,
+                                           lp_s + (uint32_t)row * row_bytes, out_ptr + i * frame_step);
+            }
+        } else {                                              // last, partial chunk
+#pragma unroll 1
+            for (int i = 0; i < cnt; ++i) {
+                const int row = REV ? (cnt - 1 - i) : i;
+                lattice_step<K, GRAM, REV>(st, lane, has_prev, has_next, bin + i * PAD * 8u, bout + i * PAD * 8u,
+                                           lp_s + (uint32_t)row * row_bytes, out_ptr + i * frame_step);
+            }
         }
+        out_ptr += kChunk * frame_step;
+        if (prof) { tq4 = clock64(); acc_work += tq4 - tq3; }
         __syncwarp();
-        if (ch + kStages < nchunks) issue(ch + kStages);
+        if (lane == 0) {
+            if (has_next) mbar_arrive(&pp.ready[w * S + stage]);
+            mbar_arrive(&pp.consumed[stage]);
+        }
+        if (++stage == S) { stage = 0; ++wrap; }
+        if (prof) acc_tail += clock64() - tq4;
+    }
+    if (prof) {
+        long long *o = g_lat_dbg + ((size_t)blockIdx.x * 32 + (REV ? 16 : 0) + w) * 8;
+        o[0] = acc_ready; o[1] = acc_issue; o[2] = acc_full; o[3] = acc_work; o[4] = acc_tail; o[5] = nchunks;
+        o[6] = gtime();
     }
 }
 
 template <int K, bool GRAM>
-__device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const LatticeParams &p, int b, int Lb, int Nb,
-                                          bool rev, int lane) {
-    const int32_t *lab = p.labels + (size_t)b * p.Lmax;
-    const int32_t *big = GRAM ? p.bigrams + (size_t)b * p.Lmax : nullptr;
-    st.flag = 0ull;
-    st.dead = 0ull;
-    st.valid = 0ull;
+__device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const ProblemDesc &d, int b, int Lb, int Nb,
+                                          bool rev, int gl) {
+    const int32_t *lab = d.labels + (size_t)b * d.Lmax;
+    const int32_t *big = GRAM ? d.bigrams + (size_t)b * d.Lmax : nullptr;
+    const bool shifted = rev && !GRAM && K == 2;         // see Shifted<>
+    st.flag = 0u;
+    st.dead = 0u;
+    st.valid = 0u;
 #pragma unroll
     for (int r = 0; r < K; ++r) {
-        const int q = K * lane + r;
-        const int j = rev ? (Nb - 1 - q) : q;            // forward node index
-        const bool ok = (q < Nb);
-        st.h[r] = (q == 0) ? 0.f : SENT;                 // virtual state: all mass on node 0 (gram_ctc.py:144)
+        const int q = K * gl + r;
+        const int j = rev ? (shifted ? Nb - q : Nb - 1 - q) : q;       // forward node index
+        const bool ok = shifted ? (q >= 1 && q <= Nb) : (q < Nb);
+        const int q_start = shifted ? 1 : 0;
+        st.h[r] = (q == q_start) ? 0.f : SENT;           // virtual state: all mass on the first node (gram_ctc.py:144)
         st.l[r] = 0.f;
-        if (ok) st.valid |= (1ull << r);
+        if (ok) st.valid |= (1u << r);
+        if (shifted && q == 0) st.dead |= 1u;
         int ci = 0;
         if (ok) {
             if constexpr (!GRAM) {
@@ -241,7 +360,7 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const LatticeP
                     bool open;
                     if (!rev) open = (i >= 1) && (lab[i] != lab[i - 1]);
                     else open = (i + 1 < Lb) && (lab[i + 1] != lab[i]);
-                    if (open) st.flag |= (1ull << r);
+                    if (open) st.flag |= (1u << r);
                 }
             } else {
                 const int i = j / 3, type = j % 3;
@@ -250,14 +369,14 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const LatticeP
                     bool open;
                     if (!rev) open = (i >= 1) && (lab[i] != lab[i - 1]);
                     else open = (i + 1 < Lb) && (lab[i + 1] != lab[i]);
-                    if (open) st.flag |= (1ull << r);
+                    if (open) st.flag |= (1u << r);
                 } else if (type == 2) {
-                    ci = 1 + p.Lmax + i;
+                    ci = 1 + d.Lmax + i;
                     bool open;
                     if (!rev) open = (i >= 2) && (big[i] != big[i - 2]);
                     else open = (i + 2 < Lb) && (big[i + 2] != big[i]);
-                    if (open) st.flag |= (1ull << r);
-                    if (big[i] == -1) st.dead |= (1ull << r);
+                    if (open) st.flag |= (1u << r);
+                    if (big[i] == -1) st.dead |= (1u << r);
                 }
             }
         }
@@ -265,159 +384,199 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const LatticeP
     }
 }
 
-template <int K, bool GRAM>
-__global__ void __launch_bounds__(64, 1) lattice_kernel(LatticeParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int b = blockIdx.x;
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    UttInfo *ui = p.utt + b;
-    const int Tb = ui->Tb, Lb = ui->Lb, Nb = ui->Nb;
+struct SmemPlan {
+    size_t lp_elems, bnd_elems;      // float2 elements per direction
+    size_t off_bars, off_red, total;
+    int nbars_dir;
+};
 
-    // shared memory carve-up: per direction [kStages][C][W] + [kStages][C][Np] float2, then barriers, then P
-    const size_t lp_elems = (size_t)kStages * p.C * p.W;
-    const size_t fv_elems = (size_t)kStages * p.C * p.Np;
-    float2 *base = reinterpret_cast<float2 *>(smem_raw);
-    Pipe pipe;
-    pipe.lp = base + (size_t)warp * (lp_elems + fv_elems);
-    pipe.fv = pipe.lp + lp_elems;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + 2 * (lp_elems + fv_elems));
-    pipe.bar = bars + warp * kStages;
-    pipe.parity = 0u;
-    float *pshare = reinterpret_cast<float *>(bars + 2 * kStages);
+__host__ __device__ inline SmemPlan plan_smem(int Wlp, int W, int S, int PAD) {
+    SmemPlan p;
+    p.lp_elems = (size_t)S * kChunk * Wlp;
+    p.bnd_elems = (size_t)(W > 1 ? W - 1 : 1) * S * kChunk * PAD;
+    p.bnd_elems = (p.bnd_elems + 1) & ~(size_t)1;                      // keep 16-byte alignment of what follows
+    p.nbars_dir = 2 * S + S * (W > 1 ? W - 1 : 0);
+    size_t o = 2 * (p.lp_elems + p.bnd_elems) * sizeof(float2);
+    p.off_bars = align_up(o, 16);
+    o = p.off_bars + 2 * (size_t)p.nbars_dir * sizeof(uint64_t);
+    p.off_red = o;
+    o += (2 * kMaxWarpsPerDir + 4) * sizeof(float);
+    p.total = o;
+    return p;
+}
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * kStages; ++i) mbar_init(&bars[i], 1);
-        mbar_init_fence();
-    }
-    __syncthreads();
-
-    if (Tb <= 0) {                                       // no frames: P = 1 iff there is nothing to emit
-        if (threadIdx.x == 0) {
-            const bool feas = (Lb == 0);
-            ui->Ph = feas ? 0.f : -SENT;
-            ui->Pl = 0.f;
-            ui->loss = feas ? 0.f : 1e10f;
-            ui->flags |= feas ? 0 : 2;
-            p.loss_per_utt[b] = ui->loss;
+__device__ __forceinline__ void init_barriers(uint64_t *bars, int nbars_dir, int S, int W) {
+    // per direction: full[S] (1 arrival + tx), consumed[S] (W arrivals), ready[(W-1)*S] (1 arrival)
+    for (int dir = 0; dir < 2; ++dir) {
+        uint64_t *b = bars + dir * nbars_dir;
+        for (int i = 0; i < nbars_dir; ++i) {
+            const bool is_consumed = (i >= S && i < 2 * S);
+            mbar_init(&b[i], is_consumed ? (uint32_t)W : 1u);
         }
+    }
+    mbar_init_fence();
+}
+
+// MAXW bounds the warps per direction of an instantiation, so that small lattices (the common case) are not
+// compiled under the 64-register cap a 1024-thread CTA implies.
+template <int K, bool GRAM, int MAXW>
+__global__ void __launch_bounds__(64 * MAXW, 1) lattice_kernel(LatticeParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int PAD = Geo<K, GRAM>::PAD;
+    const ProblemDesc &d = p.d;
+    if ((int)blockIdx.x >= d.B) {                          // ---- symbol-table CTAs (prep.cuh) ----
+        prep_utterance(d, p.w, p.ws, (int)blockIdx.x - d.B, reinterpret_cast<int *>(smem_raw));
         return;
     }
+    const int b = blockIdx.x;
+    const int W = p.W, S = p.S;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int dir = warp >= W ? 1 : 0;
+    const int w = warp - dir * W;
+    UttInfo *ui = reinterpret_cast<UttInfo *>(p.ws + p.w.off_utt) + b;
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(p.ws + p.w.off_hdr);
 
-    UttCtx c;
-    c.lp_g = p.lp + (size_t)b * p.T * p.W;
-    c.fv_g = p.fv + (size_t)b * p.T * p.Np;
-    c.gam_g = p.gam + (size_t)b * p.T * p.Np;
-    c.W = p.W; c.Np = p.Np; c.C = p.C; c.Nb = Nb;
-    c.Ph = 0.f; c.Pl = 0.f;
+    int Tb = d.input_lengths ? d.input_lengths[b] : d.T;
+    int Lb = d.label_lengths ? d.label_lengths[b] : d.Lmax;
+    Tb = max(0, min(Tb, d.T));
+    Lb = max(0, min(Lb, d.Lmax));
+    const int Nb = (GRAM ? 3 : 2) * Lb + 1;
 
-    const int mid = (Tb - 1) >> 1;
-    LaneState<K, GRAM> st;
-    init_lane<K, GRAM>(st, p, b, Lb, Nb, warp == 1, lane);
+    const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);
+    float2 *f2base = reinterpret_cast<float2 *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + sp.off_bars);
+    float *red = reinterpret_cast<float *>(smem_raw + sp.off_red);
+    DirPipe pp;
+    pp.lp = smem_u32(f2base + (size_t)dir * (sp.lp_elems + sp.bnd_elems));
+    pp.bnd = pp.lp + (uint32_t)(sp.lp_elems * sizeof(float2));
+    pp.full = bars + dir * sp.nbars_dir;
+    pp.consumed = pp.full + S;
+    pp.ready = pp.consumed + S;
 
-    // ---- phase A: first visitors ----
-    if (warp == 0) run_phase<K, GRAM, false, false>(st, pipe, c, 0, mid + 1, /*store_last=*/false, lane);
-    else           run_phase<K, GRAM, true, false>(st, pipe, c, Tb - 1, Tb - mid, /*store_last=*/true, lane);
-    fence_proxy_async();
+    if (threadIdx.x == 0) init_barriers(bars, sp.nbars_dir, S, W);
+    __syncthreads();
+
+    float2 *av = reinterpret_cast<float2 *>(p.ws + p.w.off_av) + (size_t)b * d.T * p.w.Np;
+    float2 *bv = reinterpret_cast<float2 *>(p.ws + p.w.off_bv) + (size_t)b * d.T * p.w.Np;
+    if (Tb > 0) {
+        UttCtx c;
+        c.lp_g = reinterpret_cast<const float2 *>(p.ws + p.w.off_lp) + (size_t)b * d.T * p.w.W;
+        c.out_g = dir == 0 ? av : bv;
+        c.Wlp = p.w.W; c.Np = p.w.Np; c.Nb = Nb; c.W = W; c.S = S;
+        LaneState<K, GRAM> st;
+        init_lane<K, GRAM>(st, d, b, Lb, Nb, dir == 1, 32 * w + lane);
+        if (dir == 0) run_direction<K, GRAM, false>(st, pp, c, 0, Tb, w, lane);         // alpha: frames 0 .. Tb-1
+        else          run_direction<K, GRAM, true>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
+    }
     __threadfence_block();
     __syncthreads();
 
-    // ---- log P at the meeting frame: LSE_j(alpha_mid[j] + beta_mid[j]) ----
-    if (warp == 0) {
-        const float2 *brow = c.fv_g + (size_t)mid * p.Np;
-        float bh[K], bl[K];
-        float pm = SENT;
-#pragma unroll
-        for (int r = 0; r < K; ++r) {
-            const int j = K * lane + r;
-            float2 o = make_float2(SENT, 0.f);
-            if (j < Nb) o = __ldcg(brow + j);
-            bh[r] = o.x; bl[r] = o.y;
-            pm = fmaxf(pm, st.h[r] + o.x);
-        }
-        pm = warp_max(pm);
-        float s = 0.f;
-#pragma unroll
-        for (int r = 0; r < K; ++r) s += ex2_approx(((st.h[r] + bh[r]) - pm) + (st.l[r] + bl[r]));
-        s = warp_sum(s);
-        const bool feas = (pm > SENT_TEST) && (s > 0.f);
-        float Ph, Pl;
-        if (feas) {
-            const float lg = log2f(s);
-            const float rr = rintf(lg);
-            Ph = pm + rr;
-            Pl = lg - rr;
+    // ---- log P = LSE of alpha over the final nodes at the last frame (gram_ctc.py:279; SURVEY 8a "end") ----
+    if (threadIdx.x == 0) {
+        float loss;
+        bool feas;
+        float Ph = -SENT, Pl = 0.f;                       // +1e30: every gamma becomes log 0
+        if (Tb <= 0) {                                   // no frames: P = 1 iff there is nothing to emit
+            feas = (Lb == 0);
+            if (feas) Ph = 0.f;
+            loss = feas ? 0.f : 1e10f;
         } else {
-            Ph = -SENT;                                  // +1e30: every gamma becomes log 0
-            Pl = 0.f;
+            const float2 *last = av + (size_t)(Tb - 1) * p.w.Np;
+            const int nfin = GRAM ? 3 : 2;
+            float fh[3], fl[3];
+            float pm = SENT;
+            for (int i = 0; i < 3; ++i) { fh[i] = SENT; fl[i] = 0.f; }
+            for (int i = 0; i < nfin; ++i) {
+                const int j = Nb - 1 - i;
+                if (j >= 0) { const float2 v = __ldcg(last + j); fh[i] = v.x; fl[i] = v.y; }
+                pm = fmaxf(pm, fh[i]);
+            }
+            double sum = 0.0;
+            for (int i = 0; i < nfin; ++i)
+                if (fh[i] > SENT_TEST) sum += exp2((double)(fh[i] - pm) + (double)fl[i]);
+            feas = (pm > SENT_TEST) && (sum > 0.0);
+            if (feas) {
+                const double lg = log2(sum);
+                const double total = (double)pm + lg;    // log2 P
+                const double rr = rint(total);
+                Ph = (float)rr;
+                Pl = (float)(total - rr);
+                loss = (float)(-total * LN2_D);
+            } else {
+                loss = 1e10f;                            // what the reference returns
+            }
         }
-        // gamma at the meeting frame
-#pragma unroll
-        for (int r = 0; r < K; ++r) {
-            const int j = K * lane + r;
-            if (j < Nb) c.gam_g[(size_t)mid * p.Np + j] = ((st.h[r] + bh[r]) - Ph) + ((st.l[r] + bl[r]) - Pl);
-        }
-        if (lane == 0) {
-            pshare[0] = Ph;
-            pshare[1] = Pl;
-            const float loss = feas ? (float)(-((double)Ph + (double)Pl) * LN2_D) : 1e10f;
-            ui->Ph = Ph;
-            ui->Pl = Pl;
-            ui->loss = loss;
-            if (!feas) ui->flags |= 2;
-            p.loss_per_utt[b] = loss;
-        }
+        ui->Ph = Ph; ui->Pl = Pl; ui->loss = loss; ui->infeasible = feas ? 0 : 1;
+        p.loss_per_utt[b] = loss;
+        // ---- the last CTA reduces the batch in a fixed order (gram_ctc.py:280-281) ----
+        __threadfence();
+        const unsigned done = atomicAdd(&hdr->k2_done, 1u) + 1u;
+        red[0] = (done == (unsigned)d.B) ? 1.f : 0.f;
     }
     __syncthreads();
-    c.Ph = pshare[0];
-    c.Pl = pshare[1];
-    fence_proxy_async();
+    if (red[0] != 0.f && warp == 0) {
+        __threadfence();
+        double acc = 0.0;
+        for (int i = lane; i < d.B; i += 32) acc += (double)__ldcg(p.loss_per_utt + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) *p.loss_reduced = (float)(acc * (double)p.loss_scale);
+    }
+}
 
-    // ---- phase B: second visitors ----
-    if (warp == 0) run_phase<K, GRAM, false, true>(st, pipe, c, mid + 1, Tb - 1 - mid, true, lane);
-    else           run_phase<K, GRAM, true, true>(st, pipe, c, mid - 1, mid, true, lane);
+template <int K, bool GRAM, int MAXW>
+cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
+    auto kern = lattice_kernel<K, GRAM, MAXW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<2 * p.d.B, 64 * p.W, smem, stream>>>(p);
+    return cudaGetLastError();
 }
 
 template <int K, bool GRAM>
 cudaError_t launch_one(const LatticeParams &p, size_t smem, cudaStream_t stream) {
-    auto kern = lattice_kernel<K, GRAM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<p.B, 64, smem, stream>>>(p);
-    return cudaGetLastError();
+    if (p.W <= 4) return launch_w<K, GRAM, 4>(p, smem, stream);
+    if (p.W <= 8) return launch_w<K, GRAM, 8>(p, smem, stream);
+    return launch_w<K, GRAM, kMaxWarpsPerDir>(p, smem, stream);
 }
+
+constexpr size_t kLatticeSmemBudget = 224 * 1024;
 
 }  // namespace
 
-int lattice_max_nodes(int kind) { return kind == 0 ? 32 * 24 : 32 * 36; }
+void lattice_set_debug(long long *p) { cudaMemcpyToSymbol(g_lat_dbg, &p, sizeof(p)); }
 
-cudaError_t launch_lattice(int kind, LatticeParams p, int Nmax, cudaStream_t stream, int *status) {
+int lattice_max_nodes(int kind) { return kind == 0 ? 32 * 4 * kMaxWarpsPerDir : 32 * 6 * kMaxWarpsPerDir; }
+
+cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
     *status = 0;
-    // chunk length: as many frames per bulk copy as fit ~96 KB per direction, at most 16
-    const size_t per_frame = (size_t)(p.W + p.Np) * sizeof(float2);
-    int C = (int)((size_t)(100 * 1024) / ((size_t)kStages * per_frame));
-    if (C > 16) C = 16;
-    if (C < 1) { *status = 2; return cudaSuccess; }
-    p.C = C;
-    const size_t smem = 2 * (size_t)kStages * C * per_frame + 2 * kStages * sizeof(uint64_t) + 16;
-    const int need = (Nmax + 31) / 32;
+    const int kind = p.d.kind;
+    const int Nmax = p.w.Nmax;
+    // nodes per lane: as few as possible (the recursion is issue-bound per warp), more only when the
+    // lattice would not fit 16 warps per direction
+    int K;
+    if (kind == 0) K = (Nmax <= 32 * 2 * kMaxWarpsPerDir) ? 2 : 4;
+    else K = (Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6;
+    if (const char *e = getenv("B200CTC_K")) K = atoi(e);          // experiment knob
+    const int W = (Nmax + (kind == 0 && K == 2 ? 1 : 0) + 32 * K - 1) / (32 * K);   // +1: phantom node (Shifted<>)
+    if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
+    const int PAD = kind == 0 ? 2 : 7;
+    int S = kMaxStages;
+    while (S > 2 && plan_smem(p.w.W, W, S, PAD).total > kLatticeSmemBudget) --S;
+    const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);
+    if (sp.total > kLatticeSmemBudget) { *status = 2; return cudaSuccess; }
+    size_t smem = sp.total;
+    const size_t prep = prep_smem_bytes(kind, p.d.Lmax, p.w.nwords);
+    if (prep > smem) smem = prep;
+    if (smem > 227 * 1024) { *status = 2; return cudaSuccess; }
+    p.W = W; p.S = S;
     if (kind == 0) {
-        if (need <= 2) return launch_one<2, false>(p, smem, stream);
-        if (need <= 4) return launch_one<4, false>(p, smem, stream);
-        if (need <= 6) return launch_one<6, false>(p, smem, stream);
-        if (need <= 8) return launch_one<8, false>(p, smem, stream);
-        if (need <= 12) return launch_one<12, false>(p, smem, stream);
-        if (need <= 16) return launch_one<16, false>(p, smem, stream);
-        if (need <= 24) return launch_one<24, false>(p, smem, stream);
-    } else {
-        if (need <= 9) return launch_one<9, true>(p, smem, stream);
-        if (need <= 12) return launch_one<12, true>(p, smem, stream);
-        if (need <= 18) return launch_one<18, true>(p, smem, stream);
-        if (need <= 24) return launch_one<24, true>(p, smem, stream);
-        if (need <= 36) return launch_one<36, true>(p, smem, stream);
+        if (K == 6) return launch_one<6, false>(p, smem, stream);
+        if (K == 8) return launch_one<8, false>(p, smem, stream);
+        return K == 2 ? launch_one<2, false>(p, smem, stream) : launch_one<4, false>(p, smem, stream);
     }
-    *status = 2;
-    return cudaSuccess;
+    return K == 3 ? launch_one<3, true>(p, smem, stream) : launch_one<6, true>(p, smem, stream);
 }
 
 }  // namespace b200ctc

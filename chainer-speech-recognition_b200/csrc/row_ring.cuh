@@ -84,10 +84,6 @@ __device__ __forceinline__ Ring ring_setup(unsigned char *smem, const RingLayout
     return r;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // Producer side: claim the slot for row sequence number q (waits until its previous occupant was released).
 __device__ __forceinline__ int ring_claim(const Ring &r, unsigned q) {
     const int s = (int)(q % (unsigned)r.slots);

@@ -1,5 +1,4 @@
-// softmax_gather.cu -- kernel 0 (per-utterance bookkeeping) and kernel 1 (fused log-softmax
-// statistics + label gather + optional greedy argmax).
+// softmax_gather.cu -- kernel 1: fused log-softmax statistics + label gather + optional greedy argmax.
 //
 // Replaces, in the reference (asr/loss/gram_ctc.py):
 //   _softmax :18-21 and _log_matrix :48-57 over the whole (T,B,V) tensor (two extra 717 MB arrays at
@@ -20,109 +19,6 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kUnroll = 4;
-
-// ---------------------------------------------------------------------------------------------
-// kernel 0: per-utterance bookkeeping for the gradient kernel -- which vocabulary ids can the lattice
-// emit, and which nodes share an id (the merge of _compute_label_probability, gram_ctc.py:180-217).
-// One CTA per utterance.  Output, per utterance:
-//   usym[u]            distinct emitted ids, sorted ascending, blank included (Ub of them)
-//   uoff[u]..uoff[u+1] range in unode[] listing the non-blank-type nodes that carry id usym[u]
-//                      (the blank-type nodes -- every 2nd / 3rd node -- are summed directly)
-//   bm[], pc[]         V-bit bitmap of emitted ids and, per 32-bit word, the number of set bits before it,
-//                      so that "posterior slot of column k" = pc[k/32] + popc(bm[k/32] & low bits).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) prep_kernel(ProblemDesc d, WsLayout w, unsigned char *ws) {
-    extern __shared__ int sm[];
-    __shared__ int s_U;
-    const int b = blockIdx.x;
-    UttInfo *ui = reinterpret_cast<UttInfo *>(ws + w.off_utt) + b;
-    int *usym = reinterpret_cast<int *>(ws + w.off_usym) + (size_t)b * w.Nmax;
-    int *uoff = reinterpret_cast<int *>(ws + w.off_uoff) + (size_t)b * (w.Nmax + 1);
-    int *unode = reinterpret_cast<int *>(ws + w.off_unode) + (size_t)b * w.Nmax;
-    unsigned *bm_g = reinterpret_cast<unsigned *>(ws + w.off_bm) + (size_t)b * w.nwords;
-    int *pc_g = reinterpret_cast<int *>(ws + w.off_pc) + (size_t)b * w.nwords;
-
-    int Tb = d.input_lengths ? d.input_lengths[b] : d.T;
-    int Lb = d.label_lengths ? d.label_lengths[b] : d.Lmax;
-    int flags = 0;
-    if (Tb < 0 || Tb > d.T) { flags |= 1; Tb = max(0, min(Tb, d.T)); }
-    if (Lb < 0 || Lb > d.Lmax) { flags |= 1; Lb = max(0, min(Lb, d.Lmax)); }
-    const int per = d.kind == 0 ? 2 : 3;
-    const int Nb = per * Lb + 1;
-    // entry 0 = the blank id itself; entries 1..M = the non-blank-type nodes in node order
-    // (CTC: label i -> node 2i+1; Gram: unigram i -> node 3i+1, bigram i -> node 3i+2).
-    const int M = (per - 1) * Lb;
-    const int E = M + 1;
-    int *esym = sm;               // [E] symbol (or -1)
-    int *efirst = sm + E;         // [E] first entry with the same symbol
-    int *epos = sm + 2 * E;       // [E] number of earlier node entries with the same symbol
-    int *erank = sm + 3 * E;      // [E] sorted position of a first entry's symbol
-    int *cnt = sm + 4 * E;        // [E] node-list length per distinct symbol
-    unsigned *bm = reinterpret_cast<unsigned *>(sm + 5 * E);   // [nwords]
-    const int32_t *lab = d.labels + (size_t)b * d.Lmax;
-    const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)b * d.Lmax : nullptr;
-    if (threadIdx.x == 0) s_U = 0;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        int s;
-        if (e == 0) s = d.blank;
-        else if (d.kind == 0) s = lab[e - 1];
-        else s = ((e - 1) & 1) ? big[(e - 1) >> 1] : lab[(e - 1) >> 1];
-        if (s < 0 || s >= d.V) s = -1;                     // dead bigram (or an id outside the vocabulary)
-        esym[e] = s;
-        cnt[e] = 0;
-    }
-    for (int i = threadIdx.x; i < w.nwords; i += blockDim.x) bm[i] = 0u;
-    __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        const int s = esym[e];
-        int first = e, pos = 0;
-        bool found = false;
-        if (s >= 0) {
-            for (int e2 = 0; e2 < e; ++e2)
-                if (esym[e2] == s) {
-                    if (!found) { first = e2; found = true; }
-                    if (e2 >= 1) ++pos;
-                }
-        }
-        efirst[e] = first;
-        epos[e] = pos;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        const int s = esym[e];
-        if (s < 0 || efirst[e] != e) continue;
-        int r = 0;
-        for (int e2 = 0; e2 < E; ++e2)
-            if (esym[e2] >= 0 && efirst[e2] == e2 && esym[e2] < s) ++r;
-        erank[e] = r;
-        usym[r] = s;
-        atomicAdd(&s_U, 1);
-        atomicOr(&bm[s >> 5], 1u << (s & 31));
-    }
-    __syncthreads();
-    for (int e = 1 + threadIdx.x; e < E; e += blockDim.x)
-        if (esym[e] >= 0) atomicAdd(&cnt[erank[efirst[e]]], 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int U = s_U;
-        int acc = 0;
-        for (int u = 0; u < U; ++u) { uoff[u] = acc; acc += cnt[u]; }
-        uoff[U] = acc;
-        ui->Tb = Tb; ui->Lb = Lb; ui->Nb = Nb; ui->Ub = U;
-        ui->flags = flags; ui->ublank = erank[0]; ui->pad = 0;
-    }
-    if (threadIdx.x == 32) {
-        int acc = 0;
-        for (int i = 0; i < w.nwords; ++i) { pc_g[i] = acc; bm_g[i] = bm[i]; acc += __popc(bm[i]); }
-    }
-    __syncthreads();
-    for (int e = 1 + threadIdx.x; e < E; e += blockDim.x) {
-        if (esym[e] < 0) continue;
-        const int en = e - 1;
-        const int node = d.kind == 0 ? (2 * en + 1) : (3 * (en >> 1) + 1 + (en & 1));
-        unode[uoff[erank[efirst[e]]] + epos[e]] = node;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel 1
@@ -477,17 +373,6 @@ int grid_for_frames(long long frames) {
 }
 
 }  // namespace
-
-cudaError_t launch_prep(const ProblemDesc &d, const WsLayout &w, void *ws, cudaStream_t stream) {
-    const int per = d.kind == 0 ? 1 : 2;
-    const size_t smem = sizeof(int) * (5 * ((size_t)per * d.Lmax + 1) + (size_t)w.nwords);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    prep_kernel<<<d.B, 128, smem, stream>>>(d, w, static_cast<unsigned char *>(ws));
-    return cudaGetLastError();
-}
 
 bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl) {
     if (getenv("B200CTC_NO_TMA")) return false;

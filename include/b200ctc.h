@@ -63,8 +63,9 @@ int b200ctc_workspace_bytes(int kind, int B, int T, int V, int Lmax, size_t *byt
  * Forward: replaces GramCTC.forward (gram_ctc.py:246-282) / Chainer's CTC forward.
  *   loss_per_utt  (B) float32, out: -log P(labels_b | x_b); exactly 1e10 for an infeasible
  *                 alignment (what the reference returns).
- *   loss_sum      (1) float32, out: sum_b loss_per_utt[b] (the caller divides by the GLOBAL batch
- *                 size for reduce='mean', gram_ctc.py:281, after its all-reduce across ranks).
+ *   loss_reduced  (1) float32, out: loss_scale * sum_b loss_per_utt[b], summed in a fixed order.
+ *                 reduce='mean' (gram_ctc.py:281): loss_scale = 1 / B_global; on several GPUs the
+ *                 caller all-reduces (sum) this one float across ranks.
  *   argmax_out    (B,T) int64 or NULL: greedy indices over the raw activations, first maximum
  *                 wins, NaN counts as maximal (numpy.argmax semantics, run/ctc/cnn/train.py:232).
  *   bigrams       NULL for kind == B200CTC_KIND_CTC.
@@ -74,7 +75,7 @@ int b200ctc_forward(int kind,
                     const int32_t *labels, const int32_t *bigrams,
                     const int32_t *input_lengths, const int32_t *label_lengths,
                     int blank, int B, int T, int V, int Lmax,
-                    float *loss_per_utt, float *loss_sum, int64_t *argmax_out,
+                    float *loss_per_utt, float *loss_reduced, float loss_scale, int64_t *argmax_out,
                     void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
 
 /*
