@@ -14,6 +14,11 @@ using namespace b200ctc;
 
 namespace {
 
+// zeroes the workspace header (ticket counters) in stream order
+__global__ void zero_header_kernel(WsHeader *h) {
+    if (threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
+}
+
 thread_local char g_err[512] = "";
 
 int fail(int code, const char *fmt, const char *a = "", long long x = 0, long long y = 0) {
@@ -89,7 +94,8 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
     d.input_lengths = input_lengths; d.label_lengths = label_lengths;
 
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    if ((rc = check_cuda(cudaMemsetAsync(ws + w.off_hdr, 0, sizeof(WsHeader), stream), "workspace header memset"))) return rc;
+    zero_header_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<WsHeader *>(ws + w.off_hdr));
+    if ((rc = check_cuda(cudaGetLastError(), "workspace header reset"))) return rc;
     if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, stream), "softmax/gather kernel"))) return rc;
 
     LatticeParams lp;

@@ -11,6 +11,7 @@
 // One warp per frame, frames handed out by a ticket counter; 128-bit streaming loads/stores.  Which
 // columns carry a posterior is looked up in a per-utterance V-bit bitmap (1 word per 32 columns, L1
 // resident), so the correction happens in registers and every gradient element is written once.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "row_ring.cuh"
@@ -252,8 +253,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const int per = d.kind == 0 ? 2 : 3;
     const int n4 = d.V >> 2;
     for (unsigned q = (unsigned)(warp - 1);; q += kRingConsumers) {
-        const int s = (int)(q % (unsigned)ring.slots);
-        mbar_wait(&ring.full[s], (q / (unsigned)ring.slots) & 1u);
+        const int s = ring_acquire(ring, q);
         const RowMeta m = ring.meta[s];
         if (m.kind < 0) break;
         const int b = m.b, t = m.t;
@@ -328,7 +328,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
     const size_t extra = sizeof(float) * ((size_t)g.d.V + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
     const RingLayout rl = make_ring(sizeof(float) * ((size_t)g.d.V + 4 * (size_t)w.Np), extra);
     if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
-        ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl)) {
+        ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl) && !getenv("B200CTC_NO_TMA_K3")) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
         if (ctas > sm_count()) ctas = sm_count();
         cudaError_t e = cudaFuncSetAttribute(gradient_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);

@@ -558,7 +558,6 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
     int K;
     if (kind == 0) K = (Nmax <= 32 * 2 * kMaxWarpsPerDir) ? 2 : 4;
     else K = (Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6;
-    if (const char *e = getenv("B200CTC_K")) K = atoi(e);          // experiment knob
     const int W = (Nmax + (kind == 0 && K == 2 ? 1 : 0) + 32 * K - 1) / (32 * K);   // +1: phantom node (Shifted<>)
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
@@ -571,11 +570,7 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
     if (prep > smem) smem = prep;
     if (smem > 227 * 1024) { *status = 2; return cudaSuccess; }
     p.W = W; p.S = S;
-    if (kind == 0) {
-        if (K == 6) return launch_one<6, false>(p, smem, stream);
-        if (K == 8) return launch_one<8, false>(p, smem, stream);
-        return K == 2 ? launch_one<2, false>(p, smem, stream) : launch_one<4, false>(p, smem, stream);
-    }
+    if (kind == 0) return K == 2 ? launch_one<2, false>(p, smem, stream) : launch_one<4, false>(p, smem, stream);
     return K == 3 ? launch_one<3, true>(p, smem, stream) : launch_one<6, true>(p, smem, stream);
 }
 

@@ -31,6 +31,7 @@ struct RowMeta {
 };
 
 struct RingLayout {
+    int batch;             // frames per ticket (<= slots)
     int slots;             // R
     size_t slot_bytes;     // row (+ per-row extras), multiple of 128
     size_t off_meta, off_full, off_empty, off_extra, total;
@@ -43,6 +44,7 @@ __host__ __device__ inline RingLayout make_ring(size_t slot_payload, size_t extr
     long long n = ((long long)kRingSmemBudget - (long long)fixed) / (long long)r.slot_bytes;
     if (n > kMaxSlots) n = kMaxSlots;
     r.slots = (int)(n < 0 ? 0 : n);
+    r.batch = r.slots < kTicketBatch ? r.slots : kTicketBatch;
     size_t o = r.slot_bytes * (size_t)r.slots;
     r.off_meta = o;  o += sizeof(RowMeta) * kMaxSlots;
     r.off_full = o;  o += 8 * kMaxSlots;
@@ -71,7 +73,7 @@ __device__ __forceinline__ Ring ring_setup(unsigned char *smem, const RingLayout
     r.full = reinterpret_cast<uint64_t *>(smem + rl.off_full);
     r.empty = reinterpret_cast<uint64_t *>(smem + rl.off_empty);
     r.slots = rl.slots;
-    r.batch = rl.slots < kTicketBatch ? rl.slots : kTicketBatch;
+    r.batch = rl.batch;
     r.slot_bytes = rl.slot_bytes;
     if (threadIdx.x == 0) {
         for (int i = 0; i < rl.slots; ++i) {
@@ -89,6 +91,19 @@ __device__ __forceinline__ int ring_claim(const Ring &r, unsigned q) {
     const int s = (int)(q % (unsigned)r.slots);
     const unsigned n = q / (unsigned)r.slots;
     if (n > 0) mbar_wait(&r.empty[s], (n - 1) & 1u);
+    return s;
+}
+
+// Consumer side: wait until row sequence number q has landed in its slot; returns the slot.
+// A parity wait can only tell "this phase" from "the one before", and rows complete out of order (a batch is
+// issued by several lanes at once), so a fast consumer may get here while the slot's PREVIOUS occupant
+// (row q - slots) is still loading -- the parity of its own row would then alias to an older, completed phase.
+// Waiting first for the previous occupant's release pins the barrier to the right phase.
+__device__ __forceinline__ int ring_acquire(const Ring &r, unsigned q) {
+    const int s = (int)(q % (unsigned)r.slots);
+    const unsigned n = q / (unsigned)r.slots;
+    if (n > 0) mbar_wait(&r.empty[s], (n - 1) & 1u);
+    mbar_wait(&r.full[s], n & 1u);
     return s;
 }
 

@@ -273,8 +273,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
     float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
     const int n4 = d.V >> 2;
     for (unsigned q = (unsigned)(warp - 1);; q += kRingConsumers) {
-        const int s = (int)(q % (unsigned)ring.slots);
-        mbar_wait(&ring.full[s], (q / (unsigned)ring.slots) & 1u);
+        const int s = ring_acquire(ring, q);
         const RowMeta m = ring.meta[s];
         if (m.kind < 0) break;
         const float *row = reinterpret_cast<const float *>(ring.slot(s));
@@ -394,7 +393,7 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
     const int b_major = d.stride_b > d.stride_t ? 1 : 0;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
     const RingLayout rl = make_ring((size_t)d.V * 4, 0);
-    if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl)) {
+    if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) && !getenv("B200CTC_NO_TMA_K1")) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
         if (ctas > sm_count()) ctas = sm_count();
         cudaError_t e;
