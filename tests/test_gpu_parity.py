@@ -138,3 +138,84 @@ def test_greedy_argmax_bit_exact(pkg):
     prob = synth().ctc_problem(4, 50, 40, 8, seed=1)
     _, _, am = run_cuda(pkg, prob, "ctc", want_argmax=True)
     assert np.array_equal(am, np.argmax(prob["x"], axis=2).T)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors = outputs of the reference itself (tests/golden/generate_golden.py)
+# ---------------------------------------------------------------------------------------------
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference_golden(pkg, path):
+    z = np.load(path)
+    g = {k: z[k] for k in z.files}
+    kind = str(g["kind"])
+    prob = {"x": g["x"], "labels": g["labels"], "bigrams": g["bigrams"], "input_length": g["input_length"],
+            "label_length": g["label_length"], "blank": 0}
+    loss, grad, _ = run_cuda(pkg, prob, kind)
+    assert np.allclose(loss, g["ref_loss"], rtol=1e-5, atol=1e-5)
+    # the golden gradients carry the reference's own float32 noise on random logits
+    tol = 1e-5 if ("trained" in path or "wide" in path) else 5e-5
+    assert np.abs(grad - g["ref_grad"]).max() <= tol
+    lm, gm, _ = run_cuda(pkg, prob, kind, reduce="mean")
+    assert np.isclose(lm, g["ref_loss_mean"], rtol=1e-5)
+    assert np.abs(gm - g["ref_grad_mean"]).max() <= tol
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: direct comparison with the oracle plus size-independent properties
+# ---------------------------------------------------------------------------------------------
+def _properties(prob, loss, grad):
+    T, B, V = prob["x"].shape
+    for b in range(B):
+        Tb = int(prob["input_length"][b])
+        assert not grad[Tb:, b].any()                                   # exact zeros on padded frames
+    # softmax and the merged posteriors both sum to one over the vocabulary => every gradient row sums to ~0
+    rows = np.abs(grad.astype(np.float64).sum(axis=2))
+    assert rows.max() <= 2e-5, rows.max()
+    assert np.isfinite(loss).all() and (loss > 0).all()
+
+
+@pytest.mark.parametrize("trained", [False, True])
+def test_full_size_ctc_config(pkg, trained):
+    prob = synth().ctc_problem(64, 800, 3500, 80, seed=0, trained=trained)      # BASELINE configs[1]
+    loss, grad, am = run_cuda(pkg, prob, "ctc", want_argmax=True)
+    loss_ref, grad_ref, am_ref = run_oracle(prob, "ctc", want_argmax=True)
+    assert_parity(loss, grad, loss_ref, grad_ref, "cfg2")
+    assert np.array_equal(am, am_ref)                                           # bit-exact greedy indices
+    _properties(prob, loss, grad)
+
+
+def test_full_size_gram_config(pkg):
+    prob = synth().gram_problem(32, 600, 8000, 60, seed=0)                       # BASELINE configs[2]
+    loss, grad, _ = run_cuda(pkg, prob, "gram")
+    loss_ref, grad_ref, _ = run_oracle(prob, "gram")
+    assert_parity(loss, grad, loss_ref, grad_ref, "cfg3")
+    _properties(prob, loss, grad)
+
+
+@pytest.mark.parametrize("T,V", [(1600, 100), (3200, 100), (1600, 3500)])
+def test_long_utterance_sweep(pkg, T, V):
+    prob = synth().ctc_problem(4, T, V, T // 10, seed=1, trained=True)           # BASELINE configs[4] shapes
+    loss, grad, _ = run_cuda(pkg, prob, "ctc")
+    loss_ref, grad_ref, _ = run_oracle(prob, "ctc")
+    assert_parity(loss, grad, loss_ref, grad_ref, "sweep T=%d V=%d" % (T, V))
+    _properties(prob, loss, grad)
+
+
+def test_second_backward_over_the_same_graph(pkg):
+    """The reference mutates its saved softmax in backward (gram_ctc.py:290-296); here a retained graph can be
+    differentiated again and gives the same answer."""
+    import torch
+    prob = synth().ctc_problem(8, 200, 3500, 40, seed=3)
+    x = torch.tensor(prob["x"], device="cuda:0", requires_grad=True)
+    loss = pkg.ctc(x, torch.tensor(prob["labels"], device="cuda:0"), 0, torch.tensor(prob["input_length"], device="cuda:0"),
+                   torch.tensor(prob["label_length"], device="cuda:0"), reduce="mean")
+    loss.backward(retain_graph=True)
+    g1 = x.grad.clone(); x.grad = None
+    loss.backward()
+    assert torch.equal(g1, x.grad)
