@@ -252,10 +252,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     float *post_sm = post_all + (size_t)(warp - 1) * ((w.Umax + 3) & ~3);
     const int per = d.kind == 0 ? 2 : 3;
     const int n4 = d.V >> 2;
-    for (unsigned q = (unsigned)(warp - 1);; q += kRingConsumers) {
+    if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
+    for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
         const int s = ring_acquire(ring, q);
         const RowMeta m = ring.meta[s];
-        if (m.kind < 0) break;
+        if (m.kind < 0) {                       // stop record: hand the slot back (the ring may be shorter than
+            __syncwarp();                       // the number of consumers) and leave
+            if (lane == 0) mbar_arrive(&ring.empty[s]);
+            break;
+        }
         const int b = m.b, t = m.t;
         float *row = reinterpret_cast<float *>(ring.slot(s));
         const float2 *a_sm = reinterpret_cast<const float2 *>(row + d.V);       // alpha row

@@ -31,6 +31,7 @@ struct RowMeta {
 };
 
 struct RingLayout {
+    int consumers;         // active consumer warps = min(kRingConsumers, slots), see ring_acquire
     int batch;             // frames per ticket (<= slots)
     int slots;             // R
     size_t slot_bytes;     // row (+ per-row extras), multiple of 128
@@ -45,6 +46,7 @@ __host__ __device__ inline RingLayout make_ring(size_t slot_payload, size_t extr
     if (n > kMaxSlots) n = kMaxSlots;
     r.slots = (int)(n < 0 ? 0 : n);
     r.batch = r.slots < kTicketBatch ? r.slots : kTicketBatch;
+    r.consumers = r.slots < kRingConsumers ? r.slots : kRingConsumers;
     size_t o = r.slot_bytes * (size_t)r.slots;
     r.off_meta = o;  o += sizeof(RowMeta) * kMaxSlots;
     r.off_full = o;  o += 8 * kMaxSlots;
@@ -61,6 +63,7 @@ struct Ring {
     RowMeta *meta;
     uint64_t *full, *empty;
     int slots;
+    int nc;                // active consumers (<= slots)
     int batch;             // frames per ticket = min(kTicketBatch, slots): a batch never waits on its own rows
     size_t slot_bytes;
     __device__ __forceinline__ unsigned char *slot(int s) const { return base + (size_t)s * slot_bytes; }
@@ -74,6 +77,7 @@ __device__ __forceinline__ Ring ring_setup(unsigned char *smem, const RingLayout
     r.empty = reinterpret_cast<uint64_t *>(smem + rl.off_empty);
     r.slots = rl.slots;
     r.batch = rl.batch;
+    r.nc = rl.consumers;
     r.slot_bytes = rl.slot_bytes;
     if (threadIdx.x == 0) {
         for (int i = 0; i < rl.slots; ++i) {
@@ -98,7 +102,10 @@ __device__ __forceinline__ int ring_claim(const Ring &r, unsigned q) {
 // A parity wait can only tell "this phase" from "the one before", and rows complete out of order (a batch is
 // issued by several lanes at once), so a fast consumer may get here while the slot's PREVIOUS occupant
 // (row q - slots) is still loading -- the parity of its own row would then alias to an older, completed phase.
-// Waiting first for the previous occupant's release pins the barrier to the right phase.
+// Waiting first for the previous occupant's release pins the barrier to the right phase.  That wait is itself
+// only unambiguous if the occupant before THAT has been released, which holds because the number of active
+// consumers never exceeds the number of slots: consumer c reaches row q after finishing row q - nc, which was
+// issued only once every row up to q - nc - slots <= q - 2*slots had been released.
 __device__ __forceinline__ int ring_acquire(const Ring &r, unsigned q) {
     const int s = (int)(q % (unsigned)r.slots);
     const unsigned n = q / (unsigned)r.slots;
@@ -108,12 +115,17 @@ __device__ __forceinline__ int ring_acquire(const Ring &r, unsigned q) {
 }
 
 // Producer side (whole warp): tell every consumer to stop -- one stop record per consumer, in sequence order.
+// Issued by lane 0 one after the other: the ring may have fewer slots than consumers, in which case a stop
+// record can only be placed once an earlier one has been picked up (consumers release stop slots too).
 __device__ __forceinline__ void ring_stop(const Ring &r, unsigned q, int lane) {
-    if (lane < kRingConsumers) {
-        const int s = ring_claim(r, q + (unsigned)lane);
-        r.meta[s].kind = -1;
-        mbar_arrive(&r.full[s]);
+    if (lane == 0) {
+        for (int c = 0; c < r.nc; ++c) {
+            const int s = ring_claim(r, q + (unsigned)c);
+            r.meta[s].kind = -1;
+            mbar_arrive(&r.full[s]);
+        }
     }
+    __syncwarp();
 }
 
 // Producer side (whole warp): ticket handling.  Lane 0 keeps the *next* batch's ticket in flight in `pend`

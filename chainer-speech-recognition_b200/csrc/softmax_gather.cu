@@ -272,10 +272,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
     float *lse_out = reinterpret_cast<float *>(ws + w.off_lse);
     float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
     const int n4 = d.V >> 2;
-    for (unsigned q = (unsigned)(warp - 1);; q += kRingConsumers) {
+    if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
+    for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
         const int s = ring_acquire(ring, q);
         const RowMeta m = ring.meta[s];
-        if (m.kind < 0) break;
+        if (m.kind < 0) {                       // stop record: hand the slot back (the ring may be shorter than
+            __syncwarp();                       // the number of consumers) and leave
+            if (lane == 0) mbar_arrive(&ring.empty[s]);
+            break;
+        }
         const float *row = reinterpret_cast<const float *>(ring.slot(s));
         const float4 *row4 = reinterpret_cast<const float4 *>(row);
         // pass 1: maximum (and greedy index)
