@@ -8,10 +8,10 @@ The directory name is not a Python identifier; import it with
     asr/loss/ctc.py        connectionist_temporal_classification(...)   (reference: Chainer's, via run/ctc/*)
     csrc/                  sm_100a kernels + the C ABI (include/b200ctc.h)
 """
-from . import _lib
+from . import _lib, distributed, synth
 from ._build import build
 from .asr.loss import (gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
                        ConnectionistTemporalClassification, greedy_argmax)
 
 __all__ = ["gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
-           "ConnectionistTemporalClassification", "greedy_argmax", "build"]
+           "ConnectionistTemporalClassification", "greedy_argmax", "build", "distributed", "synth"]
