@@ -11,7 +11,7 @@ The directory name is not a Python identifier; import it with
 from . import _lib, distributed, synth
 from ._build import build
 from .asr.loss import (gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
-                       ConnectionistTemporalClassification, greedy_argmax)
+                       ConnectionistTemporalClassification, greedy_argmax, ctc_host, gram_ctc_host)
 
 __all__ = ["gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
-           "ConnectionistTemporalClassification", "greedy_argmax", "build", "distributed", "synth"]
+           "ConnectionistTemporalClassification", "greedy_argmax", "ctc_host", "gram_ctc_host", "build", "distributed", "synth"]

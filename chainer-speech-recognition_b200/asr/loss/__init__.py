@@ -3,3 +3,4 @@ plus plain CTC, which the reference takes from Chainer (``F.connectionist_tempor
 from .gram_ctc import gram_ctc, GramCTC                                      # noqa: F401
 from .ctc import connectionist_temporal_classification, ctc, ConnectionistTemporalClassification   # noqa: F401
 from ._function import greedy_argmax                                         # noqa: F401
+from .host import ctc_host, gram_ctc_host                                   # noqa: F401

@@ -222,3 +222,25 @@ def test_second_backward_over_the_same_graph(pkg):
     g1 = x.grad.clone(); x.grad = None
     loss.backward()
     assert torch.equal(g1, x.grad)
+
+
+def test_host_entry_point_matches_device_path(pkg):
+    """asr/loss/host.py: host arrays in, host gradient out, pipelined over utterance groups -- same numbers."""
+    import torch
+    for kind in ("ctc", "gram"):
+        s = synth()
+        prob = s.ctc_problem(9, 70, 200, 12, seed=5) if kind == "ctc" else s.gram_problem(9, 70, 200, 12, seed=5, n_unigram=40)
+        loss_ref, grad_ref, _ = run_oracle(prob, kind)
+        xb = np.ascontiguousarray(prob["x"].transpose(1, 0, 2))                      # (B,T,V)
+        if kind == "ctc":
+            loss, grad = pkg.ctc_host(xb, prob["labels"], 0, prob["input_length"], prob["label_length"], reduce="no", groups=4)
+            lm, gm = pkg.ctc_host(torch.from_numpy(xb).pin_memory(), prob["labels"], 0, prob["input_length"],
+                                  prob["label_length"], reduce="mean", groups=3)
+        else:
+            loss, grad = pkg.gram_ctc_host(xb, prob["labels"], prob["bigrams"], 0, prob["input_length"],
+                                           prob["label_length"], reduce="no", groups=4)
+            lm, gm = pkg.gram_ctc_host(xb, prob["labels"], prob["bigrams"], 0, prob["input_length"],
+                                       prob["label_length"], reduce="mean", groups=2)
+        assert_parity(loss, grad.numpy().transpose(1, 0, 2), loss_ref, grad_ref, "host " + kind)
+        assert abs(lm - loss_ref.mean()) <= 1e-5 * abs(loss_ref.mean())
+        assert np.abs(gm.numpy().transpose(1, 0, 2) - grad_ref / 9).max() <= 1e-5
