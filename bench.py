@@ -105,6 +105,15 @@ class ClockSampler(object):
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the CPU arm
+    should be limited to)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def algorithmic_bytes(V, in_len, B, T):
     """read activations once (softmax), once more (gradient), write the gradient once."""
     valid = int(np.sum(in_len))
@@ -135,7 +144,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     from oracle import c_oracle
-    threads = c_oracle.max_threads()
+    threads = host_threads()
     W = WORKLOAD
     sample_b = W["B"]
     prob = synth().ctc_problem(sample_b, W["T"], W["V"], W["L"], seed=0)
@@ -301,8 +310,7 @@ def main():
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import c_oracle
-        threads = c_oracle.max_threads()
+        threads = host_threads()
         v, secs, reps = cpu_baseline(prob, threads)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": "oracle C port (oracle/ctc_oracle.c, float64, OpenMP x%d): %d passes over the "

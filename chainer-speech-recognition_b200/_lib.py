@@ -34,6 +34,16 @@ def _bind(lib):
         c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p,
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_float,
         c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.b200ctc_fused_workspace_bytes.restype = c.c_int
+    lib.b200ctc_fused_workspace_bytes.argtypes = [c.c_int] * 6 + [c.POINTER(c.c_size_t)]
+    lib.b200ctc_forward_backward.restype = c.c_int
+    lib.b200ctc_forward_backward.argtypes = [
+        c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_float, c.c_float,
+        c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.b200ctc_rescale_grad.restype = c.c_int
+    lib.b200ctc_rescale_grad.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_int, c.c_int, c.c_void_p,
+                                         c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
     lib.b200ctc_greedy_argmax.restype = c.c_int
     lib.b200ctc_greedy_argmax.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_int, c.c_int,
                                           c.c_void_p, c.c_void_p]
@@ -77,6 +87,12 @@ def check(status):
         import torch
         raise torch.cuda.OutOfMemoryError(msg)
     raise B200CTCError(msg)
+
+
+def fused_workspace_bytes(kind, B, T, V, Lmax, groups):
+    out = ctypes.c_size_t(0)
+    check(load().b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, groups, ctypes.byref(out)))
+    return int(out.value)
 
 
 def workspace_bytes(kind, B, T, V, Lmax):

@@ -7,11 +7,23 @@ with torch so that CUDA OOM surfaces as ``torch.cuda.OutOfMemoryError`` (the cal
 CuPy equivalent to shrink the batch, run/ctc/cnn/train.py:204-211).
 """
 import collections.abc
+import os
 
 import numpy as np
 import torch
 
 from ... import _lib
+
+
+def pipeline_groups(B):
+    """Utterance groups of the pipelined forward+gradient path (0 = the separate forward / backward calls).
+    Off by default: measured on B200 it does not pay yet (0.49-0.60 ms vs 0.47 ms per step at B=64,T=800,V=3500)
+    because the persistent row-streaming CTAs of one group occupy every SM and the lattice CTAs of another
+    cannot start next to them.  B200CTC_GROUPS=1..8 turns it on."""
+    env = os.environ.get("B200CTC_GROUPS")
+    if env is not None:
+        return max(0, min(8, min(int(env), B)))
+    return 0
 
 
 def _stream_ptr(device):
@@ -66,21 +78,36 @@ class LatticeLossFunction(torch.autograd.Function):
         T, B, V = acts.shape
         Lmax = labels.shape[1]
         dev = acts.device
-        nbytes = _lib.workspace_bytes(kind, B, T, V, Lmax)
-        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
         loss_b = torch.empty(B, dtype=torch.float32, device=dev)
         loss_red = torch.empty((), dtype=torch.float32, device=dev)
         loss_scale = 1.0 / float(batch_global) if reduce == "mean" else 1.0     # gram_ctc.py:280-281
         argmax = torch.empty((B, T), dtype=torch.int64, device=dev) if want_argmax else None
-        with torch.cuda.device(dev):
-            _lib.check(lib.b200ctc_forward(
-                kind, acts.data_ptr(), acts.stride(0), acts.stride(1),
-                labels.data_ptr(), bigrams.data_ptr() if bigrams is not None else None,
-                input_length.data_ptr() if input_length is not None else None,
-                label_length.data_ptr() if label_length is not None else None,
-                blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(), loss_scale,
-                argmax.data_ptr() if argmax is not None else None,
-                workspace.data_ptr(), workspace.numel(), 0, _stream_ptr(dev)))
+        groups = pipeline_groups(B) if (ctx.needs_input_grad[0] and not want_argmax) else 0
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        if groups > 0:
+            # training step: loss and gradient in one pipelined call (include/b200ctc.h, b200ctc_forward_backward)
+            grad = torch.empty_like(acts)
+            if grad.stride(2) != 1:
+                grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
+            nbytes = _lib.fused_workspace_bytes(kind, B, T, V, Lmax, groups)
+            workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.b200ctc_forward_backward(
+                    kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
+                    ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
+                    loss_scale, loss_scale, grad.data_ptr(), grad.stride(0), grad.stride(1), groups,
+                    workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
+            ctx.fused_grad = grad
+        else:
+            nbytes = _lib.workspace_bytes(kind, B, T, V, Lmax)
+            workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.b200ctc_forward(
+                    kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
+                    ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
+                    loss_scale, ptr(argmax), workspace.data_ptr(), workspace.numel(), 0, _stream_ptr(dev)))
+            ctx.fused_grad = None
+        ctx.groups, ctx.backward_calls = groups, 0
         ctx.kind, ctx.blank, ctx.reduce, ctx.dims = kind, blank, reduce, (B, T, V, Lmax)
         ctx.batch_global = batch_global
         ctx.save_for_backward(acts, labels, bigrams if bigrams is not None else labels, workspace)
@@ -108,16 +135,40 @@ class LatticeLossFunction(torch.autograd.Function):
         gy = gy.to(device=dev, dtype=torch.float32).contiguous()
         per_utt = 0 if ctx.reduce == "mean" else 1
         scale = 1.0 / float(ctx.batch_global) if ctx.reduce == "mean" else 1.0     # :291-294
+        ctx.backward_calls += 1
+        big_ptr = bigrams.data_ptr() if ctx.has_bigrams else None
+        if ctx.groups > 0 and ctx.backward_calls == 1:
+            # the gradient was produced at forward time for a unit upstream gradient: apply gy (no-op if it is 1)
+            grad, ctx.fused_grad = ctx.fused_grad, None          # hand over ownership: autograd may keep it as x.grad
+            with torch.cuda.device(dev):
+                _lib.check(lib.b200ctc_rescale_grad(grad.data_ptr(), grad.stride(0), grad.stride(1), B, T, V,
+                                                    gy.data_ptr(), per_utt, ctx.groups, ctx.kind, Lmax,
+                                                    workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
+            return (grad,) + (None,) * 10
         grad = torch.empty_like(acts)
         if grad.stride(2) != 1:
             grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.b200ctc_backward(
-                ctx.kind, acts.data_ptr(), acts.stride(0), acts.stride(1),
-                labels.data_ptr(), bigrams.data_ptr() if ctx.has_bigrams else None,
-                ctx.blank, B, T, V, Lmax, gy.data_ptr(), per_utt, scale,
-                grad.data_ptr(), grad.stride(0), grad.stride(1),
-                workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
+            if ctx.groups > 0:
+                # a retained graph differentiated again: each group's slice of the workspace is a regular workspace
+                nb = (B + ctx.groups - 1) // ctx.groups
+                gbytes = (_lib.workspace_bytes(ctx.kind, nb, T, V, Lmax) + 255) // 256 * 256
+                for g in range(min(ctx.groups, B)):
+                    b0 = g * nb
+                    n = min(nb, B - b0)
+                    if n <= 0:
+                        continue
+                    a, gr = acts[:, b0:b0 + n], grad[:, b0:b0 + n]
+                    _lib.check(lib.b200ctc_backward(
+                        ctx.kind, a.data_ptr(), a.stride(0), a.stride(1), labels[b0:b0 + n].data_ptr(),
+                        bigrams[b0:b0 + n].data_ptr() if ctx.has_bigrams else None, ctx.blank, n, T, V, Lmax,
+                        gy[b0:b0 + n].data_ptr() if per_utt else gy.data_ptr(), per_utt, scale, gr.data_ptr(),
+                        gr.stride(0), gr.stride(1), workspace.data_ptr() + g * gbytes, gbytes, _stream_ptr(dev)))
+            else:
+                _lib.check(lib.b200ctc_backward(
+                    ctx.kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), big_ptr,
+                    ctx.blank, B, T, V, Lmax, gy.data_ptr(), per_utt, scale, grad.data_ptr(), grad.stride(0),
+                    grad.stride(1), workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
         return (grad,) + (None,) * 10
 
 

@@ -19,6 +19,55 @@ __global__ void zero_header_kernel(WsHeader *h) {
     if (threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
 }
 
+// gradient *= gy / applied, in place, skipped entirely when the ratio is 1 (the usual loss.backward()):
+// used by the pipelined path, which computes the gradient with a unit upstream gradient at forward time.
+__global__ void rescale_grad_kernel(float *grad, int64_t stride_t, int64_t stride_b, int B, int T, int V,
+                                    const float *gy, int per_utterance, float *applied) {
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float want = per_utterance ? gy[b] : gy[0];
+        const float have = applied[per_utterance ? b : 0];
+        if (want == have) continue;
+        const float r = want / have;
+        for (int t = blockIdx.x; t < T; t += gridDim.x) {
+            float *row = grad + (int64_t)t * stride_t + (int64_t)b * stride_b;
+            for (int v = threadIdx.x; v < V; v += blockDim.x) row[v] *= r;
+        }
+    }
+}
+__global__ void rescale_commit_kernel(const float *gy, int per_utterance, int B, float *applied) {
+    const int n = per_utterance ? B : 1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) applied[i] = gy[i];
+}
+__global__ void fill_ones_kernel(float *p, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 1.f;
+}
+__global__ void sum_partials_kernel(const float *partials, int n, float *out) {
+    if (threadIdx.x == 0) { double a = 0.0; for (int i = 0; i < n; ++i) a += (double)partials[i]; *out = (float)a; }
+}
+
+constexpr int kMaxGroups = 8;
+struct StreamPool {
+    int device = -1;
+    cudaStream_t s[kMaxGroups] = {};
+    cudaEvent_t fork = nullptr, join[kMaxGroups] = {};
+};
+StreamPool g_pool[16];
+
+StreamPool *get_pool() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    StreamPool &p = g_pool[dev];
+    if (p.device != dev) {
+        for (int i = 0; i < kMaxGroups; ++i) {
+            if (cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        p.device = dev;
+    }
+    return &p;
+}
+
 thread_local char g_err[512] = "";
 
 int fail(int code, const char *fmt, const char *a = "", long long x = 0, long long y = 0) {
@@ -125,6 +174,106 @@ int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stri
     g.grad_loss = grad_loss; g.per_utterance = per_utterance; g.scale = scale;
     g.grad_out = grad_out; g.gstride_t = gstride_t; g.gstride_b = gstride_b;
     return check_cuda(launch_gradient(g, w, workspace, static_cast<cudaStream_t>(stream_)), "gradient kernel");
+}
+
+size_t fused_group_bytes(int kind, int B, int T, int V, int Lmax, int groups) {
+    const int nb = (B + groups - 1) / groups;
+    return align_up(make_layout(kind, nb, T, V, Lmax).total, 256);
+}
+
+int b200ctc_fused_workspace_bytes(int kind, int B, int T, int V, int Lmax, int groups, size_t *bytes_out) {
+    if (!bytes_out) return fail(B200CTC_INVALID_ARGUMENT, "bytes_out is NULL%s");
+    int rc = validate(kind, B, T, V, Lmax, 0, false);
+    if (rc) return rc;
+    if (groups < 1 || groups > kMaxGroups) return fail(B200CTC_INVALID_ARGUMENT, "groups must be in [1, 8]%s");
+    // [per-group workspaces][partial loss per group][applied upstream gradient per utterance]
+    *bytes_out = (size_t)groups * fused_group_bytes(kind, B, T, V, Lmax, groups) + 256 + align_up(sizeof(float) * (size_t)(B > 0 ? B : 1), 256);
+    return B200CTC_OK;
+}
+
+int b200ctc_forward_backward(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
+                             const int32_t *bigrams, const int32_t *input_lengths, const int32_t *label_lengths,
+                             int blank, int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_reduced,
+                             float loss_scale, float grad_scale, float *grad_out, int64_t gstride_t, int64_t gstride_b,
+                             int groups, void *workspace, size_t workspace_bytes, void *stream_) {
+    int rc = validate(kind, B, T, V, Lmax, blank, true);
+    if (rc) return rc;
+    if (groups < 1 || groups > kMaxGroups) return fail(B200CTC_INVALID_ARGUMENT, "groups must be in [1, 8]%s");
+    if (!loss_per_utt || !loss_reduced || !workspace || !grad_out) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    size_t need = 0;
+    b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, groups, &need);
+    if (workspace_bytes < need) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0 || T == 0) return check_cuda(cudaMemsetAsync(loss_reduced, 0, sizeof(float), stream), "memset");
+    if (groups > B) groups = B;
+    StreamPool *pool = get_pool();
+    if (!pool) return fail(B200CTC_CUDA_ERROR, "could not create the internal stream pool%s");
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const size_t gbytes = fused_group_bytes(kind, B, T, V, Lmax, groups);
+    float *partials = reinterpret_cast<float *>(ws + (size_t)groups * gbytes);
+    float *applied = reinterpret_cast<float *>(ws + (size_t)groups * gbytes + 256);
+    const int nb_max = (B + groups - 1) / groups;
+
+    fill_ones_kernel<<<(B + 255) / 256, 256, 0, stream>>>(applied, B);
+    if ((rc = check_cuda(cudaGetLastError(), "fill kernel"))) return rc;
+    if ((rc = check_cuda(cudaEventRecord(pool->fork, stream), "event record"))) return rc;
+    // lattice CTAs of one group run next to the row-streaming kernels of the others: keep that many SMs free
+    set_ring_sm_reserve(groups > 1 ? (nb_max < 32 ? nb_max : 32) : 0);
+    for (int g = 0; g < groups && rc == 0; ++g) {
+        const int b0 = g * nb_max;
+        const int nb = (b0 + nb_max <= B) ? nb_max : (B - b0);
+        if (nb <= 0) { cudaMemsetAsync(partials + g, 0, sizeof(float), stream); continue; }
+        cudaStream_t sg = pool->s[g];
+        if ((rc = check_cuda(cudaStreamWaitEvent(sg, pool->fork, 0), "stream wait"))) break;
+        const WsLayout w = make_layout(kind, nb, T, V, Lmax);
+        unsigned char *wsg = ws + (size_t)g * gbytes;
+        ProblemDesc d;
+        d.kind = kind; d.B = nb; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
+        d.acts = acts + (int64_t)b0 * stride_b; d.stride_t = stride_t; d.stride_b = stride_b;
+        d.labels = labels + (size_t)b0 * Lmax;
+        d.bigrams = (kind == B200CTC_KIND_GRAM) ? bigrams + (size_t)b0 * Lmax : nullptr;
+        d.input_lengths = input_lengths ? input_lengths + b0 : nullptr;
+        d.label_lengths = label_lengths ? label_lengths + b0 : nullptr;
+        zero_header_kernel<<<1, 32, 0, sg>>>(reinterpret_cast<WsHeader *>(wsg + w.off_hdr));
+        if ((rc = check_cuda(launch_softmax_gather(d, w, wsg, nullptr, sg), "softmax/gather kernel"))) break;
+        LatticeParams lp;
+        lp.d = d; lp.w = w; lp.ws = wsg;
+        lp.loss_per_utt = loss_per_utt + b0; lp.loss_reduced = partials + g; lp.loss_scale = loss_scale;
+        lp.W = 0; lp.S = 0;
+        int st = 0;
+        if ((rc = check_cuda(launch_lattice(lp, sg, &st), "lattice kernel"))) break;
+        if (st) { rc = fail(B200CTC_UNSUPPORTED, "lattice does not fit the kernel's shared-memory pipeline%s"); break; }
+        GradParams gp;
+        gp.d = d; gp.d.input_lengths = nullptr; gp.d.label_lengths = nullptr;
+        gp.grad_loss = applied; gp.per_utterance = 0; gp.scale = grad_scale;          // unit upstream gradient
+        gp.grad_out = grad_out + (int64_t)b0 * gstride_b; gp.gstride_t = gstride_t; gp.gstride_b = gstride_b;
+        if ((rc = check_cuda(launch_gradient(gp, w, wsg, sg), "gradient kernel"))) break;
+        if ((rc = check_cuda(cudaEventRecord(pool->join[g], sg), "event record"))) break;
+        if ((rc = check_cuda(cudaStreamWaitEvent(stream, pool->join[g], 0), "stream wait"))) break;
+    }
+    set_ring_sm_reserve(0);
+    if (rc) return rc;
+    sum_partials_kernel<<<1, 32, 0, stream>>>(partials, groups, loss_reduced);
+    return check_cuda(cudaGetLastError(), "partial sum kernel");
+}
+
+int b200ctc_rescale_grad(float *grad, int64_t gstride_t, int64_t gstride_b, int B, int T, int V, const float *grad_loss,
+                         int per_utterance, int groups, int kind, int Lmax, void *workspace, size_t workspace_bytes,
+                         void *stream_) {
+    if (!grad || !grad_loss || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    size_t need = 0;
+    int rc = b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, groups, &need);
+    if (rc) return rc;
+    if (workspace_bytes < need) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
+    if ((size_t)B * T == 0) return B200CTC_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (groups > B) groups = B;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    float *applied = reinterpret_cast<float *>(ws + (size_t)groups * fused_group_bytes(kind, B, T, V, Lmax, groups) + 256);
+    dim3 grid(T < 64 ? T : 64, B < 128 ? B : 128);
+    rescale_grad_kernel<<<grid, 256, 0, stream>>>(grad, gstride_t, gstride_b, B, T, V, grad_loss, per_utterance, applied);
+    rescale_commit_kernel<<<1, 256, 0, stream>>>(grad_loss, per_utterance, B, applied);
+    return check_cuda(cudaGetLastError(), "rescale kernel");
 }
 
 int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,

@@ -335,7 +335,8 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
     if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
         ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl) && !getenv("B200CTC_NO_TMA_K3")) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
-        if (ctas > sm_count()) ctas = sm_count();
+        if (ctas > sm_count() - ring_sm_reserve()) ctas = sm_count() - ring_sm_reserve();
+        if (ctas < 1) ctas = 1;
         cudaError_t e = cudaFuncSetAttribute(gradient_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
         if (e != cudaSuccess) return e;
         gradient_ring_kernel<<<(int)ctas, kRingThreads, rl.total, stream>>>(g, w, wsb, b_major, rl);

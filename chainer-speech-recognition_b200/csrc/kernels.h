@@ -23,6 +23,9 @@ cudaError_t launch_argmax(const float *acts, int64_t stride_t, int64_t stride_b,
 struct RingLayout;
 bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl);
 int sm_count();
+// SMs the ring kernels leave free (the pipelined forward+gradient path runs lattice CTAs next to them)
+int ring_sm_reserve();
+void set_ring_sm_reserve(int n);
 
 // kernel 2: alpha/beta lattice recursion (+ symbol-table CTAs, + batch loss reduction by the last CTA)
 struct LatticeParams {

@@ -384,6 +384,10 @@ bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, co
            (V & 3) == 0 && rl.slots >= kMinSlots;
 }
 
+namespace { thread_local int g_ring_reserve = 0; }
+int ring_sm_reserve() { return g_ring_reserve; }
+void set_ring_sm_reserve(int n) { g_ring_reserve = n; }
+
 int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -400,7 +404,8 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
     const RingLayout rl = make_ring((size_t)d.V * 4, 0);
     if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) && !getenv("B200CTC_NO_TMA_K1")) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
-        if (ctas > sm_count()) ctas = sm_count();
+        if (ctas > sm_count() - ring_sm_reserve()) ctas = sm_count() - ring_sm_reserve();
+        if (ctas < 1) ctas = 1;
         cudaError_t e;
         if (argmax_out) {
             e = cudaFuncSetAttribute(softmax_gather_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);

@@ -12,7 +12,8 @@
  * Conventions
  *   - plain C types only; every pointer is a CUDA *device* pointer unless the name ends in _host;
  *   - the caller owns every buffer, including the workspace; the library keeps no device memory
- *     and no global state besides a thread-local last-error string;
+ *     and no global state besides a thread-local last-error string (and, for b200ctc_forward_backward
+ *     only, a per-device pool of internal streams and events);
  *   - every function returns a status code (B200CTC_OK == 0) and never throws;
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
  *     except the *_host convenience entry points;
@@ -94,6 +95,30 @@ int b200ctc_backward(int kind,
                      const float *grad_loss, int per_utterance, float scale,
                      float *grad_out, int64_t gstride_t, int64_t gstride_b,
                      const void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Pipelined forward + gradient in one call (the fast path for training: GramCTC.forward immediately
+ * followed by GramCTC.backward, asr/loss/gram_ctc.py:246-297, as optimizer.update does,
+ * run/ctc/cnn/train.py:200).  The batch is cut into `groups` contiguous utterance groups; each group runs
+ * softmax/gather -> lattice -> gradient on its own internal stream, so the latency-bound lattice
+ * recursion of one group hides behind the bandwidth-bound kernels of the others.  The gradient is written
+ * for a unit upstream gradient times grad_scale (1/B_global for 'mean'); b200ctc_rescale_grad applies the
+ * real upstream gradient later and is a no-op when it is 1.  Internal streams fork from and join `stream`.
+ * The library keeps one small stream/event pool per device for this entry point (its only global state).
+ */
+int b200ctc_fused_workspace_bytes(int kind, int B, int T, int V, int Lmax, int groups, size_t *bytes_out);
+int b200ctc_forward_backward(int kind,
+                             const float *acts, int64_t stride_t, int64_t stride_b,
+                             const int32_t *labels, const int32_t *bigrams,
+                             const int32_t *input_lengths, const int32_t *label_lengths,
+                             int blank, int B, int T, int V, int Lmax,
+                             float *loss_per_utt, float *loss_reduced, float loss_scale, float grad_scale,
+                             float *grad_out, int64_t gstride_t, int64_t gstride_b,
+                             int groups, void *workspace, size_t workspace_bytes, void *stream);
+/* grad *= grad_loss / (what was applied before), in place; per_utterance as in b200ctc_backward. */
+int b200ctc_rescale_grad(float *grad, int64_t gstride_t, int64_t gstride_b, int B, int T, int V,
+                         const float *grad_loss, int per_utterance, int groups, int kind, int Lmax,
+                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* Greedy path alone (run/ctc/cnn/train.py:232 and its 9 sibling call sites): out (B,T) int64. */
 int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b,
