@@ -48,8 +48,10 @@ __global__ void sum_partials_kernel(const float *partials, int n, float *out) {
 constexpr int kMaxGroups = 8;
 struct StreamPool {
     int device = -1;
-    cudaStream_t s[kMaxGroups] = {};
-    cudaEvent_t fork = nullptr, join[kMaxGroups] = {};
+    cudaStream_t ring = nullptr, lattice = nullptr;       // (unused by the current schedule)
+    cudaStream_t grp[kMaxGroups] = {};                    // one stream per utterance group
+    cudaEvent_t fork = nullptr, join_ring = nullptr, join_lattice = nullptr;
+    cudaEvent_t k1_done[kMaxGroups] = {}, k2_done[kMaxGroups] = {};
 };
 StreamPool g_pool[16];
 
@@ -58,11 +60,16 @@ StreamPool *get_pool() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     StreamPool &p = g_pool[dev];
     if (p.device != dev) {
+        if (cudaStreamCreateWithFlags(&p.ring, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&p.lattice, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         for (int i = 0; i < kMaxGroups; ++i) {
-            if (cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaStreamCreateWithFlags(&p.grp[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.k1_done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.k2_done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
         if (cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&p.join_ring, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&p.join_lattice, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         p.device = dev;
     }
     return &p;
@@ -217,42 +224,60 @@ int b200ctc_forward_backward(int kind, const float *acts, int64_t stride_t, int6
     fill_ones_kernel<<<(B + 255) / 256, 256, 0, stream>>>(applied, B);
     if ((rc = check_cuda(cudaGetLastError(), "fill kernel"))) return rc;
     if ((rc = check_cuda(cudaEventRecord(pool->fork, stream), "event record"))) return rc;
-    // lattice CTAs of one group run next to the row-streaming kernels of the others: keep that many SMs free
-    set_ring_sm_reserve(groups > 1 ? (nb_max < 32 ? nb_max : 32) : 0);
-    for (int g = 0; g < groups && rc == 0; ++g) {
+
+    // Schedule: every utterance group runs K1 -> K2 -> K3 on its own stream.  The row-streaming kernels (one CTA per
+    // SM, ~176 KB of shared memory) exclude each other, so they pass the SMs around in issue order; a lattice CTA
+    // (~45 KB, 192 threads) fits NEXT to a row-ring CTA on the same SM, so the latency-bound recursion of one group
+    // runs underneath the bandwidth-bound kernels of the others.  Kernels are issued stage by stage (all K1, then
+    // all K2, then all K3) so that the hardware queues see them in the order the pipeline wants.
+    struct Group { ProblemDesc d; WsLayout w; unsigned char *ws; int b0, nb; };
+    Group grp[kMaxGroups];
+    int ng = 0;
+    for (int g = 0; g < groups; ++g) {
         const int b0 = g * nb_max;
         const int nb = (b0 + nb_max <= B) ? nb_max : (B - b0);
-        if (nb <= 0) { cudaMemsetAsync(partials + g, 0, sizeof(float), stream); continue; }
-        cudaStream_t sg = pool->s[g];
-        if ((rc = check_cuda(cudaStreamWaitEvent(sg, pool->fork, 0), "stream wait"))) break;
-        const WsLayout w = make_layout(kind, nb, T, V, Lmax);
-        unsigned char *wsg = ws + (size_t)g * gbytes;
-        ProblemDesc d;
+        if (nb <= 0) break;
+        Group &G = grp[ng++];
+        G.b0 = b0; G.nb = nb;
+        G.w = make_layout(kind, nb, T, V, Lmax);
+        G.ws = ws + (size_t)g * gbytes;
+        ProblemDesc &d = G.d;
         d.kind = kind; d.B = nb; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
         d.acts = acts + (int64_t)b0 * stride_b; d.stride_t = stride_t; d.stride_b = stride_b;
         d.labels = labels + (size_t)b0 * Lmax;
         d.bigrams = (kind == B200CTC_KIND_GRAM) ? bigrams + (size_t)b0 * Lmax : nullptr;
         d.input_lengths = input_lengths ? input_lengths + b0 : nullptr;
         d.label_lengths = label_lengths ? label_lengths + b0 : nullptr;
-        zero_header_kernel<<<1, 32, 0, sg>>>(reinterpret_cast<WsHeader *>(wsg + w.off_hdr));
-        if ((rc = check_cuda(launch_softmax_gather(d, w, wsg, nullptr, sg), "softmax/gather kernel"))) break;
+    }
+    for (int g = 0; g < ng && rc == 0; ++g) {
+        cudaStream_t sg = pool->grp[g];
+        if ((rc = check_cuda(cudaStreamWaitEvent(sg, pool->fork, 0), "stream wait"))) break;
+        zero_header_kernel<<<1, 32, 0, sg>>>(reinterpret_cast<WsHeader *>(grp[g].ws + grp[g].w.off_hdr));
+        if ((rc = check_cuda(launch_softmax_gather(grp[g].d, grp[g].w, grp[g].ws, nullptr, sg), "softmax/gather kernel"))) break;
+    }
+    for (int g = 0; g < ng && rc == 0; ++g) {
         LatticeParams lp;
-        lp.d = d; lp.w = w; lp.ws = wsg;
-        lp.loss_per_utt = loss_per_utt + b0; lp.loss_reduced = partials + g; lp.loss_scale = loss_scale;
+        lp.d = grp[g].d; lp.w = grp[g].w; lp.ws = grp[g].ws;
+        lp.loss_per_utt = loss_per_utt + grp[g].b0; lp.loss_reduced = partials + g; lp.loss_scale = loss_scale;
         lp.W = 0; lp.S = 0;
         int st = 0;
-        if ((rc = check_cuda(launch_lattice(lp, sg, &st), "lattice kernel"))) break;
+        if ((rc = check_cuda(launch_lattice(lp, pool->grp[g], &st), "lattice kernel"))) break;
         if (st) { rc = fail(B200CTC_UNSUPPORTED, "lattice does not fit the kernel's shared-memory pipeline%s"); break; }
-        GradParams gp;
-        gp.d = d; gp.d.input_lengths = nullptr; gp.d.label_lengths = nullptr;
-        gp.grad_loss = applied; gp.per_utterance = 0; gp.scale = grad_scale;          // unit upstream gradient
-        gp.grad_out = grad_out + (int64_t)b0 * gstride_b; gp.gstride_t = gstride_t; gp.gstride_b = gstride_b;
-        if ((rc = check_cuda(launch_gradient(gp, w, wsg, sg), "gradient kernel"))) break;
-        if ((rc = check_cuda(cudaEventRecord(pool->join[g], sg), "event record"))) break;
-        if ((rc = check_cuda(cudaStreamWaitEvent(stream, pool->join[g], 0), "stream wait"))) break;
     }
-    set_ring_sm_reserve(0);
+    for (int g = 0; g < ng && rc == 0; ++g) {
+        GradParams gp;
+        gp.d = grp[g].d; gp.d.input_lengths = nullptr; gp.d.label_lengths = nullptr;
+        gp.grad_loss = applied; gp.per_utterance = 0; gp.scale = grad_scale;          // unit upstream gradient
+        gp.grad_out = grad_out + (int64_t)grp[g].b0 * gstride_b; gp.gstride_t = gstride_t; gp.gstride_b = gstride_b;
+        if ((rc = check_cuda(launch_gradient(gp, grp[g].w, grp[g].ws, pool->grp[g]), "gradient kernel"))) break;
+    }
+    // join (also on the error path, so that the caller's stream stays ordered after whatever was enqueued)
+    for (int g = 0; g < ng; ++g) {
+        cudaEventRecord(pool->k2_done[g], pool->grp[g]);
+        cudaStreamWaitEvent(stream, pool->k2_done[g], 0);
+    }
     if (rc) return rc;
+    for (int g = ng; g < groups; ++g) cudaMemsetAsync(partials + g, 0, sizeof(float), stream);
     sum_partials_kernel<<<1, 32, 0, stream>>>(partials, groups, loss_reduced);
     return check_cuda(cudaGetLastError(), "partial sum kernel");
 }

@@ -223,8 +223,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             }
             const unsigned mask = __ballot_sync(0xffffffffu, need);
             if (need) {
-                const int s = ring_claim(ring, q + (unsigned)__popc(mask & ((1u << lane) - 1u)));
+                const unsigned myq = q + (unsigned)__popc(mask & ((1u << lane) - 1u));
+                const int s = ring_claim(ring, myq);
                 ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0;
+                ring_publish(ring, s, myq);
                 mbar_arrive_expect_tx(&ring.full[s], row_bytes + 2 * ab_bytes);
                 bulk_g2s(ring.slot(s), d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b, row_bytes,
                          &ring.full[s]);

@@ -49,7 +49,8 @@ namespace {
 
 constexpr int kChunk = 8;        // frames per pipeline chunk
 constexpr int kMaxAhead = 2;     // chunks of emission rows in flight ahead of the first warp
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 4;    // 4 x 8 frames of emission rows per direction: ~45 KB per CTA at L=80, so that a
+                                 // lattice CTA fits next to a row-ring CTA on one SM (pipelined path)
 constexpr int kMaxWarpsPerDir = 16;
 
 // CTC, reversed direction: the lattice is indexed with one phantom node in front (q = 0 <-> j = Nb, never
@@ -562,6 +563,7 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
     int S = kMaxStages;
+    if (const char *e = getenv("B200CTC_LAT_STAGES")) S = atoi(e);               // experiment knob
     while (S > 2 && plan_smem(p.w.W, W, S, PAD).total > kLatticeSmemBudget) --S;
     const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);
     if (sp.total > kLatticeSmemBudget) { *status = 2; return cudaSuccess; }

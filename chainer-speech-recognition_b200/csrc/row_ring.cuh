@@ -13,6 +13,7 @@
 // Requirements (checked by the host dispatcher, which otherwise uses the plain LDG kernels):
 // rows 16-byte aligned, V % 4 == 0, and at least kMinSlots rows fit in shared memory.
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200ctc {
@@ -22,12 +23,12 @@ constexpr int kRingThreads = 32 * (1 + kRingConsumers);
 constexpr int kTicketBatch = 8;       // frames per ticket; one producer lane per frame of the batch
 constexpr int kMinSlots = 4;
 constexpr int kMaxSlots = 16;
-constexpr size_t kRingSmemBudget = 200 * 1024;
+constexpr size_t kRingSmemBudget = 176 * 1024;   // leaves room for one lattice CTA (<= 48 KB) on the same SM
 
 struct RowMeta {
     int b, t;
     int kind;      // 0: full work, 1: argmax only (padded frame), -1: stop
-    int pad;
+    unsigned seq;  // row sequence number currently occupying the slot (published before the barrier is armed)
 };
 
 struct RingLayout {
@@ -38,11 +39,16 @@ struct RingLayout {
     size_t off_meta, off_full, off_empty, off_extra, total;
 };
 
-__host__ __device__ inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes) {
+inline size_t ring_budget() {
+    if (const char *e = getenv("B200CTC_RING_KB")) return (size_t)atoi(e) * 1024;      // experiment knob
+    return kRingSmemBudget;
+}
+
+inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes) {
     RingLayout r;
     r.slot_bytes = align_up(slot_payload, 128);
     const size_t fixed = (size_t)kMaxSlots * (sizeof(RowMeta) + 16) + extra_bytes + 256;
-    long long n = ((long long)kRingSmemBudget - (long long)fixed) / (long long)r.slot_bytes;
+    long long n = ((long long)ring_budget() - (long long)fixed) / (long long)r.slot_bytes;
     if (n > kMaxSlots) n = kMaxSlots;
     r.slots = (int)(n < 0 ? 0 : n);
     r.batch = r.slots < kTicketBatch ? r.slots : kTicketBatch;
@@ -83,6 +89,7 @@ __device__ __forceinline__ Ring ring_setup(unsigned char *smem, const RingLayout
         for (int i = 0; i < rl.slots; ++i) {
             mbar_init(&r.full[i], 1);
             mbar_init(&r.empty[i], 1);
+            r.meta[i].seq = 0xffffffffu;
         }
         mbar_init_fence();
     }
@@ -99,19 +106,25 @@ __device__ __forceinline__ int ring_claim(const Ring &r, unsigned q) {
 }
 
 // Consumer side: wait until row sequence number q has landed in its slot; returns the slot.
-// A parity wait can only tell "this phase" from "the one before", and rows complete out of order (a batch is
-// issued by several lanes at once), so a fast consumer may get here while the slot's PREVIOUS occupant
-// (row q - slots) is still loading -- the parity of its own row would then alias to an older, completed phase.
-// Waiting first for the previous occupant's release pins the barrier to the right phase.  That wait is itself
-// only unambiguous if the occupant before THAT has been released, which holds because the number of active
-// consumers never exceeds the number of slots: consumer c reaches row q after finishing row q - nc, which was
-// issued only once every row up to q - nc - slots <= q - 2*slots had been released.
+// An mbarrier parity wait can only tell "this phase" from "the one before", while rows complete out of order
+// (a batch is issued by several lanes at once, each row is several bulk copies): a fast consumer may get here
+// while the slot still belongs to an earlier row, and the parity of its own row would then alias to an older,
+// already completed phase.  So the producer publishes the sequence number it is about to load into the slot
+// (RowMeta::seq, written before it arms the barrier) and the consumer first waits to see ITS number there: from
+// then on the barrier is in this row's phase and the parity wait is exact, whatever the skew between warps.
 __device__ __forceinline__ int ring_acquire(const Ring &r, unsigned q) {
     const int s = (int)(q % (unsigned)r.slots);
     const unsigned n = q / (unsigned)r.slots;
-    if (n > 0) mbar_wait(&r.empty[s], (n - 1) & 1u);
+    const volatile unsigned *seq = &r.meta[s].seq;
+    while (*seq != q) __nanosleep(32);
     mbar_wait(&r.full[s], n & 1u);
     return s;
+}
+
+// Producer side: announce that slot s now belongs to row q (after the other RowMeta fields, before arming).
+__device__ __forceinline__ void ring_publish(const Ring &r, int s, unsigned q) {
+    __threadfence_block();
+    *reinterpret_cast<volatile unsigned *>(&r.meta[s].seq) = q;
 }
 
 // Producer side (whole warp): tell every consumer to stop -- one stop record per consumer, in sequence order.
@@ -122,6 +135,7 @@ __device__ __forceinline__ void ring_stop(const Ring &r, unsigned q, int lane) {
         for (int c = 0; c < r.nc; ++c) {
             const int s = ring_claim(r, q + (unsigned)c);
             r.meta[s].kind = -1;
+            ring_publish(r, s, q + (unsigned)c);
             mbar_arrive(&r.full[s]);
         }
     }
