@@ -16,14 +16,11 @@ from ... import _lib
 
 
 def pipeline_groups(B):
-    """Utterance groups of the pipelined forward+gradient path (0 = the separate forward / backward calls).
-    Off by default: measured on B200 it does not pay yet (0.49-0.60 ms vs 0.47 ms per step at B=64,T=800,V=3500)
-    because the persistent row-streaming CTAs of one group occupy every SM and the lattice CTAs of another
-    cannot start next to them.  B200CTC_GROUPS=1..8 turns it on."""
-    env = os.environ.get("B200CTC_GROUPS")
-    if env is not None:
-        return max(0, min(8, min(int(env), B)))
-    return 0
+    """1 = use the one-call forward+gradient path (b200ctc_forward_backward, "one-read" schedule) when the activations
+    need a gradient, 0 = separate forward / backward calls (default).  Measured on B200 at B=64,T=800,V=3500 the
+    one-read schedule is only 3 % faster (0.458 vs 0.471 ms): it saves the second read of the activations, but the
+    label-column patch that replaces it is bound by random 32-byte DRAM accesses (86 us).  B200CTC_FUSED=1 enables it."""
+    return 1 if os.environ.get("B200CTC_FUSED", "0") == "1" else 0
 
 
 def _stream_ptr(device):
@@ -149,26 +146,12 @@ class LatticeLossFunction(torch.autograd.Function):
         if grad.stride(2) != 1:
             grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
         with torch.cuda.device(dev):
-            if ctx.groups > 0:
-                # a retained graph differentiated again: each group's slice of the workspace is a regular workspace
-                nb = (B + ctx.groups - 1) // ctx.groups
-                gbytes = (_lib.workspace_bytes(ctx.kind, nb, T, V, Lmax) + 255) // 256 * 256
-                for g in range(min(ctx.groups, B)):
-                    b0 = g * nb
-                    n = min(nb, B - b0)
-                    if n <= 0:
-                        continue
-                    a, gr = acts[:, b0:b0 + n], grad[:, b0:b0 + n]
-                    _lib.check(lib.b200ctc_backward(
-                        ctx.kind, a.data_ptr(), a.stride(0), a.stride(1), labels[b0:b0 + n].data_ptr(),
-                        bigrams[b0:b0 + n].data_ptr() if ctx.has_bigrams else None, ctx.blank, n, T, V, Lmax,
-                        gy[b0:b0 + n].data_ptr() if per_utt else gy.data_ptr(), per_utt, scale, gr.data_ptr(),
-                        gr.stride(0), gr.stride(1), workspace.data_ptr() + g * gbytes, gbytes, _stream_ptr(dev)))
-            else:
-                _lib.check(lib.b200ctc_backward(
-                    ctx.kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), big_ptr,
-                    ctx.blank, B, T, V, Lmax, gy.data_ptr(), per_utt, scale, grad.data_ptr(), grad.stride(0),
-                    grad.stride(1), workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
+            # (also serves a retained graph differentiated again after the one-call path: its workspace starts
+            #  with a regular workspace)
+            _lib.check(lib.b200ctc_backward(
+                ctx.kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), big_ptr,
+                ctx.blank, B, T, V, Lmax, gy.data_ptr(), per_utt, scale, grad.data_ptr(), grad.stride(0),
+                grad.stride(1), workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
         return (grad,) + (None,) * 10
 
 

@@ -22,7 +22,7 @@ __global__ void zero_header_kernel(WsHeader *h) {
 // gradient *= gy / applied, in place, skipped entirely when the ratio is 1 (the usual loss.backward()):
 // used by the pipelined path, which computes the gradient with a unit upstream gradient at forward time.
 __global__ void rescale_grad_kernel(float *grad, int64_t stride_t, int64_t stride_b, int B, int T, int V,
-                                    const float *gy, int per_utterance, float *applied) {
+                                    const float *gy, int per_utterance, const float *applied) {
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const float want = per_utterance ? gy[b] : gy[0];
         const float have = applied[per_utterance ? b : 0];
@@ -38,41 +38,9 @@ __global__ void rescale_commit_kernel(const float *gy, int per_utterance, int B,
     const int n = per_utterance ? B : 1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) applied[i] = gy[i];
 }
-__global__ void fill_ones_kernel(float *p, int n) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 1.f;
-}
-__global__ void sum_partials_kernel(const float *partials, int n, float *out) {
-    if (threadIdx.x == 0) { double a = 0.0; for (int i = 0; i < n; ++i) a += (double)partials[i]; *out = (float)a; }
-}
-
-constexpr int kMaxGroups = 8;
-struct StreamPool {
-    int device = -1;
-    cudaStream_t ring = nullptr, lattice = nullptr;       // (unused by the current schedule)
-    cudaStream_t grp[kMaxGroups] = {};                    // one stream per utterance group
-    cudaEvent_t fork = nullptr, join_ring = nullptr, join_lattice = nullptr;
-    cudaEvent_t k1_done[kMaxGroups] = {}, k2_done[kMaxGroups] = {};
-};
-StreamPool g_pool[16];
-
-StreamPool *get_pool() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    StreamPool &p = g_pool[dev];
-    if (p.device != dev) {
-        if (cudaStreamCreateWithFlags(&p.ring, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaStreamCreateWithFlags(&p.lattice, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        for (int i = 0; i < kMaxGroups; ++i) {
-            if (cudaStreamCreateWithFlags(&p.grp[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&p.k1_done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&p.k2_done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        }
-        if (cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&p.join_ring, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&p.join_lattice, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        p.device = dev;
-    }
-    return &p;
+__global__ void fused_init_kernel(WsHeader *h, float *applied, int n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) applied[i] = 1.f;
 }
 
 thread_local char g_err[512] = "";
@@ -183,18 +151,17 @@ int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stri
     return check_cuda(launch_gradient(g, w, workspace, static_cast<cudaStream_t>(stream_)), "gradient kernel");
 }
 
-size_t fused_group_bytes(int kind, int B, int T, int V, int Lmax, int groups) {
-    const int nb = (B + groups - 1) / groups;
-    return align_up(make_layout(kind, nb, T, V, Lmax).total, 256);
+size_t fused_applied_offset(int kind, int B, int T, int V, int Lmax) {
+    return align_up(make_layout(kind, B, T, V, Lmax).total, 256);
 }
 
 int b200ctc_fused_workspace_bytes(int kind, int B, int T, int V, int Lmax, int groups, size_t *bytes_out) {
+    (void)groups;
     if (!bytes_out) return fail(B200CTC_INVALID_ARGUMENT, "bytes_out is NULL%s");
     int rc = validate(kind, B, T, V, Lmax, 0, false);
     if (rc) return rc;
-    if (groups < 1 || groups > kMaxGroups) return fail(B200CTC_INVALID_ARGUMENT, "groups must be in [1, 8]%s");
-    // [per-group workspaces][partial loss per group][applied upstream gradient per utterance]
-    *bytes_out = (size_t)groups * fused_group_bytes(kind, B, T, V, Lmax, groups) + 256 + align_up(sizeof(float) * (size_t)(B > 0 ? B : 1), 256);
+    // [regular workspace][upstream gradient already applied, per utterance]
+    *bytes_out = fused_applied_offset(kind, B, T, V, Lmax) + align_up(sizeof(float) * (size_t)(B > 0 ? B : 1), 256);
     return B200CTC_OK;
 }
 
@@ -203,83 +170,47 @@ int b200ctc_forward_backward(int kind, const float *acts, int64_t stride_t, int6
                              int blank, int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_reduced,
                              float loss_scale, float grad_scale, float *grad_out, int64_t gstride_t, int64_t gstride_b,
                              int groups, void *workspace, size_t workspace_bytes, void *stream_) {
+    (void)groups;
     int rc = validate(kind, B, T, V, Lmax, blank, true);
     if (rc) return rc;
-    if (groups < 1 || groups > kMaxGroups) return fail(B200CTC_INVALID_ARGUMENT, "groups must be in [1, 8]%s");
     if (!loss_per_utt || !loss_reduced || !workspace || !grad_out) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
     size_t need = 0;
-    b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, groups, &need);
+    b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, 1, &need);
     if (workspace_bytes < need) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (B == 0 || T == 0) return check_cuda(cudaMemsetAsync(loss_reduced, 0, sizeof(float), stream), "memset");
-    if (groups > B) groups = B;
-    StreamPool *pool = get_pool();
-    if (!pool) return fail(B200CTC_CUDA_ERROR, "could not create the internal stream pool%s");
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    const size_t gbytes = fused_group_bytes(kind, B, T, V, Lmax, groups);
-    float *partials = reinterpret_cast<float *>(ws + (size_t)groups * gbytes);
-    float *applied = reinterpret_cast<float *>(ws + (size_t)groups * gbytes + 256);
-    const int nb_max = (B + groups - 1) / groups;
+    float *applied = reinterpret_cast<float *>(ws + fused_applied_offset(kind, B, T, V, Lmax));
+    const WsLayout w = make_layout(kind, B, T, V, Lmax);
 
-    fill_ones_kernel<<<(B + 255) / 256, 256, 0, stream>>>(applied, B);
-    if ((rc = check_cuda(cudaGetLastError(), "fill kernel"))) return rc;
-    if ((rc = check_cuda(cudaEventRecord(pool->fork, stream), "event record"))) return rc;
+    ProblemDesc d;
+    d.kind = kind; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
+    d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
+    d.labels = labels; d.bigrams = kind == B200CTC_KIND_GRAM ? bigrams : nullptr;
+    d.input_lengths = input_lengths; d.label_lengths = label_lengths;
 
-    // Schedule: every utterance group runs K1 -> K2 -> K3 on its own stream.  The row-streaming kernels (one CTA per
-    // SM, ~176 KB of shared memory) exclude each other, so they pass the SMs around in issue order; a lattice CTA
-    // (~45 KB, 192 threads) fits NEXT to a row-ring CTA on the same SM, so the latency-bound recursion of one group
-    // runs underneath the bandwidth-bound kernels of the others.  Kernels are issued stage by stage (all K1, then
-    // all K2, then all K3) so that the hardware queues see them in the order the pipeline wants.
-    struct Group { ProblemDesc d; WsLayout w; unsigned char *ws; int b0, nb; };
-    Group grp[kMaxGroups];
-    int ng = 0;
-    for (int g = 0; g < groups; ++g) {
-        const int b0 = g * nb_max;
-        const int nb = (b0 + nb_max <= B) ? nb_max : (B - b0);
-        if (nb <= 0) break;
-        Group &G = grp[ng++];
-        G.b0 = b0; G.nb = nb;
-        G.w = make_layout(kind, nb, T, V, Lmax);
-        G.ws = ws + (size_t)g * gbytes;
-        ProblemDesc &d = G.d;
-        d.kind = kind; d.B = nb; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
-        d.acts = acts + (int64_t)b0 * stride_b; d.stride_t = stride_t; d.stride_b = stride_b;
-        d.labels = labels + (size_t)b0 * Lmax;
-        d.bigrams = (kind == B200CTC_KIND_GRAM) ? bigrams + (size_t)b0 * Lmax : nullptr;
-        d.input_lengths = input_lengths ? input_lengths + b0 : nullptr;
-        d.label_lengths = label_lengths ? label_lengths + b0 : nullptr;
-    }
-    for (int g = 0; g < ng && rc == 0; ++g) {
-        cudaStream_t sg = pool->grp[g];
-        if ((rc = check_cuda(cudaStreamWaitEvent(sg, pool->fork, 0), "stream wait"))) break;
-        zero_header_kernel<<<1, 32, 0, sg>>>(reinterpret_cast<WsHeader *>(grp[g].ws + grp[g].w.off_hdr));
-        if ((rc = check_cuda(launch_softmax_gather(grp[g].d, grp[g].w, grp[g].ws, nullptr, sg), "softmax/gather kernel"))) break;
-    }
-    for (int g = 0; g < ng && rc == 0; ++g) {
-        LatticeParams lp;
-        lp.d = grp[g].d; lp.w = grp[g].w; lp.ws = grp[g].ws;
-        lp.loss_per_utt = loss_per_utt + grp[g].b0; lp.loss_reduced = partials + g; lp.loss_scale = loss_scale;
-        lp.W = 0; lp.S = 0;
-        int st = 0;
-        if ((rc = check_cuda(launch_lattice(lp, pool->grp[g], &st), "lattice kernel"))) break;
-        if (st) { rc = fail(B200CTC_UNSUPPORTED, "lattice does not fit the kernel's shared-memory pipeline%s"); break; }
-    }
-    for (int g = 0; g < ng && rc == 0; ++g) {
-        GradParams gp;
-        gp.d = grp[g].d; gp.d.input_lengths = nullptr; gp.d.label_lengths = nullptr;
-        gp.grad_loss = applied; gp.per_utterance = 0; gp.scale = grad_scale;          // unit upstream gradient
-        gp.grad_out = grad_out + (int64_t)grp[g].b0 * gstride_b; gp.gstride_t = gstride_t; gp.gstride_b = gstride_b;
-        if ((rc = check_cuda(launch_gradient(gp, grp[g].w, grp[g].ws, pool->grp[g]), "gradient kernel"))) break;
-    }
-    // join (also on the error path, so that the caller's stream stays ordered after whatever was enqueued)
-    for (int g = 0; g < ng; ++g) {
-        cudaEventRecord(pool->k2_done[g], pool->grp[g]);
-        cudaStreamWaitEvent(stream, pool->k2_done[g], 0);
-    }
-    if (rc) return rc;
-    for (int g = ng; g < groups; ++g) cudaMemsetAsync(partials + g, 0, sizeof(float), stream);
-    sum_partials_kernel<<<1, 32, 0, stream>>>(partials, groups, loss_reduced);
-    return check_cuda(cudaGetLastError(), "partial sum kernel");
+    fused_init_kernel<<<(B + 255) / 256, 256, 0, stream>>>(reinterpret_cast<WsHeader *>(ws + w.off_hdr), applied, B);
+    if ((rc = check_cuda(cudaGetLastError(), "workspace header reset"))) return rc;
+    // one-read path: the softmax/gather kernel also writes softmax * scale as the gradient row while the
+    // activation row is in shared memory; after the lattice only the label columns are patched
+    cudaError_t e = launch_softmax_gather_grad(d, w, ws, grad_out, gstride_t, gstride_b, grad_scale, stream);
+    const bool one_read = (e == cudaSuccess);
+    if (e == cudaErrorNotSupported) e = launch_softmax_gather(d, w, ws, nullptr, stream);   // unaligned / huge rows
+    if ((rc = check_cuda(e, "softmax/gather kernel"))) return rc;
+    LatticeParams lp;
+    lp.d = d; lp.w = w; lp.ws = ws;
+    lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
+    lp.W = 0; lp.S = 0;
+    int st = 0;
+    if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
+    if (st) return fail(B200CTC_UNSUPPORTED, "lattice does not fit the kernel's shared-memory pipeline%s");
+    GradParams gp;
+    gp.d = d; gp.d.input_lengths = nullptr; gp.d.label_lengths = nullptr;
+    gp.grad_loss = applied; gp.per_utterance = 0; gp.scale = grad_scale;              // unit upstream gradient
+    gp.grad_out = grad_out; gp.gstride_t = gstride_t; gp.gstride_b = gstride_b;
+    if (one_read) return check_cuda(launch_posterior_patch(gp, w, ws, stream), "posterior patch kernel");
+    return check_cuda(launch_gradient(gp, w, ws, stream), "gradient kernel");
 }
 
 int b200ctc_rescale_grad(float *grad, int64_t gstride_t, int64_t gstride_b, int B, int T, int V, const float *grad_loss,
@@ -292,9 +223,8 @@ int b200ctc_rescale_grad(float *grad, int64_t gstride_t, int64_t gstride_b, int 
     if (workspace_bytes < need) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
     if ((size_t)B * T == 0) return B200CTC_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (groups > B) groups = B;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    float *applied = reinterpret_cast<float *>(ws + (size_t)groups * fused_group_bytes(kind, B, T, V, Lmax, groups) + 256);
+    float *applied = reinterpret_cast<float *>(ws + fused_applied_offset(kind, B, T, V, Lmax));
     dim3 grid(T < 64 ? T : 64, B < 128 ? B : 128);
     rescale_grad_kernel<<<grid, 256, 0, stream>>>(grad, gstride_t, gstride_b, B, T, V, grad_loss, per_utterance, applied);
     rescale_commit_kernel<<<1, 256, 0, stream>>>(grad_loss, per_utterance, B, applied);

@@ -325,7 +325,163 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     if (lane == 0) bulk_wait_all<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-read path, second half: the gradient rows already hold softmax * scale (written by the softmax/gather
+// kernel while the row was in shared memory); subtract the merged posterior at the <= L+1 columns the lattice
+// can emit (gram_ctc.py:180-217, :290).  One warp per valid frame; reads the alpha/beta rows (coalesced), merges
+// per id in a fixed order (deterministic), then one read-modify-write per emitted id.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPatchNodeIters = 8;    // lattice nodes per lane held in registers: up to 256 nodes on the fast path
+constexpr int kPatchSymIters = 4;     // emitted ids per lane on the fast path: up to 128 distinct ids
+constexpr int kPatchFrames = 8;       // consecutive frames of one utterance per work item
+
+struct PatchLoads {
+    float2 av[kPatchNodeIters], bv[kPatchNodeIters];
+    float gold[kPatchSymIters];
+};
+
+// Work item = 8 consecutive frames of one utterance: the utterance's tables (emitted ids, node lists, log P) are
+// fetched once per item, and the DRAM loads of frame i+1 (alpha/beta rows, the gradient values to patch) are in
+// flight while frame i is merged -- the kernel is otherwise a chain of dependent L2/DRAM latencies.
+__global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(GradParams gp, WsLayout w, unsigned char *ws,
+                                                                            int b_major, int sm_floats_per_warp) {
+    extern __shared__ float sm_all[];
+    (void)b_major;
+    const ProblemDesc &d = gp.d;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
+    const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
+    const float2 *av_all = reinterpret_cast<const float2 *>(ws + w.off_av);
+    const float2 *bv_all = reinterpret_cast<const float2 *>(ws + w.off_bv);
+    const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
+    const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
+    const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
+    const int per = d.kind == 0 ? 2 : 3;
+    const unsigned chunks = (unsigned)((d.T + kPatchFrames - 1) / kPatchFrames);
+    const unsigned items = (unsigned)d.B * chunks;
+    for (;;) {
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(&hdr->k3_ticket, 1u);      // the gradient kernel's counter, unused on this path
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= items) break;
+        const int b = (int)(it / chunks);
+        const int t0 = (int)(it % chunks) * kPatchFrames;
+        const UttInfo ui = utt[b];
+        const int t1 = min(t0 + kPatchFrames, ui.Tb);
+        if (t0 >= t1) continue;
+        const float gy = gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss);
+        const float sc = gy * gp.scale;
+        const float2 *arow0 = av_all + (size_t)b * d.T * w.Np;
+        const float2 *brow0 = bv_all + (size_t)b * d.T * w.Np;
+        const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
+        const int *unode = unode_all + (size_t)b * w.Nmax;
+        const int *usym = usym_all + (size_t)b * w.Nmax;
+        float *gbase = gp.grad_out + (int64_t)b * gp.gstride_b;
+        if (ui.Nb <= 32 * kPatchNodeIters && ui.Ub <= 32 * kPatchSymIters) {
+            int sym[kPatchSymIters], n0[kPatchSymIters], n1[kPatchSymIters];
+#pragma unroll
+            for (int k = 0; k < kPatchSymIters; ++k) {
+                const int u = lane + 32 * k;
+                sym[k] = -1; n0[k] = 0; n1[k] = 0;
+                if (u < ui.Ub) { sym[k] = __ldg(usym + u); n0[k] = __ldg(uoff + u); n1[k] = __ldg(uoff + u + 1); }
+            }
+            auto load = [&](int t, PatchLoads &L) {
+                const float2 *arow = arow0 + (size_t)t * w.Np, *brow = brow0 + (size_t)t * w.Np;
+                const float *grow = gbase + (int64_t)t * gp.gstride_t;
+#pragma unroll
+                for (int k = 0; k < kPatchNodeIters; ++k) {
+                    const int j = lane + 32 * k;
+                    L.av[k] = make_float2(SENT, 0.f); L.bv[k] = make_float2(SENT, 0.f);
+                    if (j < ui.Nb) { L.av[k] = __ldg(arow + j); L.bv[k] = __ldg(brow + j); }
+                }
+#pragma unroll
+                for (int k = 0; k < kPatchSymIters; ++k) L.gold[k] = sym[k] >= 0 ? grow[sym[k]] : 0.f;
+            };
+            auto finish = [&](int t, const PatchLoads &L) {
+                float *grow = gbase + (int64_t)t * gp.gstride_t;
+                float blank_part = 0.f;
+#pragma unroll
+                for (int k = 0; k < kPatchNodeIters; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < ui.Nb) {
+                        const float e = ex2_approx(((L.av[k].x + L.bv[k].x) - ui.Ph) + ((L.av[k].y + L.bv[k].y) - ui.Pl));
+                        e_sm[j] = e;                                            // 2^gamma
+                        if (j % per == 0) blank_part += e;
+                    }
+                }
+                blank_part = warp_sum(blank_part);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < kPatchSymIters; ++k) {
+                    if (sym[k] < 0) continue;
+                    float post = (lane + 32 * k == ui.ublank) ? blank_part : 0.f;
+                    for (int n = n0[k]; n < n1[k]; ++n) {
+                        const int j = __ldg(unode + n);
+                        if (j < ui.Nb) post += e_sm[j];
+                    }
+                    grow[sym[k]] = L.gold[k] - __fmul_rn(post, sc);        // distinct columns; no FMA contraction, so the
+                }                                                          // result equals the separate gradient kernel's
+                __syncwarp();
+            };
+            PatchLoads A, Bf;
+            load(t0, A);
+            for (int t = t0; t < t1; t += 2) {
+                if (t + 1 < t1) load(t + 1, Bf);
+                finish(t, A);
+                if (t + 2 < t1) load(t + 2, A);
+                if (t + 1 < t1) finish(t + 1, Bf);
+            }
+        } else {
+            for (int t = t0; t < t1; ++t) {
+                const float2 *arow = arow0 + (size_t)t * w.Np, *brow = brow0 + (size_t)t * w.Np;
+                float *grow = gbase + (int64_t)t * gp.gstride_t;
+                float blank_part = 0.f;
+                for (int j = lane; j < ui.Nb; j += 32) {
+                    const float2 a = __ldg(arow + j), bb = __ldg(brow + j);
+                    const float e = ex2_approx(((a.x + bb.x) - ui.Ph) + ((a.y + bb.y) - ui.Pl));
+                    e_sm[j] = e;
+                    if (j % per == 0) blank_part += e;
+                }
+                blank_part = warp_sum(blank_part);
+                __syncwarp();
+                for (int u = lane; u < ui.Ub; u += 32) {
+                    const int m0 = __ldg(uoff + u), m1 = __ldg(uoff + u + 1);
+                    float post = (u == ui.ublank) ? blank_part : 0.f;
+                    for (int n = m0; n < m1; ++n) {
+                        const int j = __ldg(unode + n);
+                        if (j < ui.Nb) post += e_sm[j];
+                    }
+                    float *p = grow + __ldg(usym + u);
+                    *p = *p - __fmul_rn(post, sc);
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_posterior_patch(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream) {
+    const long long frames = (long long)g.d.B * g.d.T;
+    if (frames == 0) return cudaSuccess;
+    unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
+    const int per_warp = w.Np;
+    const size_t smem = sizeof(float) * (size_t)per_warp * kWarpsPerCta;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(posterior_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const long long items = (long long)g.d.B * ((g.d.T + kPatchFrames - 1) / kPatchFrames);
+    long long ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long cap = (long long)sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
+    posterior_patch_kernel<<<(int)ctas, kWarpsPerCta * 32, smem, stream>>>(g, w, wsb, b_major, per_warp);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream) {
     const long long frames = (long long)g.d.B * g.d.T;

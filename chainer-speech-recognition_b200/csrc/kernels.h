@@ -16,6 +16,8 @@ struct ProblemDesc {
 // kernel 1: fused log-softmax statistics + label gather (+ optional greedy argmax)
 cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
                                   cudaStream_t stream);
+cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, void *ws, float *grad, int64_t gstride_t,
+                                       int64_t gstride_b, float scale, cudaStream_t stream);
 cudaError_t launch_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,
                           int64_t *argmax_out, cudaStream_t stream);
 
@@ -51,5 +53,7 @@ struct GradParams {
     int64_t gstride_t, gstride_b;
 };
 cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream);
+// one-read path: subtract the merged posteriors at the label columns of a gradient that already holds softmax * scale
+cudaError_t launch_posterior_patch(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream);
 
 }  // namespace b200ctc

@@ -49,8 +49,7 @@ namespace {
 
 constexpr int kChunk = 8;        // frames per pipeline chunk
 constexpr int kMaxAhead = 2;     // chunks of emission rows in flight ahead of the first warp
-constexpr int kMaxStages = 4;    // 4 x 8 frames of emission rows per direction: ~45 KB per CTA at L=80, so that a
-                                 // lattice CTA fits next to a row-ring CTA on one SM (pipelined path)
+constexpr int kMaxStages = 8;    // >= kMaxAhead + W + 1, or the first warp stalls on the last one's progress
 constexpr int kMaxWarpsPerDir = 16;
 
 // CTC, reversed direction: the lattice is indexed with one phantom node in front (q = 0 <-> j = Nb, never

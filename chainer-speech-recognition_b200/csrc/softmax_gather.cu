@@ -223,11 +223,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
 // take two cheap passes (max/argmax, then sum of exponentials) and the label gather reads shared
 // memory instead of going back to L2.
 // ---------------------------------------------------------------------------------------------
-template <bool ARGMAX>
+// GRAD: the one-read variant used by b200ctc_forward_backward.  While the row is still in shared memory the
+// consumer also turns it into softmax * scale and hands it to the TMA engine as the gradient row; the few label
+// columns get their posterior subtracted later by posterior_patch_kernel (gradient.cu).  The activations are then
+// read from HBM once per step instead of twice.
+struct GradOut {
+    float *grad;
+    int64_t gstride_t, gstride_b;
+    float scale;
+};
+
+template <bool ARGMAX, bool GRAD>
 __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(ProblemDesc d, WsLayout w,
                                                                               unsigned char *ws,
                                                                               int64_t *argmax_out, int b_major,
-                                                                              RingLayout rl) {
+                                                                              RingLayout rl, GradOut go) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ring ring = ring_setup(smem_raw, rl);
     const int lane = threadIdx.x & 31;
@@ -235,6 +245,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
     const uint32_t row_bytes = (uint32_t)d.V * 4u;
+    float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);      // GRAD only: V zeros for padded frames
+    if (GRAD) {
+        for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
+        fence_proxy_async();
+        __syncthreads();
+    }
 
     if (warp == 0) {
         // ===== producer (lane i owns frame i of the current batch) =====
@@ -253,6 +269,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
                 Tb = max(0, min(Tb, d.T));
                 valid = t < Tb;
                 need = valid || ARGMAX;
+                if (GRAD && !valid) {                                                 // gram_ctc.py:296: zeros, straight from smem
+                    bulk_s2g(go.grad + (int64_t)t * go.gstride_t + (int64_t)b * go.gstride_b, zero_row, row_bytes);
+                    bulk_commit();
+                }
             }
             const unsigned mask = __ballot_sync(0xffffffffu, need);
             if (need) {
@@ -267,6 +287,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
             q += (unsigned)__popc(mask);
         }
         ring_stop(ring, q, lane);
+        if (GRAD) bulk_wait_all<0>();
         return;
     }
 
@@ -342,10 +363,33 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
                 if (sym >= 0 && sym < d.V) v = split_log2p(row[sym], la, lb);
                 lprow[cidx] = v;
             }
+            if (GRAD) {
+                // softmax * scale in place (same arithmetic as the gradient kernel), then one bulk store
+                __syncwarp();
+                const float cc = -(la + lb);
+                float4 *w4 = reinterpret_cast<float4 *>(ring.slot(s));
+#pragma unroll 4
+                for (int i = lane; i < n4; i += 32) {
+                    float4 v = w4[i];
+                    v.x = ex2_approx(fmaf(v.x, LOG2E_HI, cc)) * go.scale;
+                    v.y = ex2_approx(fmaf(v.y, LOG2E_HI, cc)) * go.scale;
+                    v.z = ex2_approx(fmaf(v.z, LOG2E_HI, cc)) * go.scale;
+                    v.w = ex2_approx(fmaf(v.w, LOG2E_HI, cc)) * go.scale;
+                    w4[i] = v;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(go.grad + (int64_t)m.t * go.gstride_t + (int64_t)m.b * go.gstride_b, ring.slot(s), row_bytes);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[s]);
     }
+    if (GRAD && lane == 0) bulk_wait_all<0>();
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) argmax_kernel(const float *acts, int64_t stride_t,
@@ -408,15 +452,16 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
         if (ctas > sm_count() - ring_sm_reserve()) ctas = sm_count() - ring_sm_reserve();
         if (ctas < 1) ctas = 1;
+        const GradOut none = {nullptr, 0, 0, 0.f};
         cudaError_t e;
         if (argmax_out) {
-            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
             if (e != cudaSuccess) return e;
-            softmax_gather_ring_kernel<true><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, argmax_out, b_major, rl);
+            softmax_gather_ring_kernel<true, false><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, argmax_out, b_major, rl, none);
         } else {
-            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
             if (e != cudaSuccess) return e;
-            softmax_gather_ring_kernel<false><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, nullptr, b_major, rl);
+            softmax_gather_ring_kernel<false, false><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, nullptr, b_major, rl, none);
         }
         return cudaGetLastError();
     }
@@ -425,6 +470,28 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
         softmax_gather_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, argmax_out, b_major);
     else
         softmax_gather_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, nullptr, b_major);
+    return cudaGetLastError();
+}
+
+// One-read variant: statistics + gather + gradient row (softmax * scale) in the same pass.  Returns
+// cudaErrorNotSupported when the rows do not qualify for the TMA ring (the caller then falls back to the
+// separate gradient kernel).
+cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, void *ws, float *grad, int64_t gstride_t,
+                                       int64_t gstride_b, float scale, cudaStream_t stream) {
+    const long long frames = (long long)d.B * d.T;
+    if (frames == 0) return cudaSuccess;
+    const int b_major = d.stride_b > d.stride_t ? 1 : 0;
+    unsigned char *wsb = static_cast<unsigned char *>(ws);
+    const RingLayout rl = make_ring((size_t)d.V * 4, (size_t)d.V * 4);
+    if (!ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) || !ring_usable(grad, gstride_t, gstride_b, d.V, rl) ||
+        getenv("B200CTC_NO_TMA_K1"))
+        return cudaErrorNotSupported;
+    long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
+    if (ctas > sm_count()) ctas = sm_count();
+    const GradOut go = {grad, gstride_t, gstride_b, scale};
+    cudaError_t e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+    if (e != cudaSuccess) return e;
+    softmax_gather_ring_kernel<false, true><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, nullptr, b_major, rl, go);
     return cudaGetLastError();
 }
 

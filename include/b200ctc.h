@@ -97,14 +97,15 @@ int b200ctc_backward(int kind,
                      const void *workspace, size_t workspace_bytes, void *stream);
 
 /*
- * Pipelined forward + gradient in one call (the fast path for training: GramCTC.forward immediately
- * followed by GramCTC.backward, asr/loss/gram_ctc.py:246-297, as optimizer.update does,
- * run/ctc/cnn/train.py:200).  The batch is cut into `groups` contiguous utterance groups; each group runs
- * softmax/gather -> lattice -> gradient on its own internal stream, so the latency-bound lattice
- * recursion of one group hides behind the bandwidth-bound kernels of the others.  The gradient is written
- * for a unit upstream gradient times grad_scale (1/B_global for 'mean'); b200ctc_rescale_grad applies the
- * real upstream gradient later and is a no-op when it is 1.  Internal streams fork from and join `stream`.
- * The library keeps one small stream/event pool per device for this entry point (its only global state).
+ * Forward + gradient in one call -- the fast path for a training step (GramCTC.forward immediately followed
+ * by GramCTC.backward, asr/loss/gram_ctc.py:246-297, as optimizer.update does, run/ctc/cnn/train.py:200).
+ * "One-read" schedule: while an activation row is staged in shared memory for the softmax statistics the same
+ * kernel also writes softmax * grad_scale as that frame's gradient row; after the lattice recursion a small kernel
+ * subtracts the merged posteriors at the <= L+1 label columns.  The activations are read from HBM once per step
+ * instead of twice (8 instead of 12 bytes per element of algorithmic traffic).  The gradient is written for a
+ * unit upstream gradient times grad_scale (1/B_global for 'mean'); b200ctc_rescale_grad applies the real upstream
+ * gradient later and is a no-op when it is 1.  `groups` is reserved (pass 1).  Needs its own workspace size
+ * (b200ctc_fused_workspace_bytes); that workspace also serves a later b200ctc_backward.
  */
 int b200ctc_fused_workspace_bytes(int kind, int B, int T, int V, int Lmax, int groups, size_t *bytes_out);
 int b200ctc_forward_backward(int kind,
