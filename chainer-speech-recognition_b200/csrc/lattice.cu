@@ -22,7 +22,7 @@
 //     reading the per-frame boundary values warp w left behind.  Hand-over is by mbarrier, once per
 //     chunk, so no step ever waits on a CTA-wide barrier;
 //   * the per-frame rows of gathered label log-probs are staged in shared memory by 1-D bulk async
-//     copies (TMA engine) issued by the direction's first warp two chunks ahead.
+//     copies (TMA engine) issued by a dedicated I/O warp per direction, as far ahead as the stage ring allows.
 //
 // Both directions run the full utterance: alpha writes av[t][j] = alpha_t[j], beta writes bv[t][j] = beta_t[j],
 // as split-log2 pairs.  log P is read off alpha at the last frame.  The gradient kernel forms
@@ -48,9 +48,8 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 namespace {
 
 constexpr int kChunk = 8;        // frames per pipeline chunk
-constexpr int kMaxAhead = 2;     // chunks of emission rows in flight ahead of the first warp
-constexpr int kMaxStages = 8;    // >= kMaxAhead + W + 1, or the first warp stalls on the last one's progress
-constexpr int kMaxWarpsPerDir = 16;
+constexpr int kMaxStages = 8;    // deep enough that the I/O warp never waits on the last compute warp (W + 3)
+constexpr int kMaxWarpsPerDir = 15;   // + 1 I/O warp per direction = 1024 threads
 
 // CTC, reversed direction: the lattice is indexed with one phantom node in front (q = 0 <-> j = Nb, never
 // reachable), i.e. q <-> j = Nb - q.  That flips the slot parity (slot 0 = label, slot 1 = blank) and makes each
@@ -244,6 +243,32 @@ __device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, b
     store_results<K, GRAM, REV>(outv, out, st.valid, lane);
 }
 
+// The direction's I/O warp: stages the emission rows of every chunk, as far ahead as the stage ring allows.
+// Keeping this off the compute warps matters: the recursion is a single dependent chain per warp, and the ~300
+// cycles per chunk that waiting for a free stage and issuing the copy cost were all on the first warp's path.
+template <bool REV>
+__device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c, int f0, int n, int lane) {
+    if (n <= 0 || lane != 0) return;
+    const int S = c.S;
+    const int nchunks = (n + kChunk - 1) / kChunk;
+    const uint32_t row_bytes = (uint32_t)c.Wlp * 8u;
+    const uint32_t stage_bytes = row_bytes * kChunk;
+    int stage = 0;
+    uint32_t wrap = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int i0 = ch * kChunk;
+        const int cnt = min(kChunk, n - i0);
+        const int flo = REV ? (f0 - i0 - cnt + 1) : (f0 + i0);
+        if (wrap > 0) mbar_wait_backoff(&pp.consumed[stage], (wrap - 1) & 1u);
+        mbar_arrive_expect_tx(&pp.full[stage], row_bytes * cnt);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pp.lp + (uint32_t)stage * stage_bytes),
+                     "l"(c.lp_g + (size_t)flo * c.Wlp), "r"(row_bytes * cnt), "r"(smem_u32(&pp.full[stage]))
+                     : "memory");
+        if (++stage == S) { stage = 0; ++wrap; }
+    }
+}
+
 // Visit n frames starting at f0 (ascending for alpha, descending for beta) with warp w of W.
 template <int K, bool GRAM, bool REV>
 __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirPipe &pp, const UttCtx &c, int f0, int n,
@@ -251,9 +276,7 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
     constexpr int PAD = Geo<K, GRAM>::PAD;
     if (n <= 0) return;
     const int W = c.W, S = c.S;
-    const int kAhead = min(kMaxAhead, S - 1);
     const int nchunks = (n + kChunk - 1) / kChunk;
-    const bool leader = (w == 0);
     const bool has_prev = (w > 0), has_next = (w + 1 < W);
     const uint32_t row_bytes = (uint32_t)c.Wlp * 8u;
     const uint32_t stage_bytes = row_bytes * kChunk;
@@ -262,25 +285,6 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
     const int jbase = REV ? (c.Nb - 1 - K * gl) : (K * gl);
     const int64_t frame_step = REV ? -(int64_t)c.Np : (int64_t)c.Np;
     float2 *out_ptr = c.out_g + (size_t)f0 * c.Np + jbase;    // this lane's first node in frame f0
-
-    // leader bookkeeping: next chunk to issue, its stage and how often that stage has been used
-    int is_chunk = 0, is_stage = 0;
-    uint32_t is_wrap = 0;
-    auto issue = [&]() {                                      // leader, lane 0
-        const int i0 = is_chunk * kChunk;
-        const int cnt = min(kChunk, n - i0);
-        const int flo = REV ? (f0 - i0 - cnt + 1) : (f0 + i0);
-        if (is_wrap > 0) mbar_wait(&pp.consumed[is_stage], (is_wrap - 1) & 1u);
-        mbar_arrive_expect_tx(&pp.full[is_stage], row_bytes * cnt);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         pp.lp + (uint32_t)is_stage * stage_bytes),
-                     "l"(c.lp_g + (size_t)flo * c.Wlp), "r"(row_bytes * cnt), "r"(smem_u32(&pp.full[is_stage]))
-                     : "memory");
-        ++is_chunk;
-        if (++is_stage == S) { is_stage = 0; ++is_wrap; }
-    };
-    if (leader && lane == 0)
-        for (int ch = 0; ch < min(kAhead, nchunks); ++ch) issue();
 
     int stage = 0;
     uint32_t wrap = 0;
@@ -292,7 +296,6 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
         if (prof) tq0 = clock64();
         if (has_prev) mbar_wait_backoff(&pp.ready[(w - 1) * S + stage], wrap & 1u);
         if (prof) tq1 = clock64();
-        if (leader && lane == 0 && is_chunk < nchunks) issue();
         if (prof) tq2 = clock64();
         mbar_wait(&pp.full[stage], wrap & 1u);
         if (prof) { tq3 = clock64(); acc_ready += tq1 - tq0; acc_issue += tq2 - tq1; acc_full += tq3 - tq2; }
@@ -420,7 +423,7 @@ __device__ __forceinline__ void init_barriers(uint64_t *bars, int nbars_dir, int
 // MAXW bounds the warps per direction of an instantiation, so that small lattices (the common case) are not
 // compiled under the 64-register cap a 1024-thread CTA implies.
 template <int K, bool GRAM, int MAXW>
-__global__ void __launch_bounds__(64 * MAXW, 1) lattice_kernel(LatticeParams p) {
+__global__ void __launch_bounds__(64 * (MAXW + 1), 1) lattice_kernel(LatticeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PAD = Geo<K, GRAM>::PAD;
     const ProblemDesc &d = p.d;
@@ -432,8 +435,10 @@ __global__ void __launch_bounds__(64 * MAXW, 1) lattice_kernel(LatticeParams p) 
     const int W = p.W, S = p.S;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int dir = warp >= W ? 1 : 0;
-    const int w = warp - dir * W;
+    // warps [0,W): alpha, [W,2W): beta, 2W: alpha's I/O warp, 2W+1: beta's I/O warp
+    const bool io = warp >= 2 * W;
+    const int dir = io ? (warp - 2 * W) : (warp >= W ? 1 : 0);
+    const int w = io ? 0 : warp - dir * W;
     UttInfo *ui = reinterpret_cast<UttInfo *>(p.ws + p.w.off_utt) + b;
     WsHeader *hdr = reinterpret_cast<WsHeader *>(p.ws + p.w.off_hdr);
 
@@ -464,10 +469,15 @@ __global__ void __launch_bounds__(64 * MAXW, 1) lattice_kernel(LatticeParams p) 
         c.lp_g = reinterpret_cast<const float2 *>(p.ws + p.w.off_lp) + (size_t)b * d.T * p.w.W;
         c.out_g = dir == 0 ? av : bv;
         c.Wlp = p.w.W; c.Np = p.w.Np; c.Nb = Nb; c.W = W; c.S = S;
-        LaneState<K, GRAM> st;
-        init_lane<K, GRAM>(st, d, b, Lb, Nb, dir == 1, 32 * w + lane);
-        if (dir == 0) run_direction<K, GRAM, false>(st, pp, c, 0, Tb, w, lane);         // alpha: frames 0 .. Tb-1
-        else          run_direction<K, GRAM, true>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
+        if (io) {
+            if (dir == 0) io_direction<false>(pp, c, 0, Tb, lane);
+            else          io_direction<true>(pp, c, Tb - 1, Tb, lane);
+        } else {
+            LaneState<K, GRAM> st;
+            init_lane<K, GRAM>(st, d, b, Lb, Nb, dir == 1, 32 * w + lane);
+            if (dir == 0) run_direction<K, GRAM, false>(st, pp, c, 0, Tb, w, lane);         // alpha: frames 0 .. Tb-1
+            else          run_direction<K, GRAM, true>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
+        }
     }
     __threadfence_block();
     __syncthreads();
@@ -530,7 +540,7 @@ cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
     auto kern = lattice_kernel<K, GRAM, MAXW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<2 * p.d.B, 64 * p.W, smem, stream>>>(p);
+    kern<<<2 * p.d.B, 64 * (p.W + 1), smem, stream>>>(p);
     return cudaGetLastError();
 }
 
