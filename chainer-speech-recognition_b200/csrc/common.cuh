@@ -1,17 +1,19 @@
 // common.cuh -- shared device helpers and the workspace layout of the B200 CTC / Gram-CTC library.
 //
-// Number format used by the lattice recursion ("split log2"): a log2-probability is carried as a
-// pair (hi, lo) of float32 with hi integer-valued and |lo| <~ 1.  Sums of hi parts are exact, so
-// alpha/beta values of magnitude 10^4 (T=800 frames x ~12 bits) keep an absolute resolution of
-// ~1e-7 without any per-frame renormalisation pass, and nothing can under/overflow the way a
-// linear-space recursion would.  SENT marks log(0) (the reference uses -1e10, gram_ctc.py:222).
+// Number format used by the lattice recursion ("scaled linear"): a probability is carried as a pair
+// (m, e) of float32 meaning m * 2^e, with e integer-valued (exact up to 2^24) and m a plain mantissa
+// that is pulled back into [1,2) every few frames.  One exponent PER NODE, so neither the range between
+// nodes of one frame nor the decay along the utterance (T=800 frames x ~12 bits) can under/overflow, and
+// the recursion needs no exp/log at all: aligning two values is a multiplication by an exact power of two.
+// Probability zero is (0, SENT); any exponent below SENT_TEST means zero (the reference's log-space code
+// uses -1e10 for log 0, gram_ctc.py:222).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace b200ctc {
 
-constexpr float SENT = -1.0e30f;              // "log 0" for hi parts
+constexpr float SENT = -1.0e30f;              // exponent of probability zero ("log 0")
 constexpr float SENT_TEST = -1.0e29f;         // anything below this is treated as log 0
 constexpr float LOG2E_HI = 1.44269502162933349609375f;      // float(log2 e)
 constexpr float LOG2E_LO = 1.92596299112661746e-8f;         // log2 e - LOG2E_HI
@@ -24,8 +26,8 @@ struct UttInfo {
     int Lb;        // clamped label length
     int Nb;        // lattice nodes: 2*Lb+1 (CTC) or 3*Lb+1 (Gram-CTC)
     int Ub;        // number of distinct symbols the lattice can emit (blank included), sorted by id
-    float Ph;      // log2 P, integer part   (+1e30 when the alignment is infeasible)
-    float Pl;      // log2 P, fractional part
+    float Ph;      // P = 2^Ph / Pl: integer exponent (+1e30 when the alignment is infeasible) ...
+    float Pl;      // ... and the INVERSE of the mantissa in [1,2)  (0 when infeasible)
     float loss;    // -ln P, or 1e10 when infeasible (reference quirk)
     int flags;     // bit0: lengths were out of range and got clamped
     int ublank;    // position of the blank id in the sorted distinct-symbol list
@@ -68,7 +70,7 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     w.off_utt = o;   o = align_up(o + sizeof(UttInfo) * (size_t)B, 256);
     w.off_lse = o;   o = align_up(o + sizeof(float) * BT, 256);
     w.off_lp = o;    o = align_up(o + sizeof(float2) * BT * w.W, 256);
-    w.off_av = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // alpha_t[j], split log2
+    w.off_av = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // alpha_t[j] as (m, e)
     w.off_bv = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // beta_t[j] (excludes emission at t)
     w.off_usym = o;  o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
     w.off_uoff = o;  o = align_up(o + sizeof(int) * (size_t)B * (w.Nmax + 1), 256);
@@ -97,6 +99,27 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // rint for |x| < 2^22 on the FMA pipe (FRND would go through the slow conversion unit)
 __device__ __forceinline__ float rint_small(float x) {
     return __fsub_rn(__fadd_rn(x, RINT_MAGIC), RINT_MAGIC);
+}
+
+// 2^d for an integer-valued d <= 0, exact, on the FMA/ALU pipes; anything below -126 (SENT included) gives 0
+__device__ __forceinline__ float pow2_nonpos(float d) {
+    const float c = fmaxf(d, -127.f);
+    return __uint_as_float((__float_as_uint(c + RINT_MAGIC) << 23) + 0x3f800000u);
+}
+// (m, e) -> the same value with m in [1,2); zero, NaN and Inf are left alone
+__device__ __forceinline__ void renorm_pair(float &m, float &e) {
+    const uint32_t b = __float_as_uint(m);
+    const uint32_t x = (b >> 23) & 0xffu;
+    if (x != 0u && x != 255u) {
+        e += (float)((int)x - 127);
+        m = __uint_as_float((b & 0x807fffffu) | 0x3f800000u);
+    }
+}
+// alpha * beta / P for one lattice node (gram_ctc.py:290 "exp(label_prob - total)" before the per-symbol merge):
+// a, b = (m, e) pairs, Ph / Pinv as in UttInfo.  ex2.approx is exact on integers (checked -140..115 on sm_100a,
+// tools/ubench_step_linear.cu) and flushes to 0 below -126.
+__device__ __forceinline__ float node_posterior(float2 a, float2 b, float Ph, float Pinv) {
+    return (a.x * b.x) * ex2_approx((a.y + b.y) - Ph) * Pinv;
 }
 
 __device__ __forceinline__ float warp_max(float v) {

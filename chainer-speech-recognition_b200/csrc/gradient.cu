@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     const ProblemDesc &d = gp.d;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;        // [Np]   2^gamma of this frame
+    float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;        // [Np]   alpha*beta/P of this frame
     float *post_sm = e_sm + w.Np;                                    // [Umax] merged posterior * sc, by sorted id
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
@@ -93,13 +93,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         const float sc = gy * gp.scale;                                      // :291-294
         const float c = -lse2;
 
-        // ---- posteriors of this frame: e[j] = 2^gamma[t][j], merged per emitted id (:180-217) ----
+        // ---- posteriors of this frame: e[j] = alpha*beta/P[t][j], merged per emitted id (:180-217) ----
         const float2 *arow = av_all + ((size_t)b * d.T + t) * w.Np;
         const float2 *brow = bv_all + ((size_t)b * d.T + t) * w.Np;
         float blank_part = 0.f;
         for (int j = lane; j < ui.Nb; j += 32) {
             const float2 a = __ldg(arow + j), bb = __ldg(brow + j);
-            const float e = ex2_approx(((a.x + bb.x) - ui.Ph) + ((a.y + bb.y) - ui.Pl));    // 2^gamma
+            const float e = node_posterior(a, bb, ui.Ph, ui.Pl);
             e_sm[j] = e;
             if (j % per == 0) blank_part += e;
         }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         float *row = reinterpret_cast<float *>(ring.slot(s));
         const float2 *a_sm = reinterpret_cast<const float2 *>(row + d.V);       // alpha row
         const float2 *b_sm = a_sm + w.Np;                                    // beta row
-        float *e_sm = reinterpret_cast<float *>(row + d.V);                  // 2^gamma, written over the alpha row
+        float *e_sm = reinterpret_cast<float *>(row + d.V);                  // alpha*beta/P, written over the alpha row
         const UttInfo ui = utt[b];
         const float lse2 = __ldg(lse_all + (size_t)b * d.T + t);
         const float gy = gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss);
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             float e = 0.f;
             if (j < ui.Nb) {
                 const float2 a = a_sm[j], bb = b_sm[j];
-                e = ex2_approx(((a.x + bb.x) - ui.Ph) + ((a.y + bb.y) - ui.Pl));         // 2^gamma
+                e = node_posterior(a, bb, ui.Ph, ui.Pl);
             }
             __syncwarp();                                                    // e_sm aliases the alpha row: reads first
             if (j < ui.Nb) e_sm[j] = e;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(Grad
 #pragma unroll
                 for (int k = 0; k < kPatchNodeIters; ++k) {
                     const int j = lane + 32 * k;
-                    L.av[k] = make_float2(SENT, 0.f); L.bv[k] = make_float2(SENT, 0.f);
+                    L.av[k] = make_float2(0.f, SENT); L.bv[k] = make_float2(0.f, SENT);
                     if (j < ui.Nb) { L.av[k] = __ldg(arow + j); L.bv[k] = __ldg(brow + j); }
                 }
 #pragma unroll
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(Grad
                 for (int k = 0; k < kPatchNodeIters; ++k) {
                     const int j = lane + 32 * k;
                     if (j < ui.Nb) {
-                        const float e = ex2_approx(((L.av[k].x + L.bv[k].x) - ui.Ph) + ((L.av[k].y + L.bv[k].y) - ui.Pl));
-                        e_sm[j] = e;                                            // 2^gamma
+                        const float e = node_posterior(L.av[k], L.bv[k], ui.Ph, ui.Pl);
+                        e_sm[j] = e;                                            // alpha*beta/P
                         if (j % per == 0) blank_part += e;
                     }
                 }
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(Grad
                 float blank_part = 0.f;
                 for (int j = lane; j < ui.Nb; j += 32) {
                     const float2 a = __ldg(arow + j), bb = __ldg(brow + j);
-                    const float e = ex2_approx(((a.x + bb.x) - ui.Ph) + ((a.y + bb.y) - ui.Pl));
+                    const float e = node_posterior(a, bb, ui.Ph, ui.Pl);
                     e_sm[j] = e;
                     if (j % per == 0) blank_part += e;
                 }

@@ -10,31 +10,41 @@
 //            reversed type 0 (blank): q, q-1, q-5        type 1 (bigram): q, q-1, q-2, q-6*
 //                     type 2 (unigram): q, q-2, q-3*, q-7          (* = only if the two ids differ)
 //
-// Mapping.  One CTA per utterance, 2*W warps: warps [0,W) run alpha forward in time, warps [W,2W)
-// run beta backward in time on the reversed lattice.  Within a direction warp w owns nodes
-// [w*32K, (w+1)*32K), K consecutive nodes per lane, all state in registers.  The recursion is a chain
-// of dependent instructions per node, so it is bound by the issue rate of a single warp (ncu: IPC 0.5,
-// stall = fixed-latency "wait"); K is therefore kept small (2 for CTC, 3 for Gram-CTC) and the lattice is
-// spread over several warps, i.e. several SM sub-partitions issue in parallel.
+// Arithmetic.  The reference works in log space (one logsumexp per node and frame: 3-4 exp + 1 log on the
+// critical path).  Here every lattice value is a pair (m, e) = m * 2^e with a float32 mantissa and an
+// integer-valued float32 exponent PER NODE (common.cuh, "scaled linear").  A step is then
+//     E = max_i e_i;   pre = sum_i m_i * 2^(e_i - E);   m' = pre * em;   e' = E + ee
+// where (em, ee) is the emission probability in the same format.  The exponent recursion is a (max,+) chain
+// that does not depend on the mantissas, the mantissa chain is FMUL/FFMA only, the scale factors 2^(e_i - E)
+// are exact powers of two built on the integer pipe, and the mantissas are pulled back into [1,2) once per
+// chunk of frames (they drift by at most a factor 2^-1 .. 3 per frame).  Nothing can under/overflow whatever
+// the dynamic range between nodes or along the utterance is; a microbenchmark of the step gives ~62 cycles
+// against ~225 for the log-space step this replaces (tools/ubench_step_linear.cu, tools/ubench_step.cu).
+//
+// Mapping.  Two CTAs per utterance: one runs alpha forward in time, the other beta backward in time on the
+// reversed lattice (the two are independent until the gradient kernel multiplies them; on separate SMs they
+// do not share an issue port or the SM's store bandwidth, which is what bounds a step once the arithmetic is
+// cheap: 2 x Np float2 per frame).  Within a CTA warp w owns nodes [w*32K, (w+1)*32K), K consecutive nodes per
+// lane, all state in registers; K is kept small (2 for CTC, 3 for Gram-CTC) because the step is bound by the
+// issue rate and the dependent chain of a single warp, so the lattice is spread over several warps, i.e. SM
+// sub-partitions.
 //   * inside a warp the 2 (CTC) / 7 (Gram) boundary values come from the lower lanes by warp shuffle;
 //   * between warps they travel through shared memory, and the warps run as a systolic pipeline at
-//     chunk granularity (8 frames): warp w works on chunk c while warp w+1 works on chunk c-1 or c-2,
-//     reading the per-frame boundary values warp w left behind.  Hand-over is by mbarrier, once per
-//     chunk, so no step ever waits on a CTA-wide barrier;
-//   * the per-frame rows of gathered label log-probs are staged in shared memory by 1-D bulk async
-//     copies (TMA engine) issued by a dedicated I/O warp per direction, as far ahead as the stage ring allows.
+//     chunk granularity (16 frames): warp w works on chunk c while warp w+1 works on chunk c-1,
+//     reading the per-frame boundary values warp w left behind.  Hand-over is one mbarrier wait and one
+//     arrive per warp and chunk; the wait for chunk c+1 is issued before the last step of chunk c;
+//   * the per-frame rows of gathered emission probabilities are staged in shared memory by 1-D bulk async
+//     copies (TMA engine) issued by a dedicated I/O warp, as far ahead as the stage ring allows.
 //
-// Both directions run the full utterance: alpha writes av[t][j] = alpha_t[j], beta writes bv[t][j] = beta_t[j],
-// as split-log2 pairs.  log P is read off alpha at the last frame.  The gradient kernel forms
-// gamma = alpha + beta - log P itself while it merges the per-symbol posteriors, so the recursion carries no
-// "combine" work at all (an earlier meet-in-the-middle version that wrote gamma directly spent 40-90% more
-// cycles per step on the second half).
+// Both directions run the full utterance: alpha writes av[t][j] = alpha_t[j], beta writes bv[t][j] = beta_t[j].
+// P is read off alpha at the last frame.  The gradient kernel forms alpha * beta / P itself while it merges
+// the per-symbol posteriors, so the recursion carries no "combine" work at all.
 //
 // beta convention as in the reference (:171-175): beta_t EXCLUDES the emission at t, so
-// alpha_t + beta_t sums (in the log-sum-exp sense) to log P at every valid frame.
+// sum_j alpha_t[j] * beta_t[j] = P at every valid frame.
 //
 // The same launch carries B extra CTAs that build the gradient kernel's symbol tables (prep.cuh) while
-// the recursion runs, and the last lattice CTA to finish reduces the batch loss in a fixed order.
+// the recursion runs, and the last alpha CTA to finish reduces the batch loss in a fixed order.
 #include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -47,14 +57,14 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 
 namespace {
 
-constexpr int kChunk = 8;        // frames per pipeline chunk
-constexpr int kMaxStages = 8;    // deep enough that the I/O warp never waits on the last compute warp (W + 3)
-constexpr int kMaxWarpsPerDir = 15;   // + 1 I/O warp per direction = 1024 threads
+constexpr int kChunk = 16;       // frames per pipeline chunk (and per mantissa renormalisation)
+constexpr int kMaxStages = 8;    // W + 3 is deep enough that the I/O warp never waits on the last compute warp
+constexpr int kMaxWarpsPerDir = 16;
 
 // CTC, reversed direction: the lattice is indexed with one phantom node in front (q = 0 <-> j = Nb, never
-// reachable), i.e. q <-> j = Nb - q.  That flips the slot parity (slot 0 = label, slot 1 = blank) and makes each
-// lane's two nodes an ALIGNED pair (j even, j+1) in memory, so the beta rows are written with the same single
-// 16-byte store per lane as the alpha rows.
+// reachable: it starts at zero and has no live predecessor), i.e. q <-> j = Nb - q.  That flips the slot parity
+// (slot 0 = label, slot 1 = blank) and makes each lane's two nodes an ALIGNED pair (j even, j+1) in memory, so
+// the beta rows are written with the same single 16-byte store per lane as the alpha rows.
 template <int K, bool GRAM, bool REV>
 struct Shifted {
     static constexpr bool value = REV && !GRAM && K == 2;
@@ -68,32 +78,41 @@ struct Geo {
 
 template <int K, bool GRAM>
 struct LaneState {
-    float h[K], l[K];        // split-log2 value of the K nodes this lane owns
+    float m[K], e[K];        // mantissa / exponent of the K nodes this lane owns (post-emission)
     int ci[K];               // column of each node's symbol in the emission row (0 = blank)
-    uint32_t flag;           // bit r: the "ids differ" edge into slot r is open
-    uint32_t dead;           // bit r: dead node (bigram id -1, gram_ctc.py:94-98)
+    float openoff[K];        // 0 when the "ids differ" edge into slot r is open, SENT when it is closed
     uint32_t valid;          // bit r: node index < Nb
 };
 
-// shared-memory view of one direction's pipeline (32-bit shared-space addresses: no generic-pointer
-// conversion inside the recursion loop)
+// shared-memory view of the pipeline (32-bit shared-space addresses: no generic-pointer conversion inside the
+// recursion loop)
 struct DirPipe {
     uint32_t lp;             // [S][kChunk][Wlp] float2   staged emission rows
     uint32_t bnd;            // [W-1][S][kChunk][PAD] float2 boundary values handed from warp w to warp w+1;
                              //   as deep as the stage ring, so a buffer is free by the time it comes round again
-                             //   (a warp can only be at chunk c once every warp has consumed chunk c-S)
-    uint64_t *full;          // [S]     emission rows of a chunk have landed (tx count)
-    uint64_t *consumed;      // [S]     all W warps are done with the stage
-    uint64_t *ready;         // [W-1][S] warp w finished the chunk: its boundary values can be read
+                             //   (a warp can only be at chunk c once the last warp has consumed chunk c-S)
+    uint32_t bnd_none;       // [kChunk][PAD] float2 of (0, SENT): what warp 0 reads as "the warp before me"
+    uint64_t *full;          // [S]     emission rows of a chunk have landed (tx count); warp 0 waits on it
+    uint64_t *consumed;      // [S]     the last warp is done with the stage (hence every warp is)
+    uint64_t *ready;         // [W-1][S] warp w finished the chunk: its boundary values can be read, and the
+                             //          stage's emission rows are known to have landed
 };
 
+// Shared-memory loads as PURE asm (no volatile, no memory clobber): the compiler may hoist them to the top of a
+// chunk, off the dependent chain.  They cannot cross a barrier wait because their address is derived from a
+// token that the wait defines (after_wait()).
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     float2 v;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts_f2(uint32_t addr, float x, float y) {
-    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(x), "f"(y));
+}
+__device__ __forceinline__ uint32_t after_wait(uint32_t addr) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(addr) : "memory");
+    return r;
 }
 
 struct UttCtx {
@@ -102,105 +121,90 @@ struct UttCtx {
     int Wlp, Np, Nb, W, S;
 };
 
-// ---- one lattice step: new (pre-emission) value of slot R from the extended old array ----
-// eh/el hold nodes [K*gl - PAD, K*gl + K) for this lane; index PAD + R is slot R itself.
+// ---- one lattice step: new (pre-emission) value of slot R from the extended old arrays ----
+// xm/xe hold nodes [K*gl - PAD, K*gl + K) for this lane; index PAD + R is slot R itself.
 template <int K, bool GRAM, bool REV, int R>
-__device__ __forceinline__ void slot_update(const float (&eh)[Geo<K, GRAM>::EXT], const float (&el)[Geo<K, GRAM>::EXT],
-                                            uint32_t flag, uint32_t dead, float &pre_h, float &pre_l) {
+__device__ __forceinline__ void slot_update(const float (&xm)[Geo<K, GRAM>::EXT], const float (&xe)[Geo<K, GRAM>::EXT],
+                                            float openoff, float &pre_m, float &pre_e) {
     constexpr int PAD = Geo<K, GRAM>::PAD;
     constexpr int I = PAD + R;
-    const bool open = (flag >> R) & 1u;
     if constexpr (!GRAM) {
         constexpr bool SH = Shifted<K, GRAM, REV>::value;
         if constexpr (((R & 1) == 0) != SH) {                 // blank node: self, q-1
-            const float hm = fmaxf(eh[I], eh[I - 1]);
-            const float d0 = (eh[I] - hm) + el[I];
-            const float d1 = (eh[I - 1] - hm) + el[I - 1];
-            pre_h = hm;
-            pre_l = lg2_approx(ex2_approx(d0) + ex2_approx(d1));
+            const float E = fmaxf(xe[I], xe[I - 1]);
+            pre_m = fmaf(xm[I - 1], pow2_nonpos(xe[I - 1] - E), xm[I] * pow2_nonpos(xe[I] - E));
+            pre_e = E;
         } else {                                              // label node: self, q-1, q-2*
-            const float h2 = open ? eh[I - 2] : SENT;
-            const float hm = fmaxf(fmaxf(eh[I], eh[I - 1]), h2);
-            const float d0 = (eh[I] - hm) + el[I];
-            const float d1 = (eh[I - 1] - hm) + el[I - 1];
-            const float d2 = (h2 - hm) + el[I - 2];
-            pre_h = hm;
-            pre_l = lg2_approx(ex2_approx(d0) + ex2_approx(d1) + ex2_approx(d2));
-            if constexpr (SH && R == 0) {                     // the phantom node in front of the reversed lattice
-                if (dead & 1u) { pre_h = SENT; pre_l = 0.f; }
-            }
+            const float e2 = xe[I - 2] + openoff;
+            const float E = fmaxf(fmaxf(xe[I], xe[I - 1]), e2);
+            float s = xm[I] * pow2_nonpos(xe[I] - E);
+            s = fmaf(xm[I - 1], pow2_nonpos(xe[I - 1] - E), s);
+            s = fmaf(xm[I - 2], pow2_nonpos(e2 - E), s);
+            pre_m = s;
+            pre_e = E;
         }
     } else {
         constexpr int TYPE = R % 3;
-        // predecessor offsets per (direction, type); the starred one is gated by `open`
+        // predecessor offsets per (direction, type); the starred one is gated by `openoff`
         constexpr int A = (TYPE == 0) ? 1 : (!REV ? (TYPE == 1 ? 1 : 5) : (TYPE == 1 ? 1 : 2));
         constexpr int Bk = (TYPE == 0) ? (!REV ? 2 : 5) : (!REV ? (TYPE == 1 ? 2 : 7) : (TYPE == 1 ? 2 : 7));
         constexpr int Cs = (TYPE == 0) ? 0 : (!REV ? (TYPE == 1 ? 3 : 6) : (TYPE == 1 ? 6 : 3));
-        float hm = fmaxf(fmaxf(eh[I], eh[I - A]), eh[I - Bk]);
-        float hc = SENT, lc = 0.f;
+        float E = fmaxf(fmaxf(xe[I], xe[I - A]), xe[I - Bk]);
+        float ec = SENT;
         if constexpr (Cs != 0) {
-            hc = open ? eh[I - Cs] : SENT;
-            lc = el[I - Cs];
-            hm = fmaxf(hm, hc);
+            ec = xe[I - Cs] + openoff;
+            E = fmaxf(E, ec);
         }
-        const float d0 = (eh[I] - hm) + el[I];
-        const float d1 = (eh[I - A] - hm) + el[I - A];
-        const float d2 = (eh[I - Bk] - hm) + el[I - Bk];
-        float s = ex2_approx(d0) + ex2_approx(d1) + ex2_approx(d2);
-        if constexpr (Cs != 0) s += ex2_approx((hc - hm) + lc);
-        pre_h = hm;
-        pre_l = lg2_approx(s);
-        // a bigram node sits at type 2 forward / type 1 reversed
-        constexpr bool CAN_BE_DEAD = (!REV && TYPE == 2) || (REV && TYPE == 1);
-        if constexpr (CAN_BE_DEAD) {
-            if ((dead >> R) & 1u) { pre_h = SENT; pre_l = 0.f; }
-        }
+        float s = xm[I] * pow2_nonpos(xe[I] - E);
+        s = fmaf(xm[I - A], pow2_nonpos(xe[I - A] - E), s);
+        s = fmaf(xm[I - Bk], pow2_nonpos(xe[I - Bk] - E), s);
+        if constexpr (Cs != 0) s = fmaf(xm[I - Cs], pow2_nonpos(ec - E), s);
+        pre_m = s;
+        pre_e = E;
+        // a dead bigram node (id -1, gram_ctc.py:94-98) needs no special case: its emission column holds
+        // probability zero (softmax_gather.cu), so its post-emission state is (0, SENT) at every frame
     }
 }
 
 // Old values of the PAD nodes below this lane's first node: from lower lanes by shuffle, or -- for the first
-// BACK lanes of a warp -- from the previous warp's boundary record (SENT if there is no previous warp).
+// lanes of a warp -- from the previous warp's boundary record (warp 0 reads a constant record of zeros).
 // Branch-free: every lane reads a (clamped) boundary slot and the right source is picked by select.
 template <int K, bool GRAM>
-__device__ __forceinline__ void gather_ext(const LaneState<K, GRAM> &st, float (&eh)[Geo<K, GRAM>::EXT],
-                                           float (&el)[Geo<K, GRAM>::EXT], int lane, bool has_prev, uint32_t bnd_in) {
+__device__ __forceinline__ void gather_ext(const LaneState<K, GRAM> &st, float (&xm)[Geo<K, GRAM>::EXT],
+                                           float (&xe)[Geo<K, GRAM>::EXT], int lane, uint32_t bnd_in) {
     constexpr int PAD = Geo<K, GRAM>::PAD;
 #pragma unroll
-    for (int e = 0; e < PAD; ++e) {
-        const int delta = (PAD - e + K - 1) / K;              // lanes back (compile-time after unrolling)
-        const int slot = e - PAD + K * delta;
-        const float2 bv = lds_f2(bnd_in + 8u * (uint32_t)min(K * lane + e, PAD - 1));
-        const float nh = __shfl_up_sync(0xffffffffu, st.h[slot], delta);
-        const float nl = __shfl_up_sync(0xffffffffu, st.l[slot], delta);
+    for (int x = 0; x < PAD; ++x) {
+        const int delta = (PAD - x + K - 1) / K;              // lanes back (compile-time after unrolling)
+        const int slot = x - PAD + K * delta;
+        const float2 bv = lds_f2(bnd_in + 8u * (uint32_t)min(K * lane + x, PAD - 1));
+        const float nm = __shfl_up_sync(0xffffffffu, st.m[slot], delta);
+        const float ne = __shfl_up_sync(0xffffffffu, st.e[slot], delta);
         const bool edge = lane < delta;
-        eh[e] = edge ? (has_prev ? bv.x : SENT) : nh;
-        el[e] = edge ? (has_prev ? bv.y : 0.f) : nl;
+        xm[x] = edge ? bv.x : nm;
+        xe[x] = edge ? bv.y : ne;
     }
 #pragma unroll
     for (int r = 0; r < K; ++r) {
-        eh[PAD + r] = st.h[r];
-        el[PAD + r] = st.l[r];
+        xm[PAD + r] = st.m[r];
+        xe[PAD + r] = st.e[r];
     }
 }
 
 template <int K, bool GRAM, bool REV, int R>
 struct SlotLoop {
-    __device__ __forceinline__ static void run(LaneState<K, GRAM> &st, const float (&eh)[Geo<K, GRAM>::EXT],
-                                               const float (&el)[Geo<K, GRAM>::EXT], uint32_t lprow, float2 (&outv)[K]) {
-        float ph, pl;
-        slot_update<K, GRAM, REV, R>(eh, el, st.flag, st.dead, ph, pl);
-        const float2 e = lds_f2(lprow + 8u * (uint32_t)st.ci[R]);
-        // post-emission value, renormalised so that hi stays integer-valued and |lo| <= 0.5
-        float nl = pl + e.y;
-        float nh = ph + e.x;
-        const float rr = rint_small(nl);
-        nh += rr;
-        nl -= rr;
-        st.h[R] = nh;
-        st.l[R] = nl;
+    __device__ __forceinline__ static void run(LaneState<K, GRAM> &st, const float (&xm)[Geo<K, GRAM>::EXT],
+                                               const float (&xe)[Geo<K, GRAM>::EXT], uint32_t lprow, float2 (&outv)[K]) {
+        float pm, pe;
+        slot_update<K, GRAM, REV, R>(xm, xe, st.openoff[R], pm, pe);
+        const float2 em = lds_f2(lprow + 8u * (uint32_t)st.ci[R]);       // emission (mantissa, exponent)
+        const float nm = pm * em.x;
+        const float ne = pe + em.y;
+        st.m[R] = nm;
+        st.e[R] = ne;
         // alpha keeps the emission at t, beta excludes it (gram_ctc.py:171-175)
-        outv[R] = REV ? make_float2(ph, pl) : make_float2(nh, nl);
-        if constexpr (R + 1 < K) SlotLoop<K, GRAM, REV, R + 1>::run(st, eh, el, lprow, outv);
+        outv[R] = REV ? make_float2(pm, pe) : make_float2(nm, ne);
+        if constexpr (R + 1 < K) SlotLoop<K, GRAM, REV, R + 1>::run(st, xm, xe, lprow, outv);
     }
 };
 
@@ -227,25 +231,24 @@ __device__ __forceinline__ void store_results(const float2 (&outv)[K], float2 *o
 
 // one frame of the recursion for this lane
 template <int K, bool GRAM, bool REV>
-__device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, bool has_prev, bool has_next,
+__device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, bool has_next,
                                              uint32_t bin, uint32_t bout, uint32_t lprow, float2 *out) {
     constexpr int PAD = Geo<K, GRAM>::PAD;
-    float eh[Geo<K, GRAM>::EXT], el[Geo<K, GRAM>::EXT];
-    gather_ext<K, GRAM>(st, eh, el, lane, has_prev, bin);
+    float xm[Geo<K, GRAM>::EXT], xe[Geo<K, GRAM>::EXT];
+    gather_ext<K, GRAM>(st, xm, xe, lane, bin);
     // leave my last PAD nodes' old values for warp w+1 (predicated stores, no branch)
 #pragma unroll
     for (int r = 0; r < K; ++r) {
         const int idx = K * lane + r - (32 * K - PAD);
-        if (has_next && idx >= 0) sts_f2(bout + 8u * (uint32_t)idx, st.h[r], st.l[r]);
+        if (has_next && idx >= 0) sts_f2(bout + 8u * (uint32_t)idx, st.m[r], st.e[r]);
     }
     float2 outv[K];
-    SlotLoop<K, GRAM, REV, 0>::run(st, eh, el, lprow, outv);
+    SlotLoop<K, GRAM, REV, 0>::run(st, xm, xe, lprow, outv);
     store_results<K, GRAM, REV>(outv, out, st.valid, lane);
 }
 
-// The direction's I/O warp: stages the emission rows of every chunk, as far ahead as the stage ring allows.
-// Keeping this off the compute warps matters: the recursion is a single dependent chain per warp, and the ~300
-// cycles per chunk that waiting for a free stage and issuing the copy cost were all on the first warp's path.
+// The I/O warp: stages the emission rows of every chunk, as far ahead as the stage ring allows.
+// Keeping this off the compute warps matters: the recursion is a single dependent chain per warp.
 template <bool REV>
 __device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c, int f0, int n, int lane) {
     if (n <= 0 || lane != 0) return;
@@ -285,52 +288,62 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
     const int jbase = REV ? (c.Nb - 1 - K * gl) : (K * gl);
     const int64_t frame_step = REV ? -(int64_t)c.Np : (int64_t)c.Np;
     float2 *out_ptr = c.out_g + (size_t)f0 * c.Np + jbase;    // this lane's first node in frame f0
+    // what this warp waits for before a chunk: warp 0 the emission rows, the others the warp before them (which
+    // has seen the emission rows land by then); what it signals after: the next warp, or -- the last warp -- the
+    // I/O warp that the stage is free
+    uint64_t *const wait_bar = has_prev ? pp.ready + (w - 1) * S : pp.full;
+    uint64_t *const done_bar = has_next ? pp.ready + w * S : pp.consumed;
 
     int stage = 0;
     uint32_t wrap = 0;
-    long long acc_ready = 0, acc_issue = 0, acc_full = 0, acc_work = 0, acc_tail = 0;
+    bool early = false;                                       // the wait for the coming chunk already succeeded
+    long long acc_wait = 0, acc_work = 0, acc_tail = 0;
     const bool prof = (g_lat_dbg != nullptr) && lane == 0 && blockIdx.x < 64;
     for (int ch = 0; ch < nchunks; ++ch) {
         const int cnt = min(kChunk, n - ch * kChunk);
-        long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+        long long tq0 = 0, tq1 = 0, tq2 = 0;
         if (prof) tq0 = clock64();
-        if (has_prev) mbar_wait_backoff(&pp.ready[(w - 1) * S + stage], wrap & 1u);
-        if (prof) tq1 = clock64();
-        if (prof) tq2 = clock64();
-        mbar_wait(&pp.full[stage], wrap & 1u);
-        if (prof) { tq3 = clock64(); acc_ready += tq1 - tq0; acc_issue += tq2 - tq1; acc_full += tq3 - tq2; }
+        if (!early) {
+            if (ch == 0) mbar_wait_backoff(&wait_bar[stage], wrap & 1u);
+            else mbar_wait(&wait_bar[stage], wrap & 1u);
+        }
+        if (prof) { tq1 = clock64(); acc_wait += tq1 - tq0; }
 
-        const uint32_t lp_s = pp.lp + (uint32_t)stage * stage_bytes;
-        const uint32_t bin = pp.bnd + (uint32_t)((has_prev ? w - 1 : 0) * S + stage) * bnd_chunk_bytes;
+        const uint32_t lp_s = after_wait(pp.lp + (uint32_t)stage * stage_bytes);
+        const uint32_t bin = after_wait(has_prev ? pp.bnd + (uint32_t)((w - 1) * S + stage) * bnd_chunk_bytes : pp.bnd_none);
         const uint32_t bout = pp.bnd + (uint32_t)((has_next ? w : 0) * S + stage) * bnd_chunk_bytes;
+        const int nstage = (stage + 1 == S) ? 0 : stage + 1;
+        const uint32_t nwrap = (stage + 1 == S) ? wrap + 1 : wrap;
+        early = false;
         if (cnt == kChunk) {                                  // full chunk: straight-line code, no per-step branch
 #pragma unroll
             for (int i = 0; i < kChunk; ++i) {
                 const int row = REV ? (kChunk - 1 - i) : i;
-                lattice_step<K, GRAM, REV>(st, lane, has_prev, has_next, bin + i * PAD * 8u, bout + i * PAD * 8u,
+                if (i == kChunk - 1 && ch + 1 < nchunks) early = mbar_try_wait(&wait_bar[nstage], nwrap & 1u);
+                lattice_step<K, GRAM, REV>(st, lane, has_next, bin + i * PAD * 8u, bout + i * PAD * 8u,
                                            lp_s + (uint32_t)row * row_bytes, out_ptr + i * frame_step);
             }
         } else {                                              // last, partial chunk
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 const int row = REV ? (cnt - 1 - i) : i;
-                lattice_step<K, GRAM, REV>(st, lane, has_prev, has_next, bin + i * PAD * 8u, bout + i * PAD * 8u,
+                lattice_step<K, GRAM, REV>(st, lane, has_next, bin + i * PAD * 8u, bout + i * PAD * 8u,
                                            lp_s + (uint32_t)row * row_bytes, out_ptr + i * frame_step);
             }
         }
         out_ptr += kChunk * frame_step;
-        if (prof) { tq4 = clock64(); acc_work += tq4 - tq3; }
+        // pull the mantissas back into [1,2): they moved by at most 2^-kChunk .. 3^kChunk since the last time
+#pragma unroll
+        for (int r = 0; r < K; ++r) renorm_pair(st.m[r], st.e[r]);
+        if (prof) { tq2 = clock64(); acc_work += tq2 - tq1; }
         __syncwarp();
-        if (lane == 0) {
-            if (has_next) mbar_arrive(&pp.ready[w * S + stage]);
-            mbar_arrive(&pp.consumed[stage]);
-        }
-        if (++stage == S) { stage = 0; ++wrap; }
-        if (prof) acc_tail += clock64() - tq4;
+        if (lane == 0) mbar_arrive(&done_bar[stage]);
+        stage = nstage; wrap = nwrap;
+        if (prof) acc_tail += clock64() - tq2;
     }
     if (prof) {
-        long long *o = g_lat_dbg + ((size_t)blockIdx.x * 32 + (REV ? 16 : 0) + w) * 8;
-        o[0] = acc_ready; o[1] = acc_issue; o[2] = acc_full; o[3] = acc_work; o[4] = acc_tail; o[5] = nchunks;
+        long long *o = g_lat_dbg + ((size_t)blockIdx.x * 32 + w) * 8;
+        o[0] = acc_wait; o[1] = 0; o[2] = 0; o[3] = acc_work; o[4] = acc_tail; o[5] = nchunks;
         o[6] = gtime();
     }
 }
@@ -341,8 +354,6 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const ProblemD
     const int32_t *lab = d.labels + (size_t)b * d.Lmax;
     const int32_t *big = GRAM ? d.bigrams + (size_t)b * d.Lmax : nullptr;
     const bool shifted = rev && !GRAM && K == 2;         // see Shifted<>
-    st.flag = 0u;
-    st.dead = 0u;
     st.valid = 0u;
 #pragma unroll
     for (int r = 0; r < K; ++r) {
@@ -350,47 +361,41 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const ProblemD
         const int j = rev ? (shifted ? Nb - q : Nb - 1 - q) : q;       // forward node index
         const bool ok = shifted ? (q >= 1 && q <= Nb) : (q < Nb);
         const int q_start = shifted ? 1 : 0;
-        st.h[r] = (q == q_start) ? 0.f : SENT;           // virtual state: all mass on the first node (gram_ctc.py:144)
-        st.l[r] = 0.f;
+        st.m[r] = (q == q_start) ? 1.f : 0.f;            // virtual state: all mass on the first node (gram_ctc.py:144)
+        st.e[r] = (q == q_start) ? 0.f : SENT;
         if (ok) st.valid |= (1u << r);
-        if (shifted && q == 0) st.dead |= 1u;
         int ci = 0;
+        bool open = false;
         if (ok) {
             if constexpr (!GRAM) {
                 if (j & 1) {
                     const int i = j >> 1;
                     ci = 1 + i;
-                    bool open;
                     if (!rev) open = (i >= 1) && (lab[i] != lab[i - 1]);
                     else open = (i + 1 < Lb) && (lab[i + 1] != lab[i]);
-                    if (open) st.flag |= (1u << r);
                 }
             } else {
                 const int i = j / 3, type = j % 3;
                 if (type == 1) {
                     ci = 1 + i;
-                    bool open;
                     if (!rev) open = (i >= 1) && (lab[i] != lab[i - 1]);
                     else open = (i + 1 < Lb) && (lab[i + 1] != lab[i]);
-                    if (open) st.flag |= (1u << r);
                 } else if (type == 2) {
-                    ci = 1 + d.Lmax + i;
-                    bool open;
+                    ci = 1 + d.Lmax + i;                 // a dead bigram (id -1) has emission probability 0 there
                     if (!rev) open = (i >= 2) && (big[i] != big[i - 2]);
                     else open = (i + 2 < Lb) && (big[i + 2] != big[i]);
-                    if (open) st.flag |= (1u << r);
-                    if (big[i] == -1) st.dead |= (1u << r);
                 }
             }
         }
         st.ci[r] = ci;
+        st.openoff[r] = open ? 0.f : SENT;
     }
 }
 
 struct SmemPlan {
-    size_t lp_elems, bnd_elems;      // float2 elements per direction
+    size_t lp_elems, bnd_elems, none_elems;      // float2 elements
     size_t off_bars, off_red, total;
-    int nbars_dir;
+    int nbars;
 };
 
 __host__ __device__ inline SmemPlan plan_smem(int Wlp, int W, int S, int PAD) {
@@ -398,54 +403,44 @@ __host__ __device__ inline SmemPlan plan_smem(int Wlp, int W, int S, int PAD) {
     p.lp_elems = (size_t)S * kChunk * Wlp;
     p.bnd_elems = (size_t)(W > 1 ? W - 1 : 1) * S * kChunk * PAD;
     p.bnd_elems = (p.bnd_elems + 1) & ~(size_t)1;                      // keep 16-byte alignment of what follows
-    p.nbars_dir = 2 * S + S * (W > 1 ? W - 1 : 0);
-    size_t o = 2 * (p.lp_elems + p.bnd_elems) * sizeof(float2);
+    p.none_elems = ((size_t)kChunk * PAD + 1) & ~(size_t)1;
+    p.nbars = 2 * S + S * (W > 1 ? W - 1 : 0);
+    size_t o = (p.lp_elems + p.bnd_elems + p.none_elems) * sizeof(float2);
     p.off_bars = align_up(o, 16);
-    o = p.off_bars + 2 * (size_t)p.nbars_dir * sizeof(uint64_t);
+    o = p.off_bars + (size_t)p.nbars * sizeof(uint64_t);
     p.off_red = o;
-    o += (2 * kMaxWarpsPerDir + 4) * sizeof(float);
+    o += 4 * sizeof(float);
     p.total = o;
     return p;
 }
 
-__device__ __forceinline__ void init_barriers(uint64_t *bars, int nbars_dir, int S, int W) {
-    // per direction: full[S] (1 arrival + tx), consumed[S] (W arrivals), ready[(W-1)*S] (1 arrival)
-    for (int dir = 0; dir < 2; ++dir) {
-        uint64_t *b = bars + dir * nbars_dir;
-        for (int i = 0; i < nbars_dir; ++i) {
-            const bool is_consumed = (i >= S && i < 2 * S);
-            mbar_init(&b[i], is_consumed ? (uint32_t)W : 1u);
-        }
-    }
-    mbar_init_fence();
-}
-
-// MAXW bounds the warps per direction of an instantiation, so that small lattices (the common case) are not
-// compiled under the 64-register cap a 1024-thread CTA implies.
+// MAXW bounds the compute warps of an instantiation, so that small lattices (the common case) are not
+// compiled under the register cap a large CTA implies.
 template <int K, bool GRAM, int MAXW>
-__global__ void __launch_bounds__(64 * (MAXW + 1), 1) lattice_kernel(LatticeParams p) {
+__global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PAD = Geo<K, GRAM>::PAD;
     const ProblemDesc &d = p.d;
-    if ((int)blockIdx.x >= d.B) {                          // ---- symbol-table CTAs (prep.cuh) ----
-        prep_utterance(d, p.w, p.ws, (int)blockIdx.x - d.B, reinterpret_cast<int *>(smem_raw));
+    if ((int)blockIdx.x >= 2 * d.B) {                      // ---- symbol-table CTAs (prep.cuh) ----
+        prep_utterance(d, p.w, p.ws, (int)blockIdx.x - 2 * d.B, reinterpret_cast<int *>(smem_raw));
         return;
     }
-    const int b = blockIdx.x;
+    const int b = blockIdx.x >> 1;
+    const int dir = blockIdx.x & 1;                        // 0: alpha, 1: beta
     const int W = p.W, S = p.S;
-    const int warp = threadIdx.x >> 5;
+    // warps [0,W): recursion, warp W: I/O.  Read through a shuffle so that the compiler knows the value is
+    // warp-uniform: every branch below is then a uniform branch, and the recursion's shuffles need no divergence
+    // check (a BRA.DIV per shuffle otherwise, each one a scheduling barrier inside the unrolled chunk).
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    // warps [0,W): alpha, [W,2W): beta, 2W: alpha's I/O warp, 2W+1: beta's I/O warp
-    const bool io = warp >= 2 * W;
-    const int dir = io ? (warp - 2 * W) : (warp >= W ? 1 : 0);
-    const int w = io ? 0 : warp - dir * W;
+    const bool io = (w == W);
     UttInfo *ui = reinterpret_cast<UttInfo *>(p.ws + p.w.off_utt) + b;
     WsHeader *hdr = reinterpret_cast<WsHeader *>(p.ws + p.w.off_hdr);
 
     int Tb = d.input_lengths ? d.input_lengths[b] : d.T;
     int Lb = d.label_lengths ? d.label_lengths[b] : d.Lmax;
-    Tb = max(0, min(Tb, d.T));
-    Lb = max(0, min(Lb, d.Lmax));
+    Tb = __shfl_sync(0xffffffffu, max(0, min(Tb, d.T)), 0);
+    Lb = __shfl_sync(0xffffffffu, max(0, min(Lb, d.Lmax)), 0);
     const int Nb = (GRAM ? 3 : 2) * Lb + 1;
 
     const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);
@@ -453,13 +448,19 @@ __global__ void __launch_bounds__(64 * (MAXW + 1), 1) lattice_kernel(LatticePara
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + sp.off_bars);
     float *red = reinterpret_cast<float *>(smem_raw + sp.off_red);
     DirPipe pp;
-    pp.lp = smem_u32(f2base + (size_t)dir * (sp.lp_elems + sp.bnd_elems));
+    pp.lp = smem_u32(f2base);
     pp.bnd = pp.lp + (uint32_t)(sp.lp_elems * sizeof(float2));
-    pp.full = bars + dir * sp.nbars_dir;
+    pp.bnd_none = pp.bnd + (uint32_t)(sp.bnd_elems * sizeof(float2));
+    pp.full = bars;
     pp.consumed = pp.full + S;
     pp.ready = pp.consumed + S;
 
-    if (threadIdx.x == 0) init_barriers(bars, sp.nbars_dir, S, W);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < sp.nbars; ++i) mbar_init(&bars[i], 1u);      // every barrier has exactly one arriver
+        mbar_init_fence();
+    }
+    for (int i = threadIdx.x; i < kChunk * PAD; i += blockDim.x)
+        f2base[sp.lp_elems + sp.bnd_elems + i] = make_float2(0.f, SENT);
     __syncthreads();
 
     float2 *av = reinterpret_cast<float2 *>(p.ws + p.w.off_av) + (size_t)b * d.T * p.w.Np;
@@ -479,39 +480,40 @@ __global__ void __launch_bounds__(64 * (MAXW + 1), 1) lattice_kernel(LatticePara
             else          run_direction<K, GRAM, true>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
         }
     }
+    if (dir == 1) return;                                  // the beta CTA is done
     __threadfence_block();
     __syncthreads();
 
-    // ---- log P = LSE of alpha over the final nodes at the last frame (gram_ctc.py:279; SURVEY 8a "end") ----
+    // ---- P = sum of alpha over the final nodes at the last frame (gram_ctc.py:279; SURVEY 8a "end") ----
     if (threadIdx.x == 0) {
         float loss;
         bool feas;
-        float Ph = -SENT, Pl = 0.f;                       // +1e30: every gamma becomes log 0
+        float Ph = -SENT, Pl = 0.f;                       // exponent +1e30: every posterior becomes 0
         if (Tb <= 0) {                                   // no frames: P = 1 iff there is nothing to emit
             feas = (Lb == 0);
-            if (feas) Ph = 0.f;
+            if (feas) { Ph = 0.f; Pl = 1.f; }
             loss = feas ? 0.f : 1e10f;
         } else {
             const float2 *last = av + (size_t)(Tb - 1) * p.w.Np;
             const int nfin = GRAM ? 3 : 2;
-            float fh[3], fl[3];
-            float pm = SENT;
-            for (int i = 0; i < 3; ++i) { fh[i] = SENT; fl[i] = 0.f; }
+            float fm[3], fe[3];
+            float pe = SENT;
+            for (int i = 0; i < 3; ++i) { fm[i] = 0.f; fe[i] = SENT; }
             for (int i = 0; i < nfin; ++i) {
                 const int j = Nb - 1 - i;
-                if (j >= 0) { const float2 v = __ldcg(last + j); fh[i] = v.x; fl[i] = v.y; }
-                pm = fmaxf(pm, fh[i]);
+                if (j >= 0) { const float2 v = last[j]; fm[i] = v.x; fe[i] = v.y; }
+                pe = fmaxf(pe, fe[i]);
             }
             double sum = 0.0;
             for (int i = 0; i < nfin; ++i)
-                if (fh[i] > SENT_TEST) sum += exp2((double)(fh[i] - pm) + (double)fl[i]);
-            feas = (pm > SENT_TEST) && (sum > 0.0);
+                if (fe[i] > SENT_TEST || fm[i] != fm[i]) sum += (double)fm[i] * exp2((double)(fe[i] - pe));
+            feas = !(sum <= 0.0) && (pe > SENT_TEST || sum != sum);      // a NaN stays a NaN loss (train.py NaN guard)
             if (feas) {
-                const double lg = log2(sum);
-                const double total = (double)pm + lg;    // log2 P
-                const double rr = rint(total);
-                Ph = (float)rr;
-                Pl = (float)(total - rr);
+                const double total = (double)pe + log2(sum);             // log2 P
+                int ex = 0;
+                const double mant = 2.0 * frexp(sum, &ex);               // sum = mant * 2^(ex-1), mant in [1,2)
+                Ph = pe + (float)(ex - 1);
+                Pl = (float)(1.0 / mant);                                // P = 2^Ph / Pl
                 loss = (float)(-total * LN2_D);
             } else {
                 loss = 1e10f;                            // what the reference returns
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(64 * (MAXW + 1), 1) lattice_kernel(LatticePara
         red[0] = (done == (unsigned)d.B) ? 1.f : 0.f;
     }
     __syncthreads();
-    if (red[0] != 0.f && warp == 0) {
+    if (red[0] != 0.f && w == 0) {
         __threadfence();
         double acc = 0.0;
         for (int i = lane; i < d.B; i += 32) acc += (double)__ldcg(p.loss_per_utt + i);
@@ -540,14 +542,14 @@ cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
     auto kern = lattice_kernel<K, GRAM, MAXW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<2 * p.d.B, 64 * (p.W + 1), smem, stream>>>(p);
+    kern<<<3 * p.d.B, 32 * (p.W + 1), smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int K, bool GRAM>
 cudaError_t launch_one(const LatticeParams &p, size_t smem, cudaStream_t stream) {
-    if (p.W <= 4) return launch_w<K, GRAM, 4>(p, smem, stream);
-    if (p.W <= 8) return launch_w<K, GRAM, 8>(p, smem, stream);
+    if (p.W <= 3) return launch_w<K, GRAM, 3>(p, smem, stream);
+    if (p.W <= 7) return launch_w<K, GRAM, 7>(p, smem, stream);
     return launch_w<K, GRAM, kMaxWarpsPerDir>(p, smem, stream);
 }
 
@@ -564,14 +566,14 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
     const int kind = p.d.kind;
     const int Nmax = p.w.Nmax;
     // nodes per lane: as few as possible (the recursion is issue-bound per warp), more only when the
-    // lattice would not fit 16 warps per direction
+    // lattice would not fit 16 warps
     int K;
     if (kind == 0) K = (Nmax <= 32 * 2 * kMaxWarpsPerDir) ? 2 : 4;
     else K = (Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6;
     const int W = (Nmax + (kind == 0 && K == 2 ? 1 : 0) + 32 * K - 1) / (32 * K);   // +1: phantom node (Shifted<>)
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
-    int S = kMaxStages;
+    int S = W + 3 < kMaxStages ? W + 3 : kMaxStages;
     if (const char *e = getenv("B200CTC_LAT_STAGES")) S = atoi(e);               // experiment knob
     while (S > 2 && plan_smem(p.w.W, W, S, PAD).total > kLatticeSmemBudget) --S;
     const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);

@@ -4,7 +4,7 @@
 //   _softmax :18-21 and _log_matrix :48-57 over the whole (T,B,V) tensor (two extra 717 MB arrays at
 //   B=64,T=800,V=3500) and the per-frame `xp.take(y, index)` of loop 1/2 (:155,:175).
 // Kernel 1 reads each activation row exactly once and writes, per frame, ONE float (the log2
-// normaliser) plus the gathered log2-probabilities of the <= 1+2*Lmax symbols the lattice can emit.
+// normaliser) plus the gathered probabilities, as (mantissa, exponent) pairs, of the <= 1+2*Lmax symbols the lattice can emit.
 // No (T,B,V) log-probability tensor is ever materialised.
 //
 // One warp per frame, 128-bit loads, online (max, sum) per lane, warp-shuffle reduction.
@@ -137,9 +137,10 @@ __device__ __forceinline__ void scan_row(const float *__restrict__ row, int V, i
     }
 }
 
-// log2 p = x*log2(e) - lse2 as a split value (integer hi, small lo); exact to ~1e-7 between symbols.
-// lse2 itself comes as an unevaluated sum (la + lb) so that its own rounding does not enter.
-__device__ __forceinline__ float2 split_log2p(float x, float la, float lb) {
+// Emission probability p = 2^(x*log2(e) - lse2) in the lattice's (mantissa, integer exponent) format
+// (common.cuh).  log2 p is first formed as integer hi + small lo, exact to ~1e-7 between symbols (lse2 comes as
+// an unevaluated sum la + lb so that its own rounding does not enter); the mantissa is then 2^lo in [0.70, 1.42].
+__device__ __forceinline__ float2 emission_pair(float x, float la, float lb) {
     const float ph = x * LOG2E_HI;
     float pl = fmaf(x, LOG2E_HI, -ph);
     pl = fmaf(x, LOG2E_LO, pl);
@@ -149,8 +150,8 @@ __device__ __forceinline__ float2 split_log2p(float x, float la, float lb) {
     const float lo_full = (err + pl) - lb;
     const float hi = rintf(dd);
     const float lo = (dd - hi) + lo_full;
-    if (dd < SENT_TEST) return make_float2(SENT, 0.f);        // -inf activation: log 0 (a NaN still propagates)
-    return make_float2(hi, lo);
+    if (dd < SENT_TEST) return make_float2(0.f, SENT);        // -inf activation: probability 0 (a NaN still propagates)
+    return make_float2(exp2f(lo), hi);
 }
 
 // log2 normaliser of a row, max*log2(e) + log2(sum), as an unevaluated float pair
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
             if (c == 0) sym = d.blank;
             else if (c <= d.Lmax) sym = (c - 1 < Lb) ? lab[c - 1] : -1;
             else sym = big[c - 1 - d.Lmax];
-            float2 v = make_float2(SENT, 0.f);
-            if (sym >= 0 && sym < d.V) v = split_log2p(__ldg(row + sym), la, lb);
+            float2 v = make_float2(0.f, SENT);
+            if (sym >= 0 && sym < d.V) v = emission_pair(__ldg(row + sym), la, lb);
             lprow[c] = v;
         }
     }
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
                 if (cidx == 0) sym = d.blank;
                 else if (cidx <= d.Lmax) sym = (cidx - 1 < Lb) ? __ldg(lab + cidx - 1) : -1;
                 else sym = __ldg(big + cidx - 1 - d.Lmax);
-                float2 v = make_float2(SENT, 0.f);
-                if (sym >= 0 && sym < d.V) v = split_log2p(row[sym], la, lb);
+                float2 v = make_float2(0.f, SENT);
+                if (sym >= 0 && sym < d.V) v = emission_pair(row[sym], la, lb);
                 lprow[cidx] = v;
             }
             if (GRAD) {

@@ -1,8 +1,8 @@
 """Profiling aid: per-warp cycle breakdown of the lattice kernel (needs the debug hook in lattice.cu).
 
-For every lattice CTA and warp: cycles per chunk (8 frames) spent waiting for the previous warp's boundary
-values (ready), issuing the emission-row bulk copy (issue), waiting for it (full), in the 8 recursion steps
-(work) and in the hand-over (tail)."""
+For every lattice CTA (one per utterance and direction) and warp: cycles per chunk (16 frames) spent waiting for
+the previous warp's boundary values / the emission rows (wait), in the recursion steps (work) and in the
+hand-over."""
 import ctypes, importlib, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -33,12 +33,13 @@ e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=T
 lib.b200ctc_debug_lattice(None)
 e0.record(); [run() for _ in range(10)]; e1.record(); torch.cuda.synchronize()
 print("forward (K1+K2) %.1f us" % (e0.elapsed_time(e1) * 100))
-a = dbg.cpu().numpy().reshape(64, 32, 8)
+a = dbg.cpu().numpy().reshape(64, 32, 8)       # [lattice CTA = 2*b + direction][warp][counter]
 t_end = a[:, :, 6]; t0 = t_end[t_end > 0].min()
-for i in (0, 5, min(B - 1, 63)):
-    for nm, wi in [("a%d" % k, k) for k in range(4)] + [("b%d" % k, 16 + k) for k in range(4)]:
-        r = a[i, wi]
-        if r[5] == 0: continue
-        print("CTA %2d T %d %s per-chunk cycles: ready %.0f issue %.0f full %.0f work %.0f tail %.0f (chunks %d)" % (
-            (i, prob["input_length"][i], nm) + tuple(r[:5] / r[5]) + (r[5],)))
-print("spread of warp end times over all CTAs: %.1f us" % ((t_end.max() - t0) / 1e3))
+for b in (0, 5, min(B - 1, 31)):
+    for d, nm in ((0, "alpha"), (1, "beta")):
+        for wi in range(8):
+            r = a[2 * b + d, wi]
+            if r[5] == 0: continue
+            print("utt %2d T %d %s warp %d per-chunk cycles: wait %.0f work %.0f hand-over %.0f (chunks %d)" % (
+                b, prob["input_length"][b], nm, wi, r[0] / r[5], r[3] / r[5], r[4] / r[5], r[5]))
+print("spread of warp end times over the first 32 utterances: %.1f us" % ((t_end.max() - t0) / 1e3))
