@@ -14,9 +14,36 @@ using namespace b200ctc;
 
 namespace {
 
-// zeroes the workspace header (ticket counters) in stream order
-__global__ void zero_header_kernel(WsHeader *h) {
-    if (threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
+// zeroes the workspace header (ticket counters) and the frame-progress counters in stream order
+__global__ void zero_header_kernel(WsHeader *h, unsigned *prog, int nprog) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) prog[i] = 0u;
+}
+
+// Side stream on which the lattice kernel runs next to the softmax/gather kernel (fork/join by events, so the
+// caller still sees one stream; capturable into a CUDA graph).  One per host thread and device, created on first
+// use and kept: the only state the library holds besides the last-error string.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+constexpr int kMaxDevices = 64;
+thread_local SideStream g_side[kMaxDevices];
+
+SideStream *side_stream() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    SideStream &s = g_side[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { s.stream = nullptr; return nullptr; }
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(s.stream);
+            s = SideStream();
+            return nullptr;
+        }
+    }
+    return &s;
 }
 
 // gradient *= gy / applied, in place, skipped entirely when the ratio is 1 (the usual loss.backward()):
@@ -38,9 +65,10 @@ __global__ void rescale_commit_kernel(const float *gy, int per_utterance, int B,
     const int n = per_utterance ? B : 1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) applied[i] = gy[i];
 }
-__global__ void fused_init_kernel(WsHeader *h, float *applied, int n) {
+__global__ void fused_init_kernel(WsHeader *h, float *applied, int n, unsigned *prog, int nprog) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) applied[i] = 1.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) prog[i] = 0u;
 }
 
 thread_local char g_err[512] = "";
@@ -116,18 +144,49 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
     d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
     d.labels = labels; d.bigrams = kind == B200CTC_KIND_GRAM ? bigrams : nullptr;
     d.input_lengths = input_lengths; d.label_lengths = label_lengths;
+    d.progress = 0;
 
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    zero_header_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<WsHeader *>(ws + w.off_hdr));
+    const int nprog = B * w.nblk;
+    zero_header_kernel<<<(nprog + 255) / 256 > 0 ? (nprog + 255) / 256 : 1, 256, 0, stream>>>(
+        reinterpret_cast<WsHeader *>(ws + w.off_hdr), reinterpret_cast<unsigned *>(ws + w.off_prog), nprog);
     if ((rc = check_cuda(cudaGetLastError(), "workspace header reset"))) return rc;
-    if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, stream), "softmax/gather kernel"))) return rc;
 
     LatticeParams lp;
     lp.d = d; lp.w = w; lp.ws = ws;
     lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
     lp.W = 0; lp.S = 0;
     int st = 0;
-    if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
+
+    // The lattice kernel runs NEXT TO the softmax/gather kernel, on a side stream: the recursion is a latency-bound
+    // dependent chain that needs a few warps per utterance, the softmax a bandwidth-bound stream over all SMs, and
+    // the first feeds the second frame by frame through the progress counters (common.cuh).  Tickets walk the
+    // frames from both ends, so alpha and beta both find their next rows ready; what remains exposed is the second
+    // half of each direction after the last row has been produced.
+    // No deadlock: the softmax kernel never waits on the lattice kernel, and with B < #SMs the spinning lattice
+    // CTAs (2 per utterance) cannot occupy every SM's shared memory (an SM is closed to a ring CTA only when it
+    // holds two of them), so ring CTAs always find room.  Larger batches run the two kernels back to back.
+    SideStream *side = nullptr;
+    size_t lat_smem = 0;
+    if (B < sm_count() && T > 0 && !getenv("B200CTC_NO_CONCURRENT")) {
+        if ((rc = check_cuda(launch_lattice(lp, stream, &st, true, &lat_smem, false), "lattice kernel"))) return rc;
+        if (!st) side = side_stream();
+        st = 0;
+    }
+    if (side) {
+        d.progress = 3;
+        if (const char *e = getenv("B200CTC_DBG_PROGRESS")) d.progress = atoi(e);      // experiment knob
+        lp.d = d;
+        if ((rc = check_cuda(cudaEventRecord(side->fork, stream), "fork event"))) return rc;
+        if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, lat_smem, stream), "softmax/gather kernel"))) return rc;
+        if ((rc = check_cuda(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait"))) return rc;
+        if ((rc = check_cuda(launch_lattice(lp, side->stream, &st, true), "lattice kernel"))) return rc;
+        if ((rc = check_cuda(cudaEventRecord(side->join, side->stream), "join event"))) return rc;
+        if ((rc = check_cuda(cudaStreamWaitEvent(stream, side->join, 0), "join wait"))) return rc;
+    } else {
+        if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, 0, stream), "softmax/gather kernel"))) return rc;
+        if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
+    }
     if (st) return fail(B200CTC_UNSUPPORTED, "lattice of %s%lld nodes does not fit the kernel's shared-memory pipeline", "", w.Nmax);
     return B200CTC_OK;
 }
@@ -146,6 +205,7 @@ int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stri
     g.d.kind = kind; g.d.B = B; g.d.T = T; g.d.V = V; g.d.Lmax = Lmax; g.d.blank = blank;
     g.d.acts = acts; g.d.stride_t = stride_t; g.d.stride_b = stride_b;
     g.d.labels = labels; g.d.bigrams = bigrams; g.d.input_lengths = nullptr; g.d.label_lengths = nullptr;
+    g.d.progress = 0;
     g.grad_loss = grad_loss; g.per_utterance = per_utterance; g.scale = scale;
     g.grad_out = grad_out; g.gstride_t = gstride_t; g.gstride_b = gstride_b;
     return check_cuda(launch_gradient(g, w, workspace, static_cast<cudaStream_t>(stream_)), "gradient kernel");
@@ -189,14 +249,16 @@ int b200ctc_forward_backward(int kind, const float *acts, int64_t stride_t, int6
     d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
     d.labels = labels; d.bigrams = kind == B200CTC_KIND_GRAM ? bigrams : nullptr;
     d.input_lengths = input_lengths; d.label_lengths = label_lengths;
+    d.progress = 0;
 
-    fused_init_kernel<<<(B + 255) / 256, 256, 0, stream>>>(reinterpret_cast<WsHeader *>(ws + w.off_hdr), applied, B);
+    fused_init_kernel<<<(B * w.nblk + 255) / 256, 256, 0, stream>>>(reinterpret_cast<WsHeader *>(ws + w.off_hdr), applied, B,
+                                                                   reinterpret_cast<unsigned *>(ws + w.off_prog), B * w.nblk);
     if ((rc = check_cuda(cudaGetLastError(), "workspace header reset"))) return rc;
     // one-read path: the softmax/gather kernel also writes softmax * scale as the gradient row while the
     // activation row is in shared memory; after the lattice only the label columns are patched
     cudaError_t e = launch_softmax_gather_grad(d, w, ws, grad_out, gstride_t, gstride_b, grad_scale, stream);
     const bool one_read = (e == cudaSuccess);
-    if (e == cudaErrorNotSupported) e = launch_softmax_gather(d, w, ws, nullptr, stream);   // unaligned / huge rows
+    if (e == cudaErrorNotSupported) e = launch_softmax_gather(d, w, ws, nullptr, 0, stream);   // unaligned / huge rows
     if ((rc = check_cuda(e, "softmax/gather kernel"))) return rc;
     LatticeParams lp;
     lp.d = d; lp.w = w; lp.ws = ws;

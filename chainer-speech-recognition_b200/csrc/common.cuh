@@ -18,6 +18,7 @@ constexpr float SENT_TEST = -1.0e29f;         // anything below this is treated 
 constexpr float LOG2E_HI = 1.44269502162933349609375f;      // float(log2 e)
 constexpr float LOG2E_LO = 1.92596299112661746e-8f;         // log2 e - LOG2E_HI
 constexpr double LN2_D = 0.693147180559945309417232121458;
+constexpr int kProgBlock = 16;                // frames per progress counter = frames per lattice pipeline chunk
 constexpr float RINT_MAGIC = 12582912.0f;     // 1.5 * 2^23: (x + M) - M == rint(x) for |x| < 2^22
 
 // Per-utterance record written by the prep kernel and completed by the lattice kernel.
@@ -47,9 +48,13 @@ struct WsLayout {
     int kind, B, T, V, Lmax;
     int W;         // emission row width: [blank, label_0..label_{Lmax-1} (, bigram_0..)] padded to even
     int Nmax;      // lattice nodes for Lmax
-    int Np;        // Nmax padded to a multiple of 4
+    int Np;        // Nmax (+ boff) padded to a multiple of 4
+    int boff;      // beta_t[j] is stored at bv[t][j + boff]: 1 for CTC (aligns the reversed direction's node pairs), else 0
     int Umax;      // upper bound on distinct symbols per utterance (blank + every non-blank-type node)
     int nwords;    // ceil(V / 32): words of the per-utterance "is a lattice symbol" bitmap
+    int nblk;      // ceil(T / kProgBlock): progress counters per utterance
+    size_t off_prog;   // [B][nblk] unsigned: emission rows of frames [16k, 16k+16) written so far (softmax/gather
+                       // kernel -> lattice kernel, which may run concurrently with it)
     size_t off_hdr, off_utt, off_lse, off_lp, off_av, off_bv, off_usym, off_uoff, off_unode, off_bm, off_pc, total;
 };
 
@@ -61,9 +66,11 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     int width = 1 + (kind == 0 ? Lmax : 2 * Lmax);
     w.W = (width + 1) & ~1;
     w.Nmax = (kind == 0 ? 2 : 3) * Lmax + 1;
-    w.Np = (w.Nmax + 3) & ~3;
+    w.boff = kind == 0 ? 1 : 0;
+    w.Np = (w.Nmax + w.boff + 3) & ~3;
     w.Umax = w.Nmax - Lmax;                 // blank + (per-1)*Lmax entries
     w.nwords = (V + 31) / 32;
+    w.nblk = (T + kProgBlock - 1) / kProgBlock;
     size_t o = 0;
     const size_t BT = (size_t)B * (size_t)T;
     w.off_hdr = o;   o = align_up(o + sizeof(WsHeader), 256);
@@ -71,12 +78,13 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     w.off_lse = o;   o = align_up(o + sizeof(float) * BT, 256);
     w.off_lp = o;    o = align_up(o + sizeof(float2) * BT * w.W, 256);
     w.off_av = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // alpha_t[j] as (m, e)
-    w.off_bv = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // beta_t[j] (excludes emission at t)
+    w.off_bv = o;    o = align_up(o + sizeof(float2) * BT * w.Np, 256);      // beta_t[j] (excludes emission at t), at [j + boff]
     w.off_usym = o;  o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
     w.off_uoff = o;  o = align_up(o + sizeof(int) * (size_t)B * (w.Nmax + 1), 256);
     w.off_unode = o; o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
     w.off_bm = o;    o = align_up(o + sizeof(unsigned) * (size_t)B * w.nwords, 256);
     w.off_pc = o;    o = align_up(o + sizeof(int) * (size_t)B * w.nwords, 256);
+    w.off_prog = o;  o = align_up(o + sizeof(unsigned) * (size_t)B * w.nblk, 256);
     w.total = o;
     return w;
 }
@@ -122,6 +130,33 @@ __device__ __forceinline__ float node_posterior(float2 a, float2 b, float Ph, fl
     return (a.x * b.x) * ex2_approx((a.y + b.y) - Ph) * Pinv;
 }
 
+// ---- frame progress between the softmax/gather kernel and a concurrently running lattice kernel ----
+// Producer: called by ONE lane after a __syncwarp() that follows the warp's stores of the frame's emission row.
+__device__ __forceinline__ void signal_frame_done(unsigned char *ws, const WsLayout &w, int b, int t, bool relaxed = false) {
+    unsigned *p = reinterpret_cast<unsigned *>(ws + w.off_prog) + (size_t)b * w.nblk + t / kProgBlock;
+    if (relaxed) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+    else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+// Consumer (whole warp): how many of the blocks blk0, blk0 + step, blk0 + 2*step, ... (up to 32, inside [0, nblk))
+// are complete, counted from the front.  Block k of an utterance with Tb frames is complete when its counter has
+// reached min(kProgBlock, Tb - k*kProgBlock).  One L2 round trip for up to 32 blocks.
+__device__ __forceinline__ int count_blocks_done(const unsigned char *ws, const WsLayout &w, int b, int Tb, int blk0,
+                                                 int step, int lane) {
+    const int nb = (Tb + kProgBlock - 1) / kProgBlock;
+    const int blk = blk0 + step * lane;
+    bool ok = false;
+    if (blk >= 0 && blk < nb) {
+        const unsigned *p = reinterpret_cast<const unsigned *>(ws + w.off_prog) + (size_t)b * w.nblk + blk;
+        unsigned v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        ok = v >= (unsigned)min(kProgBlock, Tb - blk * kProgBlock);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    const int n = __ffs(~m) - 1;                      // leading run of complete blocks (32 if all)
+    if (n > 0) __threadfence();                       // acquire: the rows behind the counters are visible from here on
+    return n < 0 ? 32 : n;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -162,9 +197,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// A few immediate retries (the usual case: the partner is a handful of cycles away), then polite polling, so that
+// a warp that waits for long does not take issue slots from the warps it shares the SM with.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    for (int i = 0; i < 8; ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 // same, but backs off between polls: for waits that are expected to block for a while, so that the
 // polling does not compete with the warps it is waiting for

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         const float2 *brow = bv_all + ((size_t)b * d.T + t) * w.Np;
         float blank_part = 0.f;
         for (int j = lane; j < ui.Nb; j += 32) {
-            const float2 a = __ldg(arow + j), bb = __ldg(brow + j);
+            const float2 a = __ldg(arow + j), bb = __ldg(brow + j + w.boff);
             const float e = node_posterior(a, bb, ui.Ph, ui.Pl);
             e_sm[j] = e;
             if (j % per == 0) blank_part += e;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             const int j = j0 + lane;
             float e = 0.f;
             if (j < ui.Nb) {
-                const float2 a = a_sm[j], bb = b_sm[j];
+                const float2 a = a_sm[j], bb = b_sm[j + w.boff];
                 e = node_posterior(a, bb, ui.Ph, ui.Pl);
             }
             __syncwarp();                                                    // e_sm aliases the alpha row: reads first
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(Grad
                 for (int k = 0; k < kPatchNodeIters; ++k) {
                     const int j = lane + 32 * k;
                     L.av[k] = make_float2(0.f, SENT); L.bv[k] = make_float2(0.f, SENT);
-                    if (j < ui.Nb) { L.av[k] = __ldg(arow + j); L.bv[k] = __ldg(brow + j); }
+                    if (j < ui.Nb) { L.av[k] = __ldg(arow + j); L.bv[k] = __ldg(brow + j + w.boff); }
                 }
 #pragma unroll
                 for (int k = 0; k < kPatchSymIters; ++k) L.gold[k] = sym[k] >= 0 ? grow[sym[k]] : 0.f;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(Grad
                 float *grow = gbase + (int64_t)t * gp.gstride_t;
                 float blank_part = 0.f;
                 for (int j = lane; j < ui.Nb; j += 32) {
-                    const float2 a = __ldg(arow + j), bb = __ldg(brow + j);
+                    const float2 a = __ldg(arow + j), bb = __ldg(brow + j + w.boff);
                     const float e = node_posterior(a, bb, ui.Ph, ui.Pl);
                     e_sm[j] = e;
                     if (j % per == 0) blank_part += e;

@@ -11,11 +11,15 @@ struct ProblemDesc {
     const float *acts;
     int64_t stride_t, stride_b;
     const int32_t *labels, *bigrams, *input_lengths, *label_lengths;
+    int progress;   // bit 0: the lattice kernel runs concurrently with the softmax/gather kernel -- the latter signals
+                    //        every finished frame (progress counters) and the former waits on them;
+                    // bit 1: tickets walk the frames from both ends (what the concurrent lattice wants)
 };
 
 // kernel 1: fused log-softmax statistics + label gather (+ optional greedy argmax)
+// smem_reserve: shared memory to leave free per SM for a lattice CTA running next to this kernel (0 = none)
 cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
-                                  cudaStream_t stream);
+                                  size_t smem_reserve, cudaStream_t stream);
 cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, void *ws, float *grad, int64_t gstride_t,
                                        int64_t gstride_b, float scale, cudaStream_t stream);
 cudaError_t launch_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,
@@ -39,9 +43,14 @@ struct LatticeParams {
     float loss_scale;
     int W;                   // warps per direction
     int S;                   // pipeline stages
+    int dbg_nostore;         // timing experiment: skip the alpha/beta row stores
 };
 int lattice_max_nodes(int kind);
-cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status);
+// concurrent: the kernel is going to run next to the softmax/gather kernel (fewer pipeline stages, so that a
+// lattice CTA fits beside a ring CTA); smem_out, if not NULL, receives the dynamic shared memory per CTA.
+// With launch = false nothing is launched (planning call).
+cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bool concurrent = false,
+                           size_t *smem_out = nullptr, bool launch = true);
 
 // kernel 3: fused gradient
 struct GradParams {

@@ -57,19 +57,14 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 
 namespace {
 
-constexpr int kChunk = 16;       // frames per pipeline chunk (and per mantissa renormalisation)
+constexpr int kChunk = kProgBlock;   // frames per pipeline chunk (and per mantissa renormalisation)
 constexpr int kMaxStages = 8;    // W + 3 is deep enough that the I/O warp never waits on the last compute warp
 constexpr int kMaxWarpsPerDir = 16;
 
-// CTC, reversed direction: the lattice is indexed with one phantom node in front (q = 0 <-> j = Nb, never
-// reachable: it starts at zero and has no live predecessor), i.e. q <-> j = Nb - q.  That flips the slot parity
-// (slot 0 = label, slot 1 = blank) and makes each lane's two nodes an ALIGNED pair (j even, j+1) in memory, so
-// the beta rows are written with the same single 16-byte store per lane as the alpha rows.
-template <int K, bool GRAM, bool REV>
-struct Shifted {
-    static constexpr bool value = REV && !GRAM && K == 2;
-};
-
+// Reversed direction: q <-> j = Nb - 1 - q, so the reversed CTC lattice has the same shape as the forward one
+// (even q = blank, odd q = label) and a lane's two nodes are j-1 (label), j (blank) with j even.  The beta rows
+// are STORED one element up (WsLayout::boff = 1 for CTC), which makes that pair a 16-byte aligned one and lets
+// beta use the same single 128-bit store per lane as alpha.
 template <int K, bool GRAM>
 struct Geo {
     static constexpr int PAD = GRAM ? 7 : 2;                 // how far back a node's predecessors reach
@@ -118,7 +113,7 @@ __device__ __forceinline__ uint32_t after_wait(uint32_t addr) {
 struct UttCtx {
     const float2 *lp_g;      // this utterance's emission rows   [T][Wlp]
     float2 *out_g;           // this direction's output rows     [T][Np]
-    int Wlp, Np, Nb, W, S;
+    int Wlp, Np, Nb, W, S, boff;
 };
 
 // ---- one lattice step: new (pre-emission) value of slot R from the extended old arrays ----
@@ -129,8 +124,7 @@ __device__ __forceinline__ void slot_update(const float (&xm)[Geo<K, GRAM>::EXT]
     constexpr int PAD = Geo<K, GRAM>::PAD;
     constexpr int I = PAD + R;
     if constexpr (!GRAM) {
-        constexpr bool SH = Shifted<K, GRAM, REV>::value;
-        if constexpr (((R & 1) == 0) != SH) {                 // blank node: self, q-1
+        if constexpr ((R & 1) == 0) {                         // blank node: self, q-1
             const float E = fmaxf(xe[I], xe[I - 1]);
             pre_m = fmaf(xm[I - 1], pow2_nonpos(xe[I - 1] - E), xm[I] * pow2_nonpos(xe[I] - E));
             pre_e = E;
@@ -211,7 +205,7 @@ struct SlotLoop {
 // Write this lane's K results of one frame.  out points at the lane's first node (REV: walks downwards).
 // Partial 32-byte sectors are poison here: the output lines are never resident in L2 when first written, so a
 // half-written sector costs a DRAM fill.  For the CTC layout (K = 2) every lane therefore writes one aligned
-// 16-byte pair (see Shifted<> for how the reversed direction gets aligned pairs too).
+// 16-byte pair (WsLayout::boff is what aligns the reversed direction's pairs).
 template <int K, bool GRAM, bool REV>
 __device__ __forceinline__ void store_results(const float2 (&outv)[K], float2 *out, uint32_t store_mask, int lane) {
     if constexpr (!GRAM && K == 2) {
@@ -219,8 +213,8 @@ __device__ __forceinline__ void store_results(const float2 (&outv)[K], float2 *o
             // nodes (2gl, 2gl+1): aligned; the odd partner of the last valid node falls into the row padding
             if (store_mask & 1u) *reinterpret_cast<float4 *>(out) = make_float4(outv[0].x, outv[0].y, outv[1].x, outv[1].y);
         } else {
-            // shifted reversed indexing: slot 1 = node j (even), slot 0 = node j+1; out points at node j
-            if (store_mask & 2u) *reinterpret_cast<float4 *>(out) = make_float4(outv[1].x, outv[1].y, outv[0].x, outv[0].y);
+            // slot 0 = node j (blank), slot 1 = node j-1; out points at slot 0's (shifted, odd) storage element
+            if (store_mask & 1u) *reinterpret_cast<float4 *>(out - 1) = make_float4(outv[1].x, outv[1].y, outv[0].x, outv[0].y);
         }
     } else {
 #pragma unroll
@@ -249,25 +243,51 @@ __device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, b
 
 // The I/O warp: stages the emission rows of every chunk, as far ahead as the stage ring allows.
 // Keeping this off the compute warps matters: the recursion is a single dependent chain per warp.
+// The softmax/gather kernel may still be running (api.cu launches the two kernels concurrently): before a chunk's
+// rows are copied, the warp makes sure the 16-frame blocks the chunk touches are complete.  It keeps a watermark of
+// blocks known complete in its direction of travel and, when it has to look, checks 32 blocks with one round trip.
 template <bool REV>
-__device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c, int f0, int n, int lane) {
-    if (n <= 0 || lane != 0) return;
+__device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c, int f0, int n, int lane,
+                                             const unsigned char *ws, const WsLayout &wl, int b, bool poll) {
+    if (n <= 0) return;
     const int S = c.S;
     const int nchunks = (n + kChunk - 1) / kChunk;
     const uint32_t row_bytes = (uint32_t)c.Wlp * 8u;
     const uint32_t stage_bytes = row_bytes * kChunk;
     int stage = 0;
     uint32_t wrap = 0;
+    // blocks [0, known) (forward) / (known, last] (reversed) are complete
+    int known = REV ? (n + kProgBlock - 1) / kProgBlock : 0;
     for (int ch = 0; ch < nchunks; ++ch) {
         const int i0 = ch * kChunk;
         const int cnt = min(kChunk, n - i0);
         const int flo = REV ? (f0 - i0 - cnt + 1) : (f0 + i0);
-        if (wrap > 0) mbar_wait_backoff(&pp.consumed[stage], (wrap - 1) & 1u);
-        mbar_arrive_expect_tx(&pp.full[stage], row_bytes * cnt);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         pp.lp + (uint32_t)stage * stage_bytes),
-                     "l"(c.lp_g + (size_t)flo * c.Wlp), "r"(row_bytes * cnt), "r"(smem_u32(&pp.full[stage]))
-                     : "memory");
+        if (wrap > 0 && lane == 0) mbar_wait_backoff(&pp.consumed[stage], (wrap - 1) & 1u);
+        if (!poll) {
+        } else if (!REV) {
+            const int need = (flo + cnt - 1) / kProgBlock + 1;           // blocks [0, need) must be complete
+            while (known < need) {
+                const int got = count_blocks_done(ws, wl, b, n, known, 1, lane);
+                known += got;
+                if (got == 0) __nanosleep(128);
+            }
+        } else {
+            const int need = flo / kProgBlock;                           // blocks [need, last] must be complete
+            while (known > need) {
+                const int got = count_blocks_done(ws, wl, b, n, known - 1, -1, lane);
+                known -= got;
+                if (got == 0) __nanosleep(128);
+            }
+        }
+        if (lane == 0) {
+            fence_proxy_async();                              // rows written through the generic proxy, read by the copy engine
+            mbar_arrive_expect_tx(&pp.full[stage], row_bytes * cnt);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             pp.lp + (uint32_t)stage * stage_bytes),
+                         "l"(c.lp_g + (size_t)flo * c.Wlp), "r"(row_bytes * cnt), "r"(smem_u32(&pp.full[stage]))
+                         : "memory");
+        }
+        __syncwarp();
         if (++stage == S) { stage = 0; ++wrap; }
     }
 }
@@ -285,7 +305,7 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
     const uint32_t stage_bytes = row_bytes * kChunk;
     const uint32_t bnd_chunk_bytes = kChunk * PAD * 8u;
     const int gl = 32 * w + lane;                             // lane index within the direction
-    const int jbase = REV ? (c.Nb - 1 - K * gl) : (K * gl);
+    const int jbase = REV ? (c.Nb - 1 - K * gl + c.boff) : (K * gl);
     const int64_t frame_step = REV ? -(int64_t)c.Np : (int64_t)c.Np;
     float2 *out_ptr = c.out_g + (size_t)f0 * c.Np + jbase;    // this lane's first node in frame f0
     // what this warp waits for before a chunk: warp 0 the emission rows, the others the warp before them (which
@@ -353,16 +373,14 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const ProblemD
                                           bool rev, int gl) {
     const int32_t *lab = d.labels + (size_t)b * d.Lmax;
     const int32_t *big = GRAM ? d.bigrams + (size_t)b * d.Lmax : nullptr;
-    const bool shifted = rev && !GRAM && K == 2;         // see Shifted<>
     st.valid = 0u;
 #pragma unroll
     for (int r = 0; r < K; ++r) {
         const int q = K * gl + r;
-        const int j = rev ? (shifted ? Nb - q : Nb - 1 - q) : q;       // forward node index
-        const bool ok = shifted ? (q >= 1 && q <= Nb) : (q < Nb);
-        const int q_start = shifted ? 1 : 0;
-        st.m[r] = (q == q_start) ? 1.f : 0.f;            // virtual state: all mass on the first node (gram_ctc.py:144)
-        st.e[r] = (q == q_start) ? 0.f : SENT;
+        const int j = rev ? Nb - 1 - q : q;              // forward node index
+        const bool ok = q < Nb;
+        st.m[r] = (q == 0) ? 1.f : 0.f;                  // virtual state: all mass on the first node (gram_ctc.py:144)
+        st.e[r] = (q == 0) ? 0.f : SENT;
         if (ok) st.valid |= (1u << r);
         int ci = 0;
         bool open = false;
@@ -469,13 +487,14 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         UttCtx c;
         c.lp_g = reinterpret_cast<const float2 *>(p.ws + p.w.off_lp) + (size_t)b * d.T * p.w.W;
         c.out_g = dir == 0 ? av : bv;
-        c.Wlp = p.w.W; c.Np = p.w.Np; c.Nb = Nb; c.W = W; c.S = S;
+        c.Wlp = p.w.W; c.Np = p.w.Np; c.Nb = Nb; c.W = W; c.S = S; c.boff = p.w.boff;
         if (io) {
-            if (dir == 0) io_direction<false>(pp, c, 0, Tb, lane);
-            else          io_direction<true>(pp, c, Tb - 1, Tb, lane);
+            if (dir == 0) io_direction<false>(pp, c, 0, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
+            else          io_direction<true>(pp, c, Tb - 1, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
         } else {
             LaneState<K, GRAM> st;
             init_lane<K, GRAM>(st, d, b, Lb, Nb, dir == 1, 32 * w + lane);
+            if (p.dbg_nostore) st.valid = 0u;            // timing experiment only (B200CTC_LAT_NOSTORE): results are garbage
             if (dir == 0) run_direction<K, GRAM, false>(st, pp, c, 0, Tb, w, lane);         // alpha: frames 0 .. Tb-1
             else          run_direction<K, GRAM, true>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
         }
@@ -542,6 +561,9 @@ cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
     auto kern = lattice_kernel<K, GRAM, MAXW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // the SM's L1/shared split is chosen per kernel: ask for the maximum so that a lattice CTA and a ring CTA of the
+    // softmax/gather kernel (which asks for the same) can share an SM
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<3 * p.d.B, 32 * (p.W + 1), smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -561,7 +583,8 @@ void lattice_set_debug(long long *p) { cudaMemcpyToSymbol(g_lat_dbg, &p, sizeof(
 
 int lattice_max_nodes(int kind) { return kind == 0 ? 32 * 4 * kMaxWarpsPerDir : 32 * 6 * kMaxWarpsPerDir; }
 
-cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
+cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bool concurrent, size_t *smem_out,
+                           bool launch) {
     *status = 0;
     const int kind = p.d.kind;
     const int Nmax = p.w.Nmax;
@@ -570,10 +593,11 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
     int K;
     if (kind == 0) K = (Nmax <= 32 * 2 * kMaxWarpsPerDir) ? 2 : 4;
     else K = (Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6;
-    const int W = (Nmax + (kind == 0 && K == 2 ? 1 : 0) + 32 * K - 1) / (32 * K);   // +1: phantom node (Shifted<>)
+    const int W = (Nmax + 32 * K - 1) / (32 * K);
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
-    int S = W + 3 < kMaxStages ? W + 3 : kMaxStages;
+    // next to the softmax/gather kernel the recursion is fed at that kernel's pace: a shallow ring is enough
+    int S = W + (concurrent ? 2 : 3) < kMaxStages ? W + (concurrent ? 2 : 3) : kMaxStages;
     if (const char *e = getenv("B200CTC_LAT_STAGES")) S = atoi(e);               // experiment knob
     while (S > 2 && plan_smem(p.w.W, W, S, PAD).total > kLatticeSmemBudget) --S;
     const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);
@@ -583,6 +607,9 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status) {
     if (prep > smem) smem = prep;
     if (smem > 227 * 1024) { *status = 2; return cudaSuccess; }
     p.W = W; p.S = S;
+    p.dbg_nostore = getenv("B200CTC_LAT_NOSTORE") ? 1 : 0;
+    if (smem_out) *smem_out = smem;
+    if (!launch) return cudaSuccess;
     if (kind == 0) return K == 2 ? launch_one<2, false>(p, smem, stream) : launch_one<4, false>(p, smem, stream);
     return K == 3 ? launch_one<3, true>(p, smem, stream) : launch_one<6, true>(p, smem, stream);
 }

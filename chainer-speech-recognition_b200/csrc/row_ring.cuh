@@ -44,11 +44,18 @@ inline size_t ring_budget() {
     return kRingSmemBudget;
 }
 
-inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes) {
+// smem_reserve: shared memory to leave free on the SM for a CTA of another kernel that is meant to run next to
+// this one (the lattice kernel next to the softmax/gather kernel); 0 = none.
+inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes, size_t smem_reserve = 0) {
     RingLayout r;
     r.slot_bytes = align_up(slot_payload, 128);
     const size_t fixed = (size_t)kMaxSlots * (sizeof(RowMeta) + 16) + extra_bytes + 256;
-    long long n = ((long long)ring_budget() - (long long)fixed) / (long long)r.slot_bytes;
+    long long budget = (long long)ring_budget();
+    if (smem_reserve) {
+        const long long room = 228 * 1024 - 2 * 1024 - (long long)smem_reserve;       // 1 KB per CTA is the driver's
+        if (room < budget) budget = room;
+    }
+    long long n = (budget - (long long)fixed) / (long long)r.slot_bytes;
     if (n > kMaxSlots) n = kMaxSlots;
     r.slots = (int)(n < 0 ? 0 : n);
     r.batch = r.slots < kTicketBatch ? r.slots : kTicketBatch;

@@ -23,6 +23,17 @@ constexpr int kUnroll = 4;
 // ---------------------------------------------------------------------------------------------
 // kernel 1
 // ---------------------------------------------------------------------------------------------
+// Ticket -> frame.  Tickets walk the utterances' frames from BOTH ends towards the middle (slice 0 = frame 0 of
+// every utterance, slice 1 = frame T-1, slice 2 = frame 1, ...): the lattice kernel may run concurrently with this
+// one, its alpha CTAs consume frames in ascending and its beta CTAs in descending order, so each direction finds
+// the rows it needs next already written (common.cuh, signal_frame_done).  Independent of the memory layout: a
+// row is one contiguous 4*V-byte read either way.
+__device__ __forceinline__ void frame_of_ticket(unsigned f, int B, int T, bool two_ended, int &b, int &t) {
+    const int slice = (int)(f / (unsigned)B);
+    b = (int)(f % (unsigned)B);
+    t = !two_ended ? slice : (slice & 1) ? (T - 1 - (slice >> 1)) : (slice >> 1);
+}
+
 struct RowStat {
     float m;      // running max (raw activation units)
     float s;      // running sum of 2^((x - m) * log2 e)
@@ -169,13 +180,16 @@ __device__ __forceinline__ void split_lse2(float m, float s, float &la, float &l
 
 template <bool ARGMAX>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(ProblemDesc d, WsLayout w,
-                                                                          unsigned char *ws, int64_t *argmax_out,
-                                                                          int b_major) {
+                                                                          unsigned char *ws, int64_t *argmax_out) {
     const int lane = threadIdx.x & 31;
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     float *lse_out = reinterpret_cast<float *>(ws + w.off_lse);
     float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
+    // The "row written" signal of a frame is a release at GPU scope, i.e. it waits for the warp's outstanding stores.
+    // It is therefore sent one frame late, just before the NEXT frame's stores: by then the previous frame's stores
+    // have long been acknowledged and the release costs next to nothing.
+    int pend_b = -1, pend_t = 0;
     for (;;) {
         // work queue: one ticket per frame, handed out in memory order of the activations, so that the
         // (variable-length) valid frames spread evenly over the warps whatever the batch layout is
@@ -184,8 +198,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
         f = __shfl_sync(0xffffffffu, f, 0);
         if (f >= frames) break;
         int b, t;
-        if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
-        else { t = (int)(f / d.B); b = (int)(f % d.B); }
+        frame_of_ticket(f, d.B, d.T, (d.progress & 2) != 0, b, t);
         int Tb = d.input_lengths ? d.input_lengths[b] : d.T;
         Tb = max(0, min(Tb, d.T));
         const bool valid = t < Tb;
@@ -199,6 +212,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
         if (!valid) continue;
         float la, lb;
         split_lse2(row_max, lse2, la, lb);
+        if (lane == 0 && pend_b >= 0 && (d.progress & 1)) signal_frame_done(ws, w, pend_b, pend_t);
         if (lane == 0) lse_out[(size_t)b * d.T + t] = la + lb;
         // gather: column 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams (gram_ctc.py:24-32, :155)
         int Lb = d.label_lengths ? d.label_lengths[b] : d.Lmax;
@@ -216,7 +230,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
             if (sym >= 0 && sym < d.V) v = emission_pair(__ldg(row + sym), la, lb);
             lprow[c] = v;
         }
+        __syncwarp();
+        pend_b = b; pend_t = t;
     }
+    if (lane == 0 && pend_b >= 0 && (d.progress & 1)) signal_frame_done(ws, w, pend_b, pend_t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -228,6 +245,56 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
 // consumer also turns it into softmax * scale and hands it to the TMA engine as the gradient row; the few label
 // columns get their posterior subtracted later by posterior_patch_kernel (gradient.cu).  The activations are then
 // read from HBM once per step instead of twice.
+// "Row written" signals for a concurrently running lattice kernel (common.cuh, signal_frame_done).  A signal must
+// be a release at GPU scope, and such a fence costs ~1.5 us on this part whatever is outstanding -- per row and
+// consumer warp that was 28 us of a 105 us kernel.  So the consumers only note finished rows in a small
+// shared-memory FIFO (CTA-scope ordering, cheap) and one extra warp drains all FIFOs with ONE GPU-scope fence per
+// sweep, then bumps the progress counters (the __syncthreads / thread 0 fences / atomic pattern of a grid barrier).
+constexpr int kK1Threads = kRingThreads + 32;          // producer + consumers + signal warp
+constexpr int kFifoDepth = 4;
+struct SignalFifo {
+    int2 entry[kRingConsumers][kFifoDepth];            // (b, t); b < 0 = this consumer is done
+    unsigned head[kRingConsumers];                     // rows pushed by consumer c
+    unsigned tail[kRingConsumers];                     // rows taken by the signal warp
+};
+constexpr size_t kFifoBytes = (sizeof(SignalFifo) + 127) / 128 * 128;
+
+// consumer warp c, after a __syncwarp() that follows the row's global stores (lane 0 only)
+__device__ __forceinline__ void fifo_push(SignalFifo *f, int c, unsigned &pushed, int b, int t) {
+    volatile unsigned *tail = &f->tail[c];
+    while (pushed - *tail >= (unsigned)kFifoDepth) __nanosleep(64);
+    f->entry[c][pushed % kFifoDepth] = make_int2(b, t);
+    __threadfence_block();                             // row stores and entry before the head update
+    *reinterpret_cast<volatile unsigned *>(&f->head[c]) = ++pushed;
+}
+
+__device__ __forceinline__ void signal_warp(SignalFifo *f, int nc, int lane, unsigned char *ws, const WsLayout &w) {
+    unsigned taken = 0;
+    bool done = lane >= nc;
+    for (;;) {
+        bool have = false;
+        int2 e = make_int2(-1, 0);
+        if (!done && *reinterpret_cast<volatile unsigned *>(&f->head[lane]) != taken) {
+            __threadfence_block();
+            const volatile int *ep = reinterpret_cast<volatile int *>(&f->entry[lane][taken % kFifoDepth]);
+            e.x = ep[0];
+            e.y = ep[1];
+            have = true;
+        }
+        if (__any_sync(0xffffffffu, have)) {
+            __threadfence();                           // every row noted in the FIFOs is visible GPU-wide from here on
+            if (have) {
+                if (e.x < 0) done = true;
+                else signal_frame_done(ws, w, e.x, e.y, true);
+                *reinterpret_cast<volatile unsigned *>(&f->tail[lane]) = ++taken;
+            }
+        } else {
+            if (__all_sync(0xffffffffu, done)) break;
+            __nanosleep(256);
+        }
+    }
+}
+
 struct GradOut {
     float *grad;
     int64_t gstride_t, gstride_b;
@@ -235,10 +302,9 @@ struct GradOut {
 };
 
 template <bool ARGMAX, bool GRAD>
-__global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(ProblemDesc d, WsLayout w,
+__global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(ProblemDesc d, WsLayout w,
                                                                               unsigned char *ws,
-                                                                              int64_t *argmax_out, int b_major,
-                                                                              RingLayout rl, GradOut go) {
+                                                                              int64_t *argmax_out, RingLayout rl, GradOut go) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ring ring = ring_setup(smem_raw, rl);
     const int lane = threadIdx.x & 31;
@@ -246,11 +312,18 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
     const uint32_t row_bytes = (uint32_t)d.V * 4u;
-    float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);      // GRAD only: V zeros for padded frames
+    SignalFifo *fifo = reinterpret_cast<SignalFifo *>(smem_raw + rl.off_extra);
+    float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra + kFifoBytes);      // GRAD only: V zeros for padded frames
+    const bool signalling = (d.progress & 1) != 0;
+    if (threadIdx.x < kRingConsumers) { fifo->head[threadIdx.x] = 0u; fifo->tail[threadIdx.x] = 0u; }
     if (GRAD) {
         for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
         fence_proxy_async();
-        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == kRingConsumers + 1) {                     // ===== signal warp =====
+        if (signalling) signal_warp(fifo, ring.nc, lane, ws, w);
+        return;
     }
 
     if (warp == 0) {
@@ -264,8 +337,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
             int b = 0, t = 0;
             bool valid = false, need = false;
             if (lane < ring.batch && f < frames) {
-                if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
-                else { t = (int)(f / d.B); b = (int)(f % d.B); }
+                frame_of_ticket(f, d.B, d.T, (d.progress & 2) != 0, b, t);
                 int Tb = d.input_lengths ? __ldg(d.input_lengths + b) : d.T;
                 Tb = max(0, min(Tb, d.T));
                 valid = t < Tb;
@@ -297,6 +369,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
     float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
     const int n4 = d.V >> 2;
     if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
+    unsigned pushed = 0;
     for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
         const int s = ring_acquire(ring, q);
         const RowMeta m = ring.meta[s];
@@ -364,6 +437,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
                 if (sym >= 0 && sym < d.V) v = emission_pair(row[sym], la, lb);
                 lprow[cidx] = v;
             }
+            __syncwarp();
+            if (signalling && lane == 0) fifo_push(fifo, warp - 1, pushed, m.b, m.t);
             if (GRAD) {
                 // softmax * scale in place (same arithmetic as the gradient kernel), then one bulk store
                 __syncwarp();
@@ -390,6 +465,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) softmax_gather_ring_kernel(Pr
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[s]);
     }
+    if (signalling && lane == 0) fifo_push(fifo, warp - 1, pushed, -1, 0);
     if (GRAD && lane == 0) bulk_wait_all<0>();
 }
 
@@ -443,12 +519,11 @@ int sm_count() {
 }
 
 cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
-                                  cudaStream_t stream) {
+                                  size_t smem_reserve, cudaStream_t stream) {
     const long long frames = (long long)d.B * d.T;
     if (frames == 0) return cudaSuccess;
-    const int b_major = d.stride_b > d.stride_t ? 1 : 0;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
-    const RingLayout rl = make_ring((size_t)d.V * 4, 0);
+    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes, smem_reserve);
     if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) && !getenv("B200CTC_NO_TMA_K1")) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
         if (ctas > sm_count() - ring_sm_reserve()) ctas = sm_count() - ring_sm_reserve();
@@ -458,19 +533,21 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
         if (argmax_out) {
             e = cudaFuncSetAttribute(softmax_gather_ring_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
             if (e != cudaSuccess) return e;
-            softmax_gather_ring_kernel<true, false><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, argmax_out, b_major, rl, none);
+            cudaFuncSetAttribute(softmax_gather_ring_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            softmax_gather_ring_kernel<true, false><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, argmax_out, rl, none);
         } else {
             e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
             if (e != cudaSuccess) return e;
-            softmax_gather_ring_kernel<false, false><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, nullptr, b_major, rl, none);
+            cudaFuncSetAttribute(softmax_gather_ring_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            softmax_gather_ring_kernel<false, false><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, nullptr, rl, none);
         }
         return cudaGetLastError();
     }
     const int grid = grid_for_frames(frames);
     if (argmax_out)
-        softmax_gather_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, argmax_out, b_major);
+        softmax_gather_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, argmax_out);
     else
-        softmax_gather_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, nullptr, b_major);
+        softmax_gather_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, nullptr);
     return cudaGetLastError();
 }
 
@@ -481,9 +558,8 @@ cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, 
                                        int64_t gstride_b, float scale, cudaStream_t stream) {
     const long long frames = (long long)d.B * d.T;
     if (frames == 0) return cudaSuccess;
-    const int b_major = d.stride_b > d.stride_t ? 1 : 0;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
-    const RingLayout rl = make_ring((size_t)d.V * 4, (size_t)d.V * 4);
+    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes + (size_t)d.V * 4);
     if (!ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) || !ring_usable(grad, gstride_t, gstride_b, d.V, rl) ||
         getenv("B200CTC_NO_TMA_K1"))
         return cudaErrorNotSupported;
@@ -492,7 +568,8 @@ cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, 
     const GradOut go = {grad, gstride_t, gstride_b, scale};
     cudaError_t e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
     if (e != cudaSuccess) return e;
-    softmax_gather_ring_kernel<false, true><<<(int)ctas, kRingThreads, rl.total, stream>>>(d, w, wsb, nullptr, b_major, rl, go);
+    cudaFuncSetAttribute(softmax_gather_ring_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    softmax_gather_ring_kernel<false, true><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, nullptr, rl, go);
     return cudaGetLastError();
 }
 
