@@ -232,6 +232,7 @@ def main():
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    h0 = time.perf_counter()
     e0.record()
     for k in range(args.steps):
         x.grad = None
@@ -241,6 +242,7 @@ def main():
         loss.backward()
         ev[k][2].record()
     e1.record()
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps     # host time to ENQUEUE one step (no sync inside the loop)
     barrier()
     clocks = sampler.stop()
     elapsed_ms = e0.elapsed_time(e1)
@@ -295,7 +297,7 @@ def main():
                    "layout": "(T,B,V) float32", "l2": "inputs (717 MB) and outputs exceed the 126 MB L2; no flush needed",
                    "valid_frames_per_step": int(np.sum(prob["input_length"])), "loss": loss_value},
         "valid_frames_per_s": world * int(np.sum(prob["input_length"])) * args.steps / (elapsed_ms * 1e-3),
-        "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+        "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "host_enqueue_ms_per_step": host_ms,
         "roofline": {"bound": "hbm", "kernel": "gradient_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": k3_bytes},

@@ -153,7 +153,7 @@ __device__ __forceinline__ int count_blocks_done(const unsigned char *ws, const 
     }
     const unsigned m = __ballot_sync(0xffffffffu, ok);
     const int n = __ffs(~m) - 1;                      // leading run of complete blocks (32 if all)
-    if (n > 0) __threadfence();                       // acquire: the rows behind the counters are visible from here on
+    if (n > 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");      // acquire: the rows behind the counters are visible from here on
     return n < 0 ? 32 : n;
 }
 

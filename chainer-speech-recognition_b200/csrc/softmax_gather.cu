@@ -282,10 +282,12 @@ __device__ __forceinline__ void signal_warp(SignalFifo *f, int nc, int lane, uns
             have = true;
         }
         if (__any_sync(0xffffffffu, have)) {
-            __threadfence();                           // every row noted in the FIFOs is visible GPU-wide from here on
+            // release at GPU scope: one MEMBAR.ALL.GPU for the warp, then the REDs.  Not __threadfence(): that is a
+            // sequentially consistent fence plus an L1 invalidation (CCTL.IVALL), which would throw the consumers'
+            // cached label tables away every time.
             if (have) {
                 if (e.x < 0) done = true;
-                else signal_frame_done(ws, w, e.x, e.y, true);
+                else signal_frame_done(ws, w, e.x, e.y);
                 *reinterpret_cast<volatile unsigned *>(&f->tail[lane]) = ++taken;
             }
         } else {
