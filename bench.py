@@ -54,6 +54,22 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def profiled_traffic(kernel):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/r1_ncu_full_summary.json, written by tools/ncu_summary.py); None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")) as f:
+            for k in json.load(f):
+                if kernel in k["kernel"]:
+                    def to_bytes(v):
+                        num, unit = v.split()
+                        return float(num) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+                    return int(to_bytes(k["dram__bytes_read.sum"]) + to_bytes(k["dram__bytes_write.sum"]))
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks + throttle reasons sampled while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -298,8 +314,9 @@ def main():
                    "valid_frames_per_step": int(np.sum(prob["input_length"])), "loss": loss_value},
         "valid_frames_per_s": world * int(np.sum(prob["input_length"])) * args.steps / (elapsed_ms * 1e-3),
         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "host_enqueue_ms_per_step": host_ms,
-        "roofline": {"bound": "hbm", "kernel": "gradient_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+        "roofline": {"bound": "hbm", "kernel": "gradient_ring_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic("gradient_ring_kernel"),
+                     "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": k3_bytes},
         "step_roofline": {"achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,

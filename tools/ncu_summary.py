@@ -35,7 +35,7 @@ def short(name):
         if ch == "<":
             depth += 1
         elif ch == ">":
-            depth -= 1
+            depth = max(0, depth - 1)
         elif ch == "(" and depth == 0:
             cut = i
             break
@@ -45,7 +45,7 @@ def short(name):
         if ch == "<":
             depth += 1
         elif ch == ">":
-            depth -= 1
+            depth = max(0, depth - 1)
         elif ch == ":" and depth == 0:
             start = i + 1
     return name[start:][:70]
