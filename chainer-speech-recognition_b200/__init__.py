@@ -6,6 +6,7 @@ The directory name is not a Python identifier; import it with
 
     asr/loss/gram_ctc.py   gram_ctc(...)                                (reference: asr/loss/gram_ctc.py)
     asr/loss/ctc.py        connectionist_temporal_classification(...)   (reference: Chainer's, via run/ctc/*)
+    asr/error.py           compute_minibatch_error(...), compute_character_error_rate(...)   (reference: asr/error.py)
     csrc/                  sm_100a kernels + the C ABI (include/b200ctc.h)
 """
 from . import _lib, distributed, synth
@@ -13,5 +14,9 @@ from ._build import build
 from .asr.loss import (gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
                        ConnectionistTemporalClassification, greedy_argmax, ctc_host, gram_ctc_host)
 
-__all__ = ["gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
+from .asr.error import (compute_minibatch_error, compute_character_error_rate, build_expansion_table,
+                        minibatch_error_details)
+
+__all__ = ["compute_minibatch_error", "compute_character_error_rate", "build_expansion_table", "minibatch_error_details",
+           "gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
            "ConnectionistTemporalClassification", "greedy_argmax", "ctc_host", "gram_ctc_host", "build", "distributed", "synth"]

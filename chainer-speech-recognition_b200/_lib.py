@@ -47,7 +47,18 @@ def _bind(lib):
     lib.b200ctc_greedy_argmax.restype = c.c_int
     lib.b200ctc_greedy_argmax.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_int, c.c_int,
                                           c.c_void_p, c.c_void_p]
+    lib.b200ctc_greedy_error.restype = c.c_int
+    lib.b200ctc_greedy_error.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_int,
+                                         c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p,
+                                         c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.b200ctc_edit_distance.restype = c.c_int
+    lib.b200ctc_edit_distance.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_int,
+                                          c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t,
+                                          c.c_void_p]
     return lib
+
+
+ERROR_WORKSPACE_BYTES = 256
 
 
 def library_path():

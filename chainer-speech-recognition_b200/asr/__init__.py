@@ -1,1 +1,1 @@
-"""Mirror of the reference's ``asr`` package for the one path this repository replaces: ``asr.loss``."""
+"""Mirror of the reference's ``asr`` package for the path this repository replaces: ``asr.loss`` and ``asr.error``."""

@@ -302,4 +302,41 @@ int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b,
                       "argmax kernel");
 }
 
+int b200ctc_greedy_error(const int64_t *argmax, const int32_t *input_lengths, int B, int T, const int32_t *labels,
+                         int Lmax, int blank, const int32_t *expansion, int V, int E, int uint8_wrap, int32_t *hyp_out,
+                         int32_t *hyp_len, int32_t *ref_len, int32_t *distance, double *err_per_utt, double *err_mean,
+                         void *workspace, size_t workspace_bytes, void *stream_) {
+    if (B < 0 || T < 0 || Lmax < 0 || V <= 0 || E <= 0) return fail(B200CTC_INVALID_ARGUMENT, "bad dimensions%s");
+    if (B == 0) return B200CTC_OK;
+    if ((!argmax && T > 0) || (!labels && Lmax > 0) || !expansion || (!hyp_out && T > 0) || !err_per_utt || !workspace)
+        return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    if (workspace_bytes < B200CTC_ERROR_WORKSPACE_BYTES) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
+    if ((long long)T * E >= (1ll << 31)) return fail(B200CTC_UNSUPPORTED, "T*E too large%s");
+    if (sizeof(int) * (4 * (size_t)Lmax + 3) > 200 * 1024) return fail(B200CTC_UNSUPPORTED, "target of %s%lld ids is too long", "", Lmax);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = check_cuda(cudaMemsetAsync(workspace, 0, sizeof(unsigned), stream), "counter reset");
+    if (rc) return rc;
+    return check_cuda(launch_greedy_error(argmax, input_lengths, B, T, labels, Lmax, blank, expansion, V, E, uint8_wrap ? 1 : 0,
+                                          hyp_out, hyp_len, ref_len, distance, err_per_utt, err_mean,
+                                          static_cast<unsigned *>(workspace), stream),
+                      "greedy error kernel");
+}
+
+int b200ctc_edit_distance(const int32_t *ref, const int32_t *ref_len, int Rmax, const int32_t *hyp, const int32_t *hyp_len,
+                          int Hmax, int B, int uint8_wrap, int32_t *distance, double *err_per_utt, double *err_mean,
+                          void *workspace, size_t workspace_bytes, void *stream_) {
+    if (B < 0 || Rmax < 0 || Hmax < 0) return fail(B200CTC_INVALID_ARGUMENT, "bad dimensions%s");
+    if (B == 0) return B200CTC_OK;
+    if ((!ref && Rmax > 0) || (!hyp && Hmax > 0) || !ref_len || !hyp_len || !err_per_utt || !workspace)
+        return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    if (workspace_bytes < B200CTC_ERROR_WORKSPACE_BYTES) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
+    if (sizeof(int) * (4 * (size_t)Rmax + 3) > 200 * 1024) return fail(B200CTC_UNSUPPORTED, "reference of %s%lld ids is too long", "", Rmax);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = check_cuda(cudaMemsetAsync(workspace, 0, sizeof(unsigned), stream), "counter reset");
+    if (rc) return rc;
+    return check_cuda(launch_edit_distance(ref, ref_len, Rmax, hyp, hyp_len, Hmax, B, uint8_wrap ? 1 : 0, distance,
+                                           err_per_utt, err_mean, static_cast<unsigned *>(workspace), stream),
+                      "edit distance kernel");
+}
+
 }  // extern "C"

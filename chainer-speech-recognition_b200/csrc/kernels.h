@@ -65,4 +65,13 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
 // one-read path: subtract the merged posteriors at the label columns of a gradient that already holds softmax * scale
 cudaError_t launch_posterior_patch(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream);
 
+// evaluation path: greedy collapse + gram expansion + edit distance + error rate (greedy_error.cu)
+cudaError_t launch_greedy_error(const int64_t *argmax, const int32_t *input_lengths, int B, int T, const int32_t *labels,
+                                int Lmax, int blank, const int32_t *expansion, int V, int E, int wrap8, int32_t *hyp,
+                                int32_t *hyp_len, int32_t *ref_len, int32_t *distance, double *err_per_utt,
+                                double *err_mean, unsigned *done, cudaStream_t stream);
+cudaError_t launch_edit_distance(const int32_t *ref, const int32_t *ref_len, int Rmax, const int32_t *hyp,
+                                 const int32_t *hyp_len, int Hmax, int B, int wrap8, int32_t *distance,
+                                 double *err_per_utt, double *err_mean, unsigned *done, cudaStream_t stream);
+
 }  // namespace b200ctc

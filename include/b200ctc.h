@@ -12,8 +12,9 @@
  * Conventions
  *   - plain C types only; every pointer is a CUDA *device* pointer unless the name ends in _host;
  *   - the caller owns every buffer, including the workspace; the library keeps no device memory
- *     and no global state besides a thread-local last-error string (and, for b200ctc_forward_backward
- *     only, a per-device pool of internal streams and events);
+ *     and no global state besides a thread-local last-error string and, per host thread and device,
+ *     one internal side stream with two events (b200ctc_forward runs the lattice kernel on it next
+ *     to the softmax kernel; forked from and joined back into `stream`, capturable in a CUDA graph);
  *   - every function returns a status code (B200CTC_OK == 0) and never throws;
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
  *     except the *_host convenience entry points;
@@ -124,6 +125,38 @@ int b200ctc_rescale_grad(float *grad, int64_t gstride_t, int64_t gstride_b, int 
 /* Greedy path alone (run/ctc/cnn/train.py:232 and its 9 sibling call sites): out (B,T) int64. */
 int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b,
                           int B, int T, int V, int64_t *argmax_out, void *stream);
+
+/*
+ * Evaluation path after the greedy argmax: replaces compute_minibatch_error
+ * (asr/error.py:26-68) -- called on every development batch, run/ctc/cnn/train.py:231-233 -- and
+ * compute_character_error_rate (asr/error.py:7-24).
+ *   argmax        (B,T) int64: greedy ids (b200ctc_greedy_argmax / argmax_out of b200ctc_forward).
+ *   input_lengths (B) int32 or NULL: frames to decode per utterance.  The reference decodes all T
+ *                 frames of the padded batch (asr/error.py:40), i.e. NULL.
+ *   labels        (B,Lmax) int32 targets padded with the blank id; blanks are dropped (:33-37).
+ *   expansion     (V,E) int32: the unigram ids a vocabulary id stands for, padded with -1 -- the
+ *                 reference's string round trip id -> token -> convert_sentence_to_unigram_ids
+ *                 (:49-53, asr/vocab.py:99-126), tabulated once on the host.
+ *   uint8_wrap    != 0: distances computed modulo 256 exactly as the reference's numpy.uint8 table
+ *                 does (:10); 0: true Levenshtein distance.
+ *   hyp_out       (B, T*E) int32 scratch/out: collapsed + expanded hypothesis; hyp_len (B) its length.
+ *   ref_len, distance (B) int32 or NULL;  err_per_utt (B) float64: distance / ref_len, or hyp_len
+ *                 for an empty target (:8-9);  err_mean (1) float64 or NULL: the batch mean, summed
+ *                 in batch order in float64 like the reference's Python floats (:55, :68).
+ *   workspace     B200CTC_ERROR_WORKSPACE_BYTES bytes.
+ */
+#define B200CTC_ERROR_WORKSPACE_BYTES 256
+int b200ctc_greedy_error(const int64_t *argmax, const int32_t *input_lengths, int B, int T,
+                         const int32_t *labels, int Lmax, int blank,
+                         const int32_t *expansion, int V, int E, int uint8_wrap,
+                         int32_t *hyp_out, int32_t *hyp_len, int32_t *ref_len, int32_t *distance,
+                         double *err_per_utt, double *err_mean,
+                         void *workspace, size_t workspace_bytes, void *stream);
+/* Edit distance / error rate of explicit id sequences: ref (B,Rmax), hyp (B,Hmax), lengths (B). */
+int b200ctc_edit_distance(const int32_t *ref, const int32_t *ref_len, int Rmax,
+                          const int32_t *hyp, const int32_t *hyp_len, int Hmax, int B, int uint8_wrap,
+                          int32_t *distance, double *err_per_utt, double *err_mean,
+                          void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

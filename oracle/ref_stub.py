@@ -112,3 +112,27 @@ def run_ctc(x_tbv, labels, input_length, label_length, blank=0, reduce="no", gy=
     labels = np.asarray(labels, np.int32)
     return run_gram_ctc(x_tbv, labels, np.full_like(labels, -1), input_length, label_length,
                         blank=blank, reduce=reduce, gy=gy)
+
+
+_error_modules = None
+
+
+def load_error_module():
+    """The reference's asr/error.py and asr/vocab.py, UNMODIFIED, loaded as the synthetic package ``_refasr``
+    (asr/error.py:4-5 uses relative imports of .utils and .vocab; both are pure Python).  Returns (error, vocab)."""
+    global _error_modules
+    if _error_modules is None:
+        if not available():
+            raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
+        pkg = types.ModuleType("_refasr")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "asr")]
+        sys.modules["_refasr"] = pkg
+        mods = {}
+        for name in ("utils", "vocab", "error"):
+            spec = importlib.util.spec_from_file_location("_refasr." + name, os.path.join(REFERENCE_ROOT, "asr", name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["_refasr." + name] = mod
+            spec.loader.exec_module(mod)
+            mods[name] = mod
+        _error_modules = (mods["error"], mods["vocab"])
+    return _error_modules
