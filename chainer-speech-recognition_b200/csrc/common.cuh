@@ -199,6 +199,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 // A few immediate retries (the usual case: the partner is a handful of cycles away), then polite polling, so that
 // a warp that waits for long does not take issue slots from the warps it shares the SM with.
+// non-blocking probe (try_wait may suspend the thread for a while when the phase is not complete yet)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     for (int i = 0; i < 8; ++i)
         if (mbar_try_wait(bar, parity)) return;

@@ -57,8 +57,11 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 
 namespace {
 
-constexpr int kChunk = kProgBlock;   // frames per pipeline chunk (and per mantissa renormalisation)
-constexpr int kMaxStages = 8;    // W + 3 is deep enough that the I/O warp never waits on the last compute warp
+// Frames per pipeline chunk (and per mantissa renormalisation) are a template parameter CH: 16 for the usual
+// lattices, 8 or 4 for long label sequences, whose emission rows are wide -- the stage ring must hold the W chunks
+// the warps are working on plus 3 in front of them (a bulk copy takes ~2 us from issue to landing, longer than a
+// chunk), and a stage is CH rows.
+constexpr int kMaxStages = 24;
 constexpr int kMaxWarpsPerDir = 16;
 
 // Reversed direction: q <-> j = Nb - 1 - q, so the reversed CTC lattice has the same shape as the forward one
@@ -82,11 +85,11 @@ struct LaneState {
 // shared-memory view of the pipeline (32-bit shared-space addresses: no generic-pointer conversion inside the
 // recursion loop)
 struct DirPipe {
-    uint32_t lp;             // [S][kChunk][Wlp] float2   staged emission rows
-    uint32_t bnd;            // [W-1][S][kChunk][PAD] float2 boundary values handed from warp w to warp w+1;
+    uint32_t lp;             // [S][CH][Wlp] float2   staged emission rows
+    uint32_t bnd;            // [W-1][S][CH][PAD] float2 boundary values handed from warp w to warp w+1;
                              //   as deep as the stage ring, so a buffer is free by the time it comes round again
                              //   (a warp can only be at chunk c once the last warp has consumed chunk c-S)
-    uint32_t bnd_none;       // [kChunk][PAD] float2 of (0, SENT): what warp 0 reads as "the warp before me"
+    uint32_t bnd_none;       // [CH][PAD] float2 of (0, SENT): what warp 0 reads as "the warp before me"
     uint64_t *full;          // [S]     emission rows of a chunk have landed (tx count); warp 0 waits on it
     uint64_t *consumed;      // [S]     the last warp is done with the stage (hence every warp is)
     uint64_t *ready;         // [W-1][S] warp w finished the chunk: its boundary values can be read, and the
@@ -246,23 +249,23 @@ __device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, b
 // The softmax/gather kernel may still be running (api.cu launches the two kernels concurrently): before a chunk's
 // rows are copied, the warp makes sure the 16-frame blocks the chunk touches are complete.  It keeps a watermark of
 // blocks known complete in its direction of travel and, when it has to look, checks 32 blocks with one round trip.
-template <bool REV>
+template <bool REV, int CH>
 __device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c, int f0, int n, int lane,
                                              const unsigned char *ws, const WsLayout &wl, int b, bool poll) {
     if (n <= 0) return;
     const int S = c.S;
-    const int nchunks = (n + kChunk - 1) / kChunk;
+    const int nchunks = (n + CH - 1) / CH;
     const uint32_t row_bytes = (uint32_t)c.Wlp * 8u;
-    const uint32_t stage_bytes = row_bytes * kChunk;
+    const uint32_t stage_bytes = row_bytes * CH;
     int stage = 0;
     uint32_t wrap = 0;
     // blocks [0, known) (forward) / (known, last] (reversed) are complete
     int known = REV ? (n + kProgBlock - 1) / kProgBlock : 0;
     for (int ch = 0; ch < nchunks; ++ch) {
-        const int i0 = ch * kChunk;
-        const int cnt = min(kChunk, n - i0);
+        const int i0 = ch * CH;
+        const int cnt = min(CH, n - i0);
         const int flo = REV ? (f0 - i0 - cnt + 1) : (f0 + i0);
-        if (wrap > 0 && lane == 0) mbar_wait_backoff(&pp.consumed[stage], (wrap - 1) & 1u);
+        if (wrap > 0 && lane == 0) mbar_wait(&pp.consumed[stage], (wrap - 1) & 1u);
         if (!poll) {
         } else if (!REV) {
             const int need = (flo + cnt - 1) / kProgBlock + 1;           // blocks [0, need) must be complete
@@ -293,17 +296,17 @@ __device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c,
 }
 
 // Visit n frames starting at f0 (ascending for alpha, descending for beta) with warp w of W.
-template <int K, bool GRAM, bool REV>
+template <int K, bool GRAM, bool REV, int CH>
 __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirPipe &pp, const UttCtx &c, int f0, int n,
                                               int w, int lane) {
     constexpr int PAD = Geo<K, GRAM>::PAD;
     if (n <= 0) return;
     const int W = c.W, S = c.S;
-    const int nchunks = (n + kChunk - 1) / kChunk;
+    const int nchunks = (n + CH - 1) / CH;
     const bool has_prev = (w > 0), has_next = (w + 1 < W);
     const uint32_t row_bytes = (uint32_t)c.Wlp * 8u;
-    const uint32_t stage_bytes = row_bytes * kChunk;
-    const uint32_t bnd_chunk_bytes = kChunk * PAD * 8u;
+    const uint32_t stage_bytes = row_bytes * CH;
+    const uint32_t bnd_chunk_bytes = CH * PAD * 8u;
     const int gl = 32 * w + lane;                             // lane index within the direction
     const int jbase = REV ? (c.Nb - 1 - K * gl + c.boff) : (K * gl);
     const int64_t frame_step = REV ? -(int64_t)c.Np : (int64_t)c.Np;
@@ -320,7 +323,7 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
     long long acc_wait = 0, acc_work = 0, acc_tail = 0;
     const bool prof = (g_lat_dbg != nullptr) && lane == 0 && blockIdx.x < 64;
     for (int ch = 0; ch < nchunks; ++ch) {
-        const int cnt = min(kChunk, n - ch * kChunk);
+        const int cnt = min(CH, n - ch * CH);
         long long tq0 = 0, tq1 = 0, tq2 = 0;
         if (prof) tq0 = clock64();
         if (!early) {
@@ -335,11 +338,11 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
         const int nstage = (stage + 1 == S) ? 0 : stage + 1;
         const uint32_t nwrap = (stage + 1 == S) ? wrap + 1 : wrap;
         early = false;
-        if (cnt == kChunk) {                                  // full chunk: straight-line code, no per-step branch
+        if (cnt == CH) {                                  // full chunk: straight-line code, no per-step branch
 #pragma unroll
-            for (int i = 0; i < kChunk; ++i) {
-                const int row = REV ? (kChunk - 1 - i) : i;
-                if (i == kChunk - 1 && ch + 1 < nchunks) early = mbar_try_wait(&wait_bar[nstage], nwrap & 1u);
+            for (int i = 0; i < CH; ++i) {
+                const int row = REV ? (CH - 1 - i) : i;
+                if (i == CH - 1 && ch + 1 < nchunks) early = mbar_test_wait(&wait_bar[nstage], nwrap & 1u);
                 lattice_step<K, GRAM, REV>(st, lane, has_next, bin + i * PAD * 8u, bout + i * PAD * 8u,
                                            lp_s + (uint32_t)row * row_bytes, out_ptr + i * frame_step);
             }
@@ -351,8 +354,8 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
                                            lp_s + (uint32_t)row * row_bytes, out_ptr + i * frame_step);
             }
         }
-        out_ptr += kChunk * frame_step;
-        // pull the mantissas back into [1,2): they moved by at most 2^-kChunk .. 3^kChunk since the last time
+        out_ptr += CH * frame_step;
+        // pull the mantissas back into [1,2): they moved by at most 2^-CH .. 3^CH since the last time
 #pragma unroll
         for (int r = 0; r < K; ++r) renorm_pair(st.m[r], st.e[r]);
         if (prof) { tq2 = clock64(); acc_work += tq2 - tq1; }
@@ -416,12 +419,12 @@ struct SmemPlan {
     int nbars;
 };
 
-__host__ __device__ inline SmemPlan plan_smem(int Wlp, int W, int S, int PAD) {
+__host__ __device__ inline SmemPlan plan_smem(int Wlp, int W, int S, int PAD, int CH) {
     SmemPlan p;
-    p.lp_elems = (size_t)S * kChunk * Wlp;
-    p.bnd_elems = (size_t)(W > 1 ? W - 1 : 1) * S * kChunk * PAD;
+    p.lp_elems = (size_t)S * CH * Wlp;
+    p.bnd_elems = (size_t)(W > 1 ? W - 1 : 1) * S * CH * PAD;
     p.bnd_elems = (p.bnd_elems + 1) & ~(size_t)1;                      // keep 16-byte alignment of what follows
-    p.none_elems = ((size_t)kChunk * PAD + 1) & ~(size_t)1;
+    p.none_elems = ((size_t)CH * PAD + 1) & ~(size_t)1;
     p.nbars = 2 * S + S * (W > 1 ? W - 1 : 0);
     size_t o = (p.lp_elems + p.bnd_elems + p.none_elems) * sizeof(float2);
     p.off_bars = align_up(o, 16);
@@ -434,7 +437,7 @@ __host__ __device__ inline SmemPlan plan_smem(int Wlp, int W, int S, int PAD) {
 
 // MAXW bounds the compute warps of an instantiation, so that small lattices (the common case) are not
 // compiled under the register cap a large CTA implies.
-template <int K, bool GRAM, int MAXW>
+template <int K, bool GRAM, int MAXW, int CH>
 __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PAD = Geo<K, GRAM>::PAD;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
     Lb = __shfl_sync(0xffffffffu, max(0, min(Lb, d.Lmax)), 0);
     const int Nb = (GRAM ? 3 : 2) * Lb + 1;
 
-    const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);
+    const SmemPlan sp = plan_smem(p.w.W, W, S, PAD, CH);
     float2 *f2base = reinterpret_cast<float2 *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + sp.off_bars);
     float *red = reinterpret_cast<float *>(smem_raw + sp.off_red);
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         for (int i = 0; i < sp.nbars; ++i) mbar_init(&bars[i], 1u);      // every barrier has exactly one arriver
         mbar_init_fence();
     }
-    for (int i = threadIdx.x; i < kChunk * PAD; i += blockDim.x)
+    for (int i = threadIdx.x; i < CH * PAD; i += blockDim.x)
         f2base[sp.lp_elems + sp.bnd_elems + i] = make_float2(0.f, SENT);
     __syncthreads();
 
@@ -489,14 +492,14 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         c.out_g = dir == 0 ? av : bv;
         c.Wlp = p.w.W; c.Np = p.w.Np; c.Nb = Nb; c.W = W; c.S = S; c.boff = p.w.boff;
         if (io) {
-            if (dir == 0) io_direction<false>(pp, c, 0, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
-            else          io_direction<true>(pp, c, Tb - 1, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
+            if (dir == 0) io_direction<false, CH>(pp, c, 0, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
+            else          io_direction<true, CH>(pp, c, Tb - 1, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
         } else {
             LaneState<K, GRAM> st;
             init_lane<K, GRAM>(st, d, b, Lb, Nb, dir == 1, 32 * w + lane);
             if (p.dbg_nostore) st.valid = 0u;            // timing experiment only (B200CTC_LAT_NOSTORE): results are garbage
-            if (dir == 0) run_direction<K, GRAM, false>(st, pp, c, 0, Tb, w, lane);         // alpha: frames 0 .. Tb-1
-            else          run_direction<K, GRAM, true>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
+            if (dir == 0) run_direction<K, GRAM, false, CH>(st, pp, c, 0, Tb, w, lane);         // alpha: frames 0 .. Tb-1
+            else          run_direction<K, GRAM, true, CH>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
         }
     }
     if (dir == 1) return;                                  // the beta CTA is done
@@ -556,9 +559,9 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
     }
 }
 
-template <int K, bool GRAM, int MAXW>
+template <int K, bool GRAM, int MAXW, int CH>
 cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
-    auto kern = lattice_kernel<K, GRAM, MAXW>;
+    auto kern = lattice_kernel<K, GRAM, MAXW, CH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // the SM's L1/shared split is chosen per kernel: ask for the maximum so that a lattice CTA and a ring CTA of the
@@ -568,11 +571,12 @@ cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// instantiated combinations: few warps -> 16-frame chunks; many warps -> shorter chunks (see kMaxStages)
 template <int K, bool GRAM>
-cudaError_t launch_one(const LatticeParams &p, size_t smem, cudaStream_t stream) {
-    if (p.W <= 3) return launch_w<K, GRAM, 3>(p, smem, stream);
-    if (p.W <= 7) return launch_w<K, GRAM, 7>(p, smem, stream);
-    return launch_w<K, GRAM, kMaxWarpsPerDir>(p, smem, stream);
+cudaError_t launch_one(const LatticeParams &p, int CH, size_t smem, cudaStream_t stream) {
+    if (p.W <= 3) return launch_w<K, GRAM, 3, 16>(p, smem, stream);
+    if (p.W <= 7) return CH == 16 ? launch_w<K, GRAM, 7, 16>(p, smem, stream) : launch_w<K, GRAM, 7, 8>(p, smem, stream);
+    return CH == 8 ? launch_w<K, GRAM, kMaxWarpsPerDir, 8>(p, smem, stream) : launch_w<K, GRAM, kMaxWarpsPerDir, 4>(p, smem, stream);
 }
 
 constexpr size_t kLatticeSmemBudget = 224 * 1024;
@@ -596,11 +600,18 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     const int W = (Nmax + 32 * K - 1) / (32 * K);
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
-    // next to the softmax/gather kernel the recursion is fed at that kernel's pace: a shallow ring is enough
-    int S = W + (concurrent ? 2 : 3) < kMaxStages ? W + (concurrent ? 2 : 3) : kMaxStages;
+    // chunk length: the longest one instantiated for this W whose ring of W + 3 stages fits
+    // (next to the softmax/gather kernel a small lattice gets one stage less: shared memory taken here is taken
+    // from that kernel's ring, and measured on the bench workload the shallower ring is the better trade)
+    const int ahead = (concurrent && W <= 3) ? 2 : 3;
+    const int want = W + ahead < kMaxStages ? W + ahead : kMaxStages;
+    int CH = W <= 7 ? 16 : 8;
+    const int CHmin = W <= 3 ? 16 : (W <= 7 ? 8 : 4);
+    while (CH > CHmin && plan_smem(p.w.W, W, want, PAD, CH).total > kLatticeSmemBudget) CH >>= 1;
+    int S = want;
     if (const char *e = getenv("B200CTC_LAT_STAGES")) S = atoi(e);               // experiment knob
-    while (S > 2 && plan_smem(p.w.W, W, S, PAD).total > kLatticeSmemBudget) --S;
-    const SmemPlan sp = plan_smem(p.w.W, W, S, PAD);
+    while (S > 2 && plan_smem(p.w.W, W, S, PAD, CH).total > kLatticeSmemBudget) --S;
+    const SmemPlan sp = plan_smem(p.w.W, W, S, PAD, CH);
     if (sp.total > kLatticeSmemBudget) { *status = 2; return cudaSuccess; }
     size_t smem = sp.total;
     const size_t prep = prep_smem_bytes(kind, p.d.Lmax, p.w.nwords);
@@ -610,8 +621,8 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     p.dbg_nostore = getenv("B200CTC_LAT_NOSTORE") ? 1 : 0;
     if (smem_out) *smem_out = smem;
     if (!launch) return cudaSuccess;
-    if (kind == 0) return K == 2 ? launch_one<2, false>(p, smem, stream) : launch_one<4, false>(p, smem, stream);
-    return K == 3 ? launch_one<3, true>(p, smem, stream) : launch_one<6, true>(p, smem, stream);
+    if (kind == 0) return K == 2 ? launch_one<2, false>(p, CH, smem, stream) : launch_one<4, false>(p, CH, smem, stream);
+    return K == 3 ? launch_one<3, true>(p, CH, smem, stream) : launch_one<6, true>(p, CH, smem, stream);
 }
 
 }  // namespace b200ctc

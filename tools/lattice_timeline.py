@@ -10,10 +10,11 @@ import b200ctc
 synth = importlib.import_module("chainer-speech-recognition_b200.synth")
 lib = b200ctc._lib.load()
 kind = sys.argv[1] if len(sys.argv) > 1 else "ctc"
+dims = [int(v) for v in sys.argv[2:6]] if len(sys.argv) >= 6 else None        # B T V L
 if kind == "ctc":
-    prob = synth.ctc_problem(64, 800, 3500, 80, seed=0)
+    prob = synth.ctc_problem(*(dims or [64, 800, 3500, 80]), seed=0)
 else:
-    prob = synth.gram_problem(32, 600, 8000, 60, seed=0)
+    prob = synth.gram_problem(*(dims or [32, 600, 8000, 60]), seed=0)
 dev = torch.device("cuda:0")
 B = prob["x"].shape[1]
 x = torch.tensor(prob["x"], device=dev)
@@ -37,7 +38,7 @@ a = dbg.cpu().numpy().reshape(64, 32, 8)       # [lattice CTA = 2*b + direction]
 t_end = a[:, :, 6]; t0 = t_end[t_end > 0].min()
 for b in (0, 5, min(B - 1, 31)):
     for d, nm in ((0, "alpha"), (1, "beta")):
-        for wi in range(8):
+        for wi in range(16):
             r = a[2 * b + d, wi]
             if r[5] == 0: continue
             print("utt %2d T %d %s warp %d per-chunk cycles: wait %.0f work %.0f hand-over %.0f (chunks %d)" % (
