@@ -81,7 +81,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -260,7 +260,6 @@ def main():
     e1.record()
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps     # host time to ENQUEUE one step (no sync inside the loop)
     barrier()
-    clocks = sampler.stop()
     elapsed_ms = e0.elapsed_time(e1)
     fwd_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
     bwd_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]))
@@ -287,6 +286,7 @@ def main():
         e2e_loss = e2e_step()
     s1.record()
     barrier()
+    clocks = sampler.stop()           # sampled over both timed regions (device-resident steps and end-to-end steps)
     t2 = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -322,9 +322,9 @@ def main():
                           "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                           "algorithmic_bytes_per_step": step_bytes},
         "e2e": {"value": world * B * T * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(g_host.numel() * 4 + 4),
+                "h2d_bytes_per_step": int(np.sum(prob["input_length"])) * V * 4, "d2h_bytes_per_step": int(g_host.numel() * 4 + 4),
                 "ms_per_step": e2e_ms / args.e2e_steps, "loss": e2e_loss,
-                "api": "b200ctc.ctc_host: 8 utterance groups, H2D / kernels / D2H on three streams, pinned host buffers"},
+                "api": "b200ctc.ctc_host: 16 utterance groups, H2D (valid frames only) / kernels / D2H on three streams, pinned host buffers"},
         "gpu_launches": 4 * args.steps,          # per step: header reset, softmax/gather, lattice(+prep), gradient
         "clocks": clocks,
     }

@@ -5,6 +5,9 @@ asr/loss/gram_ctc.py:247,285); a user of that path hands over host activations a
 gradients.  Here the arithmetic still runs on the GPU: the batch is cut into utterance groups and the
 three stages of a group -- activations host->device, loss forward + gradient, gradient device->host --
 run on three CUDA streams, so the PCIe transfers in both directions overlap each other and the kernels.
+Host->device, only valid frames cross PCIe (padded frames are never read by the kernels).  The gradient comes back
+whole: letting the host zero the padded rows itself instead (they are exactly 0, gram_ctc.py:296) was measured
+slower -- a CPU memset of pinned memory runs at a fraction of the PCIe rate.
 Utterances are independent, so grouping changes no result bit-for-bit per utterance.
 
 Layout: host activations are (B,T,V) ("batch first", the decoder layout of asr/model/cnn.py:45-47), which makes
@@ -54,7 +57,7 @@ def _raw_forward_backward(kind, acts_tbv, labels, bigrams, in_len, lab_len, blan
 
 
 def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length, label_length, reduce="mean",
-                      grad_out=None, groups=8, device=None, gy=1.0):
+                      grad_out=None, groups=16, device=None, gy=1.0):
     """x_host: (B,T,V) float32 host tensor / ndarray.  Returns (loss, grad_host): loss a Python float ('mean') or a
     (B,) ndarray ('no'); grad_host a (B,T,V) host tensor = d loss / d x (times gy)."""
     if reduce not in ("mean", "no"):
@@ -74,6 +77,10 @@ def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length,
         grad_out = torch.empty((B, T, V), dtype=torch.float32, pin_memory=True)
     labels = _as_int32(labels, dev, "labels")
     bigrams = _as_int32(bigrams, dev, "label_bigram") if kind == _lib.KIND_GRAM else None
+    il_host = None
+    if input_length is not None:
+        il_host = (input_length.detach().cpu().numpy() if isinstance(input_length, torch.Tensor)
+                   else np.asarray(input_length)).astype(np.int64)
     input_length = _as_int32(input_length, dev, "input_length")
     label_length = _as_int32(label_length, dev, "label_length")
     s_in, s_run, s_out = _get_streams(dev)
@@ -92,7 +99,13 @@ def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length,
         if b1 == b0:
             continue
         with torch.cuda.stream(s_in):
-            x_dev[b0:b1].copy_(x_host[b0:b1], non_blocking=True)
+            if il_host is None:
+                x_dev[b0:b1].copy_(x_host[b0:b1], non_blocking=True)
+            else:                              # padded frames are never read by the kernels: do not ship them
+                for b in range(b0, b1):
+                    n = int(min(max(il_host[b], 0), T))
+                    if n > 0:
+                        x_dev[b, :n].copy_(x_host[b, :n], non_blocking=True)
             e_in = torch.cuda.Event(); e_in.record(s_in)
         with torch.cuda.stream(s_run):
             s_run.wait_event(e_in)

@@ -234,8 +234,10 @@ def test_host_entry_point_matches_device_path(pkg):
         xb = np.ascontiguousarray(prob["x"].transpose(1, 0, 2))                      # (B,T,V)
         if kind == "ctc":
             loss, grad = pkg.ctc_host(xb, prob["labels"], 0, prob["input_length"], prob["label_length"], reduce="no", groups=4)
+            poisoned = torch.full(xb.shape, float("nan")).pin_memory()           # padded rows must come back as zeros
             lm, gm = pkg.ctc_host(torch.from_numpy(xb).pin_memory(), prob["labels"], 0, prob["input_length"],
-                                  prob["label_length"], reduce="mean", groups=3)
+                                  prob["label_length"], reduce="mean", groups=3, grad_out=poisoned)
+            assert gm is poisoned
         else:
             loss, grad = pkg.gram_ctc_host(xb, prob["labels"], prob["bigrams"], 0, prob["input_length"],
                                            prob["label_length"], reduce="no", groups=4)
