@@ -11,12 +11,12 @@ The directory name is not a Python identifier; import it with
 """
 from . import _lib, distributed, synth
 from ._build import build
-from .asr.loss import (gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
+from .asr.loss import (gram_ctc, joint_gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
                        ConnectionistTemporalClassification, greedy_argmax, ctc_host, gram_ctc_host)
 
 from .asr.error import (compute_minibatch_error, compute_character_error_rate, build_expansion_table,
                         minibatch_error_details)
 
-__all__ = ["compute_minibatch_error", "compute_character_error_rate", "build_expansion_table", "minibatch_error_details",
+__all__ = ["joint_gram_ctc", "compute_minibatch_error", "compute_character_error_rate", "build_expansion_table", "minibatch_error_details",
            "gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
            "ConnectionistTemporalClassification", "greedy_argmax", "ctc_host", "gram_ctc_host", "build", "distributed", "synth"]

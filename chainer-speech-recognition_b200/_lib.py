@@ -9,7 +9,7 @@ import os
 from . import _build
 
 OK, INVALID_ARGUMENT, UNSUPPORTED, CUDA_ERROR, WORKSPACE_TOO_SMALL, OUT_OF_MEMORY = range(6)
-KIND_CTC, KIND_GRAM = 0, 1
+KIND_CTC, KIND_GRAM, KIND_JOINT = 0, 1, 2
 
 _lib = None
 

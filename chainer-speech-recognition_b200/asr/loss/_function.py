@@ -79,7 +79,7 @@ class LatticeLossFunction(torch.autograd.Function):
         loss_red = torch.empty((), dtype=torch.float32, device=dev)
         loss_scale = 1.0 / float(batch_global) if reduce == "mean" else 1.0     # gram_ctc.py:280-281
         argmax = torch.empty((B, T), dtype=torch.int64, device=dev) if want_argmax else None
-        groups = pipeline_groups(B) if (ctx.needs_input_grad[0] and not want_argmax) else 0
+        groups = pipeline_groups(B) if (ctx.needs_input_grad[0] and not want_argmax and kind != _lib.KIND_JOINT) else 0
         ptr = lambda t: t.data_ptr() if t is not None else None
         if groups > 0:
             # training step: loss and gradient in one pipelined call (include/b200ctc.h, b200ctc_forward_backward)
@@ -187,7 +187,7 @@ def lattice_loss(kind, xs, labels, bigrams, blank_symbol, input_length, label_le
     labels = _as_int32(labels, dev, "labels")                    # :234
     if labels.dim() != 2 or labels.shape[0] != B:
         raise ValueError("labels must have shape (B, Lmax)")
-    if kind == _lib.KIND_GRAM:
+    if kind != _lib.KIND_CTC:
         bigrams = _as_int32(bigrams, dev, "label_bigram")        # :235
         assert labels.shape[1] == bigrams.shape[1]               # :308
         if bigrams.shape != labels.shape:
@@ -195,7 +195,7 @@ def lattice_loss(kind, xs, labels, bigrams, blank_symbol, input_length, label_le
     else:
         bigrams = None
     if input_length is None:                                     # :310-313: both default together
-        label_length = None if kind == _lib.KIND_GRAM or label_length is None else label_length
+        label_length = None if kind != _lib.KIND_CTC or label_length is None else label_length
     input_length = _as_int32(input_length, dev, "input_length")
     label_length = _as_int32(label_length, dev, "label_length")
     for name, v in (("input_length", input_length), ("label_length", label_length)):

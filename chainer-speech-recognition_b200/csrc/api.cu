@@ -16,7 +16,7 @@ namespace {
 
 // zeroes the workspace header (ticket counters) and the frame-progress counters in stream order
 __global__ void zero_header_kernel(WsHeader *h, unsigned *prog, int nprog) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; h->k2b_done = 0u; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) prog[i] = 0u;
 }
 
@@ -66,7 +66,7 @@ __global__ void rescale_commit_kernel(const float *gy, int per_utterance, int B,
     for (int i = threadIdx.x; i < n; i += blockDim.x) applied[i] = gy[i];
 }
 __global__ void fused_init_kernel(WsHeader *h, float *applied, int n, unsigned *prog, int nprog) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; h->k2b_done = 0u; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) applied[i] = 1.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) prog[i] = 0u;
 }
@@ -85,7 +85,8 @@ int check_cuda(cudaError_t e, const char *what) {
 }
 
 int validate(int kind, int B, int T, int V, int Lmax, int blank, bool need_blank) {
-    if (kind != B200CTC_KIND_CTC && kind != B200CTC_KIND_GRAM) return fail(B200CTC_INVALID_ARGUMENT, "kind must be 0 (CTC) or 1 (Gram-CTC)%s");
+    if (kind != B200CTC_KIND_CTC && kind != B200CTC_KIND_GRAM && kind != B200CTC_KIND_JOINT)
+        return fail(B200CTC_INVALID_ARGUMENT, "kind must be 0 (CTC), 1 (Gram-CTC) or 2 (joint)%s");
     if (B < 0 || T < 0 || V <= 0 || Lmax < 0)
         return fail(B200CTC_INVALID_ARGUMENT, "negative or empty dimension%s (B=%lld ...)", "", B);
     if ((long long)B * (long long)T >= (1ll << 31))
@@ -128,7 +129,7 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
     if (rc) return rc;
     if (!acts && (size_t)B * T > 0) return fail(B200CTC_INVALID_ARGUMENT, "acts is NULL%s");
     if (!labels && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "labels is NULL%s");
-    if (kind == B200CTC_KIND_GRAM && !bigrams && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "bigrams is NULL for Gram-CTC%s");
+    if (kind != B200CTC_KIND_CTC && !bigrams && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "bigrams is NULL for Gram-CTC%s");
     if (!loss_per_utt || !loss_reduced || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "output or workspace pointer is NULL%s");
     if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
     if ((reinterpret_cast<uintptr_t>(acts) & 3) != 0) return fail(B200CTC_INVALID_ARGUMENT, "acts must be 4-byte aligned%s");
@@ -140,9 +141,9 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
     if (B == 0) return check_cuda(cudaMemsetAsync(loss_reduced, 0, sizeof(float), stream), "memset");
 
     ProblemDesc d;
-    d.kind = kind; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
+    d.kind = kind == B200CTC_KIND_CTC ? 0 : 1; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
     d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
-    d.labels = labels; d.bigrams = kind == B200CTC_KIND_GRAM ? bigrams : nullptr;
+    d.labels = labels; d.bigrams = kind != B200CTC_KIND_CTC ? bigrams : nullptr;
     d.input_lengths = input_lengths; d.label_lengths = label_lengths;
     d.progress = 0;
 
@@ -155,8 +156,16 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
     LatticeParams lp;
     lp.d = d; lp.w = w; lp.ws = ws;
     lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
-    lp.W = 0; lp.S = 0;
+    lp.W = 0; lp.S = 0; lp.second = 0;
     int st = 0;
+    // joint Gram-CTC + CTC: the plain-CTC lattice is a second launch behind the Gram-CTC one (same stream), on the
+    // same emission rows; it adds its loss to loss_per_utt and reduces the batch
+    LatticeParams lp2 = lp;
+    if (w.joint) {
+        lp2.d.kind = 0; lp2.d.bigrams = nullptr;
+        lp2.w = ctc_view_of_joint(w);
+        lp2.second = 1;
+    }
 
     // The lattice kernel runs NEXT TO the softmax/gather kernel, on a side stream: the recursion is a latency-bound
     // dependent chain that needs a few warps per utterance, the softmax a bandwidth-bound stream over all SMs, and
@@ -181,11 +190,16 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
         if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, lat_smem, stream), "softmax/gather kernel"))) return rc;
         if ((rc = check_cuda(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait"))) return rc;
         if ((rc = check_cuda(launch_lattice(lp, side->stream, &st, true), "lattice kernel"))) return rc;
+        if (w.joint && !st) {
+            lp2.d.progress = d.progress;
+            if ((rc = check_cuda(launch_lattice(lp2, side->stream, &st, false), "CTC lattice kernel"))) return rc;
+        }
         if ((rc = check_cuda(cudaEventRecord(side->join, side->stream), "join event"))) return rc;
         if ((rc = check_cuda(cudaStreamWaitEvent(stream, side->join, 0), "join wait"))) return rc;
     } else {
         if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, 0, stream), "softmax/gather kernel"))) return rc;
         if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
+        if (w.joint && !st && (rc = check_cuda(launch_lattice(lp2, stream, &st), "CTC lattice kernel"))) return rc;
     }
     if (st) return fail(B200CTC_UNSUPPORTED, "lattice of %s%lld nodes does not fit the kernel's shared-memory pipeline", "", w.Nmax);
     return B200CTC_OK;
@@ -202,7 +216,7 @@ int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stri
     const WsLayout w = make_layout(kind, B, T, V, Lmax);
     if (workspace_bytes < w.total) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
     GradParams g;
-    g.d.kind = kind; g.d.B = B; g.d.T = T; g.d.V = V; g.d.Lmax = Lmax; g.d.blank = blank;
+    g.d.kind = kind == B200CTC_KIND_CTC ? 0 : 1; g.d.B = B; g.d.T = T; g.d.V = V; g.d.Lmax = Lmax; g.d.blank = blank;
     g.d.acts = acts; g.d.stride_t = stride_t; g.d.stride_b = stride_b;
     g.d.labels = labels; g.d.bigrams = bigrams; g.d.input_lengths = nullptr; g.d.label_lengths = nullptr;
     g.d.progress = 0;
@@ -234,6 +248,7 @@ int b200ctc_forward_backward(int kind, const float *acts, int64_t stride_t, int6
     int rc = validate(kind, B, T, V, Lmax, blank, true);
     if (rc) return rc;
     if (!loss_per_utt || !loss_reduced || !workspace || !grad_out) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    if (kind == B200CTC_KIND_JOINT) return fail(B200CTC_UNSUPPORTED, "the one-call path does not take the joint loss%s");
     if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
     size_t need = 0;
     b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, 1, &need);
@@ -263,7 +278,7 @@ int b200ctc_forward_backward(int kind, const float *acts, int64_t stride_t, int6
     LatticeParams lp;
     lp.d = d; lp.w = w; lp.ws = ws;
     lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
-    lp.W = 0; lp.S = 0;
+    lp.W = 0; lp.S = 0; lp.second = 0;
     int st = 0;
     if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
     if (st) return fail(B200CTC_UNSUPPORTED, "lattice does not fit the kernel's shared-memory pipeline%s");

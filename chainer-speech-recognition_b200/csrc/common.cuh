@@ -41,6 +41,7 @@ struct WsHeader {
     unsigned int k3_ticket;    // next frame for the gradient kernel
     unsigned int k3_done;      // gradient warps that ran out of work (last one re-arms the queue)
     unsigned int k2_done;      // lattice CTAs that have published their loss (last one reduces the batch)
+    unsigned int k2b_done;     // same for the second (plain CTC) lattice of a joint Gram-CTC + CTC call
 };
 
 // Workspace carve-up (all offsets in bytes from a 16-byte aligned base).
@@ -55,14 +56,26 @@ struct WsLayout {
     int nblk;      // ceil(T / kProgBlock): progress counters per utterance
     size_t off_prog;   // [B][nblk] unsigned: emission rows of frames [16k, 16k+16) written so far (softmax/gather
                        // kernel -> lattice kernel, which may run concurrently with it)
+    // joint Gram-CTC + CTC (run/gram_ctc/cnn/train.py:196-198, both losses on the same activations): the Gram-CTC
+    // layout above plus the alpha/beta rows and utterance records of the plain-CTC lattice, which reads the same
+    // emission rows (its symbols are the blank and unigram columns of the Gram-CTC row)
+    int joint;         // 0 / 1
+    int Nmax2, Np2;    // CTC lattice nodes for Lmax, padded like Np (its beta rows are stored one element up)
+    size_t off_av2, off_bv2, off_utt2;
     size_t off_hdr, off_utt, off_lse, off_lp, off_av, off_bv, off_usym, off_uoff, off_unode, off_bm, off_pc, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// kind: 0 = CTC, 1 = Gram-CTC, 2 = joint Gram-CTC + CTC (laid out as Gram-CTC plus a second lattice)
 __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     WsLayout w;
+    const int joint = kind == 2 ? 1 : 0;
+    if (joint) kind = 1;
     w.kind = kind; w.B = B; w.T = T; w.V = V; w.Lmax = Lmax;
+    w.joint = joint;
+    w.Nmax2 = 2 * Lmax + 1;
+    w.Np2 = (w.Nmax2 + 1 + 3) & ~3;
     int width = 1 + (kind == 0 ? Lmax : 2 * Lmax);
     w.W = (width + 1) & ~1;
     w.Nmax = (kind == 0 ? 2 : 3) * Lmax + 1;
@@ -85,6 +98,12 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     w.off_bm = o;    o = align_up(o + sizeof(unsigned) * (size_t)B * w.nwords, 256);
     w.off_pc = o;    o = align_up(o + sizeof(int) * (size_t)B * w.nwords, 256);
     w.off_prog = o;  o = align_up(o + sizeof(unsigned) * (size_t)B * w.nblk, 256);
+    w.off_av2 = w.off_bv2 = w.off_utt2 = 0;
+    if (joint) {
+        w.off_utt2 = o;  o = align_up(o + sizeof(UttInfo) * (size_t)B, 256);
+        w.off_av2 = o;   o = align_up(o + sizeof(float2) * BT * w.Np2, 256);
+        w.off_bv2 = o;   o = align_up(o + sizeof(float2) * BT * w.Np2, 256);
+    }
     w.total = o;
     return w;
 }

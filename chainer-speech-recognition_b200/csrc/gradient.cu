@@ -35,6 +35,14 @@ __device__ __forceinline__ void zero_row(float *__restrict__ g, int V, int lane)
     if (tail0 + lane < V) g[tail0 + lane] = 0.f;
 }
 
+// joint Gram-CTC + CTC: the plain-CTC node that carries the same symbol occurrence as Gram-CTC node j -- unigram
+// node 3i+1 <-> CTC label node 2i+1 (blank nodes are summed separately, bigram nodes have no partner)
+__device__ __forceinline__ float joint_partner(const float *e2_sm, int j, int Nb2) {
+    if (Nb2 == 0 || j % 3 != 1) return 0.f;
+    const int jc = 2 * (j / 3) + 1;
+    return jc < Nb2 ? e2_sm[jc] : 0.f;
+}
+
 // softmax * sc for 4 consecutive columns, minus the (pre-scaled) posterior of the columns the lattice emits
 __device__ __forceinline__ float4 grad4(const float4 &v, float c, float sc, unsigned word, int bit0, int pc,
                                         const float *__restrict__ post_sm) {
@@ -63,6 +71,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     const int warp = threadIdx.x >> 5;
     float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;        // [Np]   alpha*beta/P of this frame
     float *post_sm = e_sm + w.Np;                                    // [Umax] merged posterior * sc, by sorted id
+    float *e2_sm = post_sm + ((w.Umax + 3) & ~3);                    // [Np2]  joint: the same for the plain-CTC lattice
+    const UttInfo *utt2 = reinterpret_cast<const UttInfo *>(ws + w.off_utt2);
+    const float2 *av2_all = reinterpret_cast<const float2 *>(ws + w.off_av2);
+    const float2 *bv2_all = reinterpret_cast<const float2 *>(ws + w.off_bv2);
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
     const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
@@ -103,6 +115,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
             e_sm[j] = e;
             if (j % per == 0) blank_part += e;
         }
+        const int Nb2 = w.joint ? 2 * ui.Lb + 1 : 0;
+        if (w.joint) {                                                       // posteriors of the plain-CTC lattice
+            const UttInfo u2 = utt2[b];
+            const float2 *a2row = av2_all + ((size_t)b * d.T + t) * w.Np2;
+            const float2 *b2row = bv2_all + ((size_t)b * d.T + t) * w.Np2;
+            for (int j = lane; j < Nb2; j += 32) {
+                const float e = node_posterior(__ldg(a2row + j), __ldg(b2row + j + 1), u2.Ph, u2.Pl);
+                e2_sm[j] = e;
+                if ((j & 1) == 0) blank_part += e;
+            }
+        }
         blank_part = warp_sum(blank_part);
         __syncwarp();
         const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
@@ -113,10 +136,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
             for (int n = n0; n < n1; ++n) {
                 const int j = __ldg(unode + n);
                 if (j < ui.Nb) post += e_sm[j];
+                post += joint_partner(e2_sm, j, Nb2);
             }
             post_sm[u] = post * sc;
         }
         __syncwarp();
+        const float sc_soft = w.joint ? 2.f * sc : sc;                       // two losses, two softmax terms
 
         // ---- stream the row: grad = (softmax - posterior) * sc, one read and one write ----
         const unsigned *bm = bm_all + (size_t)b * w.nwords;
@@ -141,22 +166,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
                 }
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u)
-                    stg_stream4(g4 + i + 32 * u, grad4(v[u], c, sc, wd[u], ((i + 32 * u) & 7) << 2, pcw[u], post_sm));
+                    stg_stream4(g4 + i + 32 * u, grad4(v[u], c, sc_soft, wd[u], ((i + 32 * u) & 7) << 2, pcw[u], post_sm));
             }
             for (; i < n4; i += 32) {
                 const float4 v = ldg_stream4(row4 + i);
                 const int wi = i >> 3;
-                stg_stream4(g4 + i, grad4(v, c, sc, __ldg(bm + wi), (i & 7) << 2, __ldg(pc + wi), post_sm));
+                stg_stream4(g4 + i, grad4(v, c, sc_soft, __ldg(bm + wi), (i & 7) << 2, __ldg(pc + wi), post_sm));
             }
             for (int k = 4 * n4 + lane; k < d.V; k += 32) {
-                float o = ex2_approx(fmaf(row[k], LOG2E_HI, c)) * sc;
+                float o = ex2_approx(fmaf(row[k], LOG2E_HI, c)) * sc_soft;
                 const unsigned word = __ldg(bm + (k >> 5));
                 if ((word >> (k & 31)) & 1u) o -= post_sm[__ldg(pc + (k >> 5)) + __popc(word & ((1u << (k & 31)) - 1u))];
                 grow[k] = o;
             }
         } else {                                                             // unaligned rows (V % 4 != 0 ...)
             for (int k = lane; k < d.V; k += 32) {
-                float o = ex2_approx(fmaf(row[k], LOG2E_HI, c)) * sc;
+                float o = ex2_approx(fmaf(row[k], LOG2E_HI, c)) * sc_soft;
                 const unsigned word = __ldg(bm + (k >> 5));
                 if ((word >> (k & 31)) & 1u) o -= post_sm[__ldg(pc + (k >> 5)) + __popc(word & ((1u << (k & 31)) - 1u))];
                 grow[k] = o;
@@ -192,6 +217,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
     const uint32_t row_bytes = (uint32_t)d.V * 4u;
     const uint32_t ab_bytes = (uint32_t)w.Np * 8u;
+    const uint32_t ab2_bytes = w.joint ? (uint32_t)w.Np2 * 8u : 0u;      // joint: + the plain-CTC lattice's alpha/beta rows
     // extra region: [V floats of zeros][per consumer: Umax floats posterior]
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
     float *post_all = zero_row + d.V;
@@ -227,11 +253,17 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                 const int s = ring_claim(ring, myq);
                 ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0;
                 ring_publish(ring, s, myq);
-                mbar_arrive_expect_tx(&ring.full[s], row_bytes + 2 * ab_bytes);
+                mbar_arrive_expect_tx(&ring.full[s], row_bytes + 2 * ab_bytes + 2 * ab2_bytes);
                 bulk_g2s(ring.slot(s), d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b, row_bytes,
                          &ring.full[s]);
                 bulk_g2s(ring.slot(s) + row_bytes, av_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
                 bulk_g2s(ring.slot(s) + row_bytes + ab_bytes, bv_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
+                if (w.joint) {
+                    const float2 *av2 = reinterpret_cast<const float2 *>(ws + w.off_av2) + ((size_t)b * d.T + t) * w.Np2;
+                    const float2 *bv2 = reinterpret_cast<const float2 *>(ws + w.off_bv2) + ((size_t)b * d.T + t) * w.Np2;
+                    bulk_g2s(ring.slot(s) + row_bytes + 2 * ab_bytes, av2, ab2_bytes, &ring.full[s]);
+                    bulk_g2s(ring.slot(s) + row_bytes + 2 * ab_bytes + ab2_bytes, bv2, ab2_bytes, &ring.full[s]);
+                }
             }
             q += (unsigned)__popc(mask);
         }
@@ -268,6 +300,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         const float2 *a_sm = reinterpret_cast<const float2 *>(row + d.V);       // alpha row
         const float2 *b_sm = a_sm + w.Np;                                    // beta row
         float *e_sm = reinterpret_cast<float *>(row + d.V);                  // alpha*beta/P, written over the alpha row
+        const float2 *a2_sm = b_sm + w.Np;                                   // joint: plain-CTC alpha row, beta row
+        const float2 *b2_sm = a2_sm + w.Np2;
+        float *e2_sm = reinterpret_cast<float *>(const_cast<float2 *>(a2_sm));
         const UttInfo ui = utt[b];
         const float lse2 = __ldg(lse_all + (size_t)b * d.T + t);
         const float gy = gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss);
@@ -286,6 +321,19 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             if (j < ui.Nb) e_sm[j] = e;
             if (j < ui.Nb && j % per == 0) blank_part += e;
         }
+        const int Nb2 = w.joint ? 2 * ui.Lb + 1 : 0;
+        if (w.joint) {
+            const UttInfo *utt2 = reinterpret_cast<const UttInfo *>(ws + w.off_utt2);
+            const float Ph2 = utt2[b].Ph, Pl2 = utt2[b].Pl;
+            for (int j0 = 0; j0 < Nb2; j0 += 32) {
+                const int j = j0 + lane;
+                float e = 0.f;
+                if (j < Nb2) e = node_posterior(a2_sm[j], b2_sm[j + 1], Ph2, Pl2);
+                __syncwarp();                                                // e2_sm aliases the alpha row: reads first
+                if (j < Nb2) e2_sm[j] = e;
+                if (j < Nb2 && (j & 1) == 0) blank_part += e;
+            }
+        }
         blank_part = warp_sum(blank_part);
         __syncwarp();
         const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
@@ -297,18 +345,20 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             for (int n = n0; n < n1; ++n) {
                 const int j = __ldg(unode + n);
                 if (j < ui.Nb) post += e_sm[j];
+                post += joint_partner(e2_sm, j, Nb2);
             }
             post_sm[u] = post * sc;
         }
+        const float sc_soft = w.joint ? 2.f * sc : sc;                       // two losses, two softmax terms
         // softmax * sc in place
         float4 *row4 = reinterpret_cast<float4 *>(row);
 #pragma unroll 4
         for (int i = lane; i < n4; i += 32) {
             float4 v = row4[i];
-            v.x = ex2_approx(fmaf(v.x, LOG2E_HI, c)) * sc;
-            v.y = ex2_approx(fmaf(v.y, LOG2E_HI, c)) * sc;
-            v.z = ex2_approx(fmaf(v.z, LOG2E_HI, c)) * sc;
-            v.w = ex2_approx(fmaf(v.w, LOG2E_HI, c)) * sc;
+            v.x = ex2_approx(fmaf(v.x, LOG2E_HI, c)) * sc_soft;
+            v.y = ex2_approx(fmaf(v.y, LOG2E_HI, c)) * sc_soft;
+            v.z = ex2_approx(fmaf(v.z, LOG2E_HI, c)) * sc_soft;
+            v.w = ex2_approx(fmaf(v.w, LOG2E_HI, c)) * sc_soft;
             row4[i] = v;
         }
         __syncwarp();
@@ -489,7 +539,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
     unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
     const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
     const size_t extra = sizeof(float) * ((size_t)g.d.V + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
-    const RingLayout rl = make_ring(sizeof(float) * ((size_t)g.d.V + 4 * (size_t)w.Np), extra);
+    const RingLayout rl = make_ring(sizeof(float) * ((size_t)g.d.V + 4 * (size_t)w.Np + (w.joint ? 4 * (size_t)w.Np2 : 0)), extra);
     if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
         ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl) && !getenv("B200CTC_NO_TMA_K3")) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
@@ -500,7 +550,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
         gradient_ring_kernel<<<(int)ctas, kRingThreads, rl.total, stream>>>(g, w, wsb, b_major, rl);
         return cudaGetLastError();
     }
-    const int per_warp = w.Np + ((w.Umax + 3) & ~3);
+    const int per_warp = w.Np + ((w.Umax + 3) & ~3) + (w.joint ? w.Np2 : 0);
     const size_t smem = sizeof(float) * (size_t)per_warp * kWarpsPerCta;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -44,7 +44,12 @@ struct LatticeParams {
     int W;                   // warps per direction
     int S;                   // pipeline stages
     int dbg_nostore;         // timing experiment: skip the alpha/beta row stores
+    int second;              // 1: this is the plain-CTC lattice of a joint call -- no symbol-table CTAs, its own
+                             //    completion counter, and its loss is ADDED to loss_per_utt (the Gram-CTC launch,
+                             //    earlier in the stream, has written its own there) before the batch is reduced
 };
+// the view of a joint workspace that the plain-CTC lattice launch works on
+WsLayout ctc_view_of_joint(const WsLayout &w);
 int lattice_max_nodes(int kind);
 // concurrent: the kernel is going to run next to the softmax/gather kernel (fewer pipeline stages, so that a
 // lattice CTA fits beside a ring CTA); smem_out, if not NULL, receives the dynamic shared memory per CTA.

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PAD = Geo<K, GRAM>::PAD;
     const ProblemDesc &d = p.d;
-    if ((int)blockIdx.x >= 2 * d.B) {                      // ---- symbol-table CTAs (prep.cuh) ----
+    if ((int)blockIdx.x >= 2 * d.B) {                      // ---- symbol-table CTAs (prep.cuh); none in a `second` launch ----
         prep_utterance(d, p.w, p.ws, (int)blockIdx.x - 2 * d.B, reinterpret_cast<int *>(smem_raw));
         return;
     }
@@ -542,10 +542,10 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
             }
         }
         ui->Ph = Ph; ui->Pl = Pl; ui->loss = loss; ui->infeasible = feas ? 0 : 1;
-        p.loss_per_utt[b] = loss;
+        p.loss_per_utt[b] = p.second ? __ldcg(p.loss_per_utt + b) + loss : loss;     // joint: Gram-CTC loss + CTC loss
         // ---- the last CTA reduces the batch in a fixed order (gram_ctc.py:280-281) ----
         __threadfence();
-        const unsigned done = atomicAdd(&hdr->k2_done, 1u) + 1u;
+        const unsigned done = atomicAdd(p.second ? &hdr->k2b_done : &hdr->k2_done, 1u) + 1u;
         red[0] = (done == (unsigned)d.B) ? 1.f : 0.f;
     }
     __syncthreads();
@@ -567,7 +567,7 @@ cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
     // the SM's L1/shared split is chosen per kernel: ask for the maximum so that a lattice CTA and a ring CTA of the
     // softmax/gather kernel (which asks for the same) can share an SM
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<3 * p.d.B, 32 * (p.W + 1), smem, stream>>>(p);
+    kern<<<(p.second ? 2 : 3) * p.d.B, 32 * (p.W + 1), smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -582,6 +582,14 @@ cudaError_t launch_one(const LatticeParams &p, int CH, size_t smem, cudaStream_t
 constexpr size_t kLatticeSmemBudget = 224 * 1024;
 
 }  // namespace
+
+WsLayout ctc_view_of_joint(const WsLayout &w) {
+    WsLayout v = w;                 // same emission rows (v.W), header, progress counters
+    v.kind = 0; v.joint = 0;
+    v.Nmax = w.Nmax2; v.Np = w.Np2; v.boff = 1;
+    v.off_av = w.off_av2; v.off_bv = w.off_bv2; v.off_utt = w.off_utt2;
+    return v;
+}
 
 void lattice_set_debug(long long *p) { cudaMemcpyToSymbol(g_lat_dbg, &p, sizeof(p)); }
 
@@ -614,7 +622,7 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     const SmemPlan sp = plan_smem(p.w.W, W, S, PAD, CH);
     if (sp.total > kLatticeSmemBudget) { *status = 2; return cudaSuccess; }
     size_t smem = sp.total;
-    const size_t prep = prep_smem_bytes(kind, p.d.Lmax, p.w.nwords);
+    const size_t prep = p.second ? 0 : prep_smem_bytes(kind, p.d.Lmax, p.w.nwords);
     if (prep > smem) smem = prep;
     if (smem > 227 * 1024) { *status = 2; return cudaSuccess; }
     p.W = W; p.S = S;

@@ -47,7 +47,11 @@ enum {
     B200CTC_OUT_OF_MEMORY = 5       /* host entry points only -> torch.cuda.OutOfMemoryError     */
 };
 
-enum { B200CTC_KIND_CTC = 0, B200CTC_KIND_GRAM = 1 };
+/* JOINT: Gram-CTC loss + plain CTC loss of the same activations and unigram labels in one pass
+ * (run/gram_ctc/cnn/train.py:196-198, `loss = gram_ctc(...); loss += F.connectionist_temporal_classification(...)`):
+ * one softmax pass, one re-read and one gradient write instead of two of each.  loss outputs are the sums of the
+ * two losses, the gradient is the gradient of the sum. */
+enum { B200CTC_KIND_CTC = 0, B200CTC_KIND_GRAM = 1, B200CTC_KIND_JOINT = 2 };
 
 /* flags for b200ctc_forward */
 enum {

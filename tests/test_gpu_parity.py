@@ -6,7 +6,7 @@ absolute, greedy indices bit-exact.
 import numpy as np
 import pytest
 
-from util import run_cuda, run_oracle, assert_parity
+from util import run_cuda, run_oracle, assert_parity, LOSS_RTOL, GRAD_ATOL
 
 pytestmark = pytest.mark.gpu
 
@@ -62,6 +62,37 @@ def test_gram_ctc_matches_oracle(pkg, shape, trained):
     loss, grad, _ = run_cuda(pkg, prob, "gram")
     loss_ref, grad_ref, _ = run_oracle(prob, "gram")
     assert_parity(loss, grad, loss_ref, grad_ref, "gram %r" % (shape,))
+
+
+@pytest.mark.parametrize("shape", GRAM_SHAPES[:6] + [(32, 600, 8000, 60)])
+@pytest.mark.parametrize("trained", [False, True])
+def test_joint_gram_ctc_plus_ctc_matches_oracle(pkg, shape, trained):
+    """joint_ctc=True: loss = gram_ctc + ctc (run/gram_ctc/cnn/train.py:196-198) from one pass; gradient of the sum."""
+    B, T, V, L = shape
+    if B * T * V > 5e7 and trained:
+        pytest.skip("one full-size case is enough")
+    prob = synth().gram_problem(B, T, V, L, seed=4, trained=trained, n_unigram=max(3, min(119, V // 3)))
+    loss, grad, _ = run_cuda(pkg, prob, "joint")
+    loss_ref, grad_ref, _ = run_oracle(prob, "joint")
+    # two losses of magnitude |loss|: the absolute gradient bound doubles
+    assert np.all(np.abs(loss - loss_ref) <= LOSS_RTOL * np.maximum(np.abs(loss_ref), 1.0)), (shape, loss, loss_ref)
+    assert np.abs(grad - grad_ref).max() <= 2 * GRAD_ATOL, (shape, np.abs(grad - grad_ref).max())
+    # and it equals the two separate calls of this library
+    lg, gg, _ = run_cuda(pkg, prob, "gram")
+    lc, gc, _ = run_cuda(pkg, prob, "ctc")
+    assert np.allclose(loss, lg + lc, rtol=1e-6, atol=1e-6)
+    assert np.abs(grad - (gg + gc)).max() <= 2e-6
+
+
+def test_joint_reduce_mean_and_padding(pkg):
+    prob = synth().gram_problem(6, 60, 90, 9, seed=12, n_unigram=30)
+    gy = np.float32(0.75)
+    loss, grad, _ = run_cuda(pkg, prob, "joint", reduce="mean", gy=gy)
+    loss_ref, grad_ref, _ = run_oracle(prob, "joint")
+    assert abs(loss - loss_ref.mean()) <= LOSS_RTOL * abs(loss_ref.mean())
+    assert np.abs(grad - grad_ref * gy / 6).max() <= 2 * GRAD_ATOL
+    for b in range(6):
+        assert np.all(grad[prob["input_length"][b]:, b, :] == 0)
 
 
 def test_reduce_mean_and_upstream_gradient(pkg):

@@ -28,6 +28,8 @@ def test_workspace_bytes_and_status_codes(pkg):
     n = L.workspace_bytes(L.KIND_CTC, 64, 800, 3500, 80)
     assert 100e6 < n < 400e6 and n % 16 == 0
     assert L.workspace_bytes(L.KIND_GRAM, 32, 600, 8000, 60) > 0
+    # joint Gram-CTC + CTC: the Gram-CTC workspace plus the plain-CTC lattice's alpha/beta rows
+    assert L.workspace_bytes(L.KIND_JOINT, 32, 600, 8000, 60) > L.workspace_bytes(L.KIND_GRAM, 32, 600, 8000, 60)
     assert L.workspace_bytes(L.KIND_CTC, 0, 10, 5, 2) >= 0
     with pytest.raises(ValueError):
         L.workspace_bytes(7, 1, 1, 1, 1)                      # bad kind -> INVALID_ARGUMENT

@@ -33,6 +33,8 @@ def run_cuda(pkg, prob, kind, reduce="no", gy=None, as_list=False, batch_first=F
         out = pkg.connectionist_temporal_classification(xin, labels, prob["blank"], il, ll, reduce=reduce, **kw)
     else:
         big = torch.tensor(prob["bigrams"], device=dev)
+        if kind == "joint":
+            kw["joint_ctc"] = True
         out = pkg.gram_ctc(xin, labels, big, prob["blank"], il, ll, reduce=reduce, **kw)
     amax = None
     if want_argmax:
@@ -52,6 +54,10 @@ def run_cuda(pkg, prob, kind, reduce="no", gy=None, as_list=False, batch_first=F
 
 def run_oracle(prob, kind, want_argmax=False, nthreads=0):
     from oracle import c_oracle
+    if kind == "joint":        # run/gram_ctc/cnn/train.py:196-198: Gram-CTC loss + plain CTC loss on the same activations
+        lg, gg, am = run_oracle(prob, "gram", want_argmax, nthreads)
+        lc, gc, _ = run_oracle(prob, "ctc", False, nthreads)
+        return lg + lc, gg + gc, am
     r = c_oracle.run(0 if kind == "ctc" else 1, prob["x"], prob["labels"], prob.get("bigrams"),
                      prob.get("input_length"), prob.get("label_length"), prob["blank"],
                      want_grad=True, want_argmax=want_argmax, nthreads=nthreads)

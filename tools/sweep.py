@@ -37,6 +37,8 @@ def configs():
     yield "cfg1", "ctc", 8, 200, 3500, 40
     yield "cfg2", "ctc", 64, 800, 3500, 80
     yield "cfg3", "gram", 32, 600, 8000, 60
+    yield "cfg3 +ctc, 2 calls", "gram+ctc", 32, 600, 8000, 60      # joint training, run/gram_ctc/cnn/train.py:196-198
+    yield "cfg3 +ctc, joint", "joint", 32, 600, 8000, 60           # the same objective from one pass (joint_ctc=True)
     yield "cfg4", "ctc", 512, 800, 3500, 80
     for T in (200, 800, 1600, 3200):
         for V in (100, 3500):
@@ -62,7 +64,10 @@ def run(name, kind, B, T, V, L, steps=20, warmup=5):
     def fwd():
         if kind == "ctc":
             return b200ctc.connectionist_temporal_classification(x, lab, 0, il, ll, reduce="mean")
-        return b200ctc.gram_ctc(x, lab, big, 0, il, ll, reduce="mean")
+        if kind == "gram+ctc":
+            return (b200ctc.gram_ctc(x, lab, big, 0, il, ll, reduce="mean") +
+                    b200ctc.connectionist_temporal_classification(x, lab, 0, il, ll, reduce="mean"))
+        return b200ctc.gram_ctc(x, lab, big, 0, il, ll, reduce="mean", joint_ctc=(kind == "joint"))
 
     for _ in range(warmup):
         x.grad = None
@@ -80,9 +85,9 @@ def run(name, kind, B, T, V, L, steps=20, warmup=5):
     f = float(np.median([ev[k][0].elapsed_time(ev[k][1]) for k in range(steps)]))
     b = float(np.median([ev[k][1].elapsed_time(ev[k][2]) for k in range(steps)]))
     s = ev[0][0].elapsed_time(ev[-1][2]) / steps
-    nbytes = 8.0 * V * float(in_len.sum()) + 4.0 * V * B * T
+    nbytes = 8.0 * V * float(in_len.sum()) + 4.0 * V * B * T          # one loss; the joint objective needs no more
     frac = nbytes / (s * 1e-3) / 1e9 / peak_gbs()
-    print("%-18s %-4s B=%-3d T=%-4d V=%-4d L=%-3d  fwd %7.3f ms  bwd %7.3f ms  step %7.3f ms  %8.1f M padded frames/s  "
+    print("%-20s %-8s B=%-3d T=%-4d V=%-4d L=%-3d  fwd %7.3f ms  bwd %7.3f ms  step %7.3f ms  %8.1f M padded frames/s  "
           "%5.1f %% of HBM roofline  loss %.4f" % (name, kind, B, T, V, L, f, b, s, B * T / s / 1e3, 100 * frac, float(loss.detach())),
           flush=True)
     del x
