@@ -102,11 +102,21 @@ int validate(int kind, int B, int T, int V, int Lmax, int blank, bool need_blank
 
 }  // namespace
 
-namespace b200ctc { void lattice_set_debug(long long *p); }
+namespace b200ctc {
+void lattice_set_debug(long long *p);
+void lattice_set_timeline(long long *p);
+void softmax_set_timeline(long long *p);
+void gradient_set_timeline(long long *p);
+}
 
 extern "C" {
 
 void b200ctc_debug_lattice(long long *p) { b200ctc::lattice_set_debug(p); }
+/* profiling hook (tools/step_timeline.py): 8 device long longs = [start, end] globaltimer ns of the softmax/gather
+ * kernel, the alpha CTAs, the beta CTAs and the gradient kernel; caller presets starts to LLONG_MAX and ends to 0 */
+void b200ctc_debug_timeline(long long *p) {
+    b200ctc::softmax_set_timeline(p); b200ctc::lattice_set_timeline(p); b200ctc::gradient_set_timeline(p);
+}
 
 int b200ctc_version(void) { return B200CTC_VERSION; }
 

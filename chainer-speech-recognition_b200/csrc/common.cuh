@@ -149,6 +149,19 @@ __device__ __forceinline__ float node_posterior(float2 a, float2 b, float Ph, fl
     return (a.x * b.x) * ex2_approx((a.y + b.y) - Ph) * Pinv;
 }
 
+// ---- timeline hook (tools/step_timeline.py): first CTA start / last CTA end of a kernel, in globaltimer ns ----
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void timeline_mark(long long *tl, int kernel_slot, bool end) {
+    if (tl && threadIdx.x == 0) {
+        if (end) atomicMax(tl + 2 * kernel_slot + 1, global_ns());
+        else atomicMin(tl + 2 * kernel_slot, global_ns());
+    }
+}
+
 // ---- frame progress between the softmax/gather kernel and a concurrently running lattice kernel ----
 // Producer: called by ONE lane after a __syncwarp() that follows the warp's stores of the frame's emission row.
 __device__ __forceinline__ void signal_frame_done(unsigned char *ws, const WsLayout &w, int b, int t, bool relaxed = false) {

@@ -18,6 +18,9 @@
 
 namespace b200ctc {
 
+__device__ long long *g_tl_k3 = nullptr;      // timeline hook, see common.cuh
+void gradient_set_timeline(long long *p) { cudaMemcpyToSymbol(g_tl_k3, &p, sizeof(p)); }
+
 namespace {
 
 constexpr int kWarpsPerCta = 8;
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const uint32_t ab_bytes = (uint32_t)w.Np * 8u;
     const uint32_t ab2_bytes = w.joint ? (uint32_t)w.Np2 * 8u : 0u;      // joint: + the plain-CTC lattice's alpha/beta rows
     // extra region: [V floats of zeros][per consumer: Umax floats posterior]
+    timeline_mark(g_tl_k3, 3, false);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
     float *post_all = zero_row + d.V;
     for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
@@ -269,6 +273,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         }
         ring_stop(ring, q, lane);
         bulk_wait_all<0>();
+        timeline_mark(g_tl_k3, 3, true);
         // re-arm the queue for a possible second backward over the same workspace
         if (lane == 0) {
             __threadfence();
@@ -547,6 +552,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
         if (ctas < 1) ctas = 1;
         cudaError_t e = cudaFuncSetAttribute(gradient_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(gradient_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         gradient_ring_kernel<<<(int)ctas, kRingThreads, rl.total, stream>>>(g, w, wsb, b_major, rl);
         return cudaGetLastError();
     }

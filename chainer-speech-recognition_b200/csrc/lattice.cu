@@ -52,6 +52,8 @@
 
 namespace b200ctc {
 
+__device__ long long *g_tl_k2 = nullptr;      // timeline hook, see common.cuh
+void lattice_set_timeline(long long *p) { cudaMemcpyToSymbol(g_tl_k2, &p, sizeof(p)); }
 __device__ long long *g_lat_dbg = nullptr;   // profiling hook (tools/lattice_timeline.py): per-warp cycle breakdown
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
@@ -448,6 +450,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
     }
     const int b = blockIdx.x >> 1;
     const int dir = blockIdx.x & 1;                        // 0: alpha, 1: beta
+    timeline_mark(g_tl_k2, 1 + dir, false);
     const int W = p.W, S = p.S;
     // warps [0,W): recursion, warp W: I/O.  Read through a shuffle so that the compiler knows the value is
     // warp-uniform: every branch below is then a uniform branch, and the recursion's shuffles need no divergence
@@ -502,7 +505,11 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
             else          run_direction<K, GRAM, true, CH>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
         }
     }
-    if (dir == 1) return;                                  // the beta CTA is done
+    if (dir == 1) {                                        // the beta CTA is done
+        __syncthreads();
+        timeline_mark(g_tl_k2, 2, true);
+        return;
+    }
     __threadfence_block();
     __syncthreads();
 
@@ -557,6 +564,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) *p.loss_reduced = (float)(acc * (double)p.loss_scale);
     }
+    timeline_mark(g_tl_k2, 1, true);
 }
 
 template <int K, bool GRAM, int MAXW, int CH>

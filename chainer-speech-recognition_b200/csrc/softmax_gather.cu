@@ -15,6 +15,9 @@
 
 namespace b200ctc {
 
+__device__ long long *g_tl_k1 = nullptr;      // timeline hook, see common.cuh
+void softmax_set_timeline(long long *p) { cudaMemcpyToSymbol(g_tl_k1, &p, sizeof(p)); }
+
 namespace {
 
 constexpr int kWarpsPerCta = 8;
@@ -28,6 +31,9 @@ constexpr int kUnroll = 4;
 // one, its alpha CTAs consume frames in ascending and its beta CTAs in descending order, so each direction finds
 // the rows it needs next already written (common.cuh, signal_frame_done).  Independent of the memory layout: a
 // row is one contiguous 4*V-byte read either way.
+// (Tried and dropped: walking every utterance from ITS two ends, in groups ordered by decreasing length so that the
+// rows produced last belong to the shortest utterances.  The exposed lattice tail shrank from 33 to 27 us, but this
+// kernel lost 8 us to the scattered row order -- no net gain, tools/step_timeline.py.)
 __device__ __forceinline__ void frame_of_ticket(unsigned f, int B, int T, bool two_ended, int &b, int &t) {
     const int slice = (int)(f / (unsigned)B);
     b = (int)(f % (unsigned)B);
@@ -314,6 +320,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
     const uint32_t row_bytes = (uint32_t)d.V * 4u;
+    timeline_mark(g_tl_k1, 0, false);
     SignalFifo *fifo = reinterpret_cast<SignalFifo *>(smem_raw + rl.off_extra);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra + kFifoBytes);      // GRAD only: V zeros for padded frames
     const bool signalling = (d.progress & 1) != 0;
@@ -363,6 +370,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
         }
         ring_stop(ring, q, lane);
         if (GRAD) bulk_wait_all<0>();
+        timeline_mark(g_tl_k1, 0, true);
         return;
     }
 
