@@ -63,9 +63,9 @@ __device__ __forceinline__ void fold4(RowStat &st, const float4 &v, int idx) {
         st.s *= ex2_approx((st.m - cm) * LOG2E_HI);
         st.m = cm;
     }
-    const float c = -st.m * LOG2E_HI;
-    st.s += ex2_approx(fmaf(v.x, LOG2E_HI, c)) + ex2_approx(fmaf(v.y, LOG2E_HI, c)) +
-            ex2_approx(fmaf(v.z, LOG2E_HI, c)) + ex2_approx(fmaf(v.w, LOG2E_HI, c));
+    const float c = st.m == -INFINITY ? 0.f : -st.m * LOG2E_HI;        // nothing finite seen yet: every term is 2^-inf = 0
+    st.s += (ex2_approx(fmaf(v.x, LOG2E_HI, c)) + ex2_approx(fmaf(v.y, LOG2E_HI, c))) +
+            (ex2_approx(fmaf(v.z, LOG2E_HI, c)) + ex2_approx(fmaf(v.w, LOG2E_HI, c)));
     fold<ARGMAX>(st, v.x, idx);
     fold<ARGMAX>(st, v.y, idx + 1);
     fold<ARGMAX>(st, v.z, idx + 2);
@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
 // shared-memory FIFO (CTA-scope ordering, cheap) and one extra warp drains all FIFOs with ONE GPU-scope fence per
 // sweep, then bumps the progress counters (the __syncthreads / thread 0 fences / atomic pattern of a grid barrier).
 constexpr int kK1Threads = kRingThreads + 32;          // producer + consumers + signal warp
+constexpr int kGatherRegs = 4;                         // emitted ids per lane on the early-release path (<= 128 columns)
 constexpr int kFifoDepth = 4;
 struct SignalFifo {
     int2 entry[kRingConsumers][kFifoDepth];            // (b, t); b < 0 = this consumer is done
@@ -390,17 +391,45 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
         }
         const float *row = reinterpret_cast<const float *>(ring.slot(s));
         const float4 *row4 = reinterpret_cast<const float4 *>(row);
-        // pass 1: maximum (and greedy index)
+        bool released = false;                  // the slot has already been handed back (early, see the gather)
+        // Emitted ids of this lane's columns, requested now so that their latency hides behind the row scan:
+        // column 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams (gram_ctc.py:24-32, :155)
+        int Lb = 0, ncol = 0;
+        const int32_t *lab = d.labels + (size_t)m.b * d.Lmax;
+        const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)m.b * d.Lmax : nullptr;
+        auto symbol_of = [&](int cidx) {
+            if (cidx == 0) return d.blank;
+            if (cidx <= d.Lmax) return (cidx - 1 < Lb) ? __ldg(lab + cidx - 1) : -1;
+            return __ldg(big + cidx - 1 - d.Lmax);
+        };
+        int syms[kGatherRegs];
+        bool early = false;
+        if (m.kind == 0) {
+            Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
+            Lb = max(0, min(Lb, d.Lmax));
+            ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
+            early = !GRAD && ncol <= 32 * kGatherRegs;
+            if (early) {
+#pragma unroll
+                for (int k = 0; k < kGatherRegs; ++k) syms[k] = (lane + 32 * k < ncol) ? symbol_of(lane + 32 * k) : -1;
+            }
+        }
+        // one pass over the staged row: per-lane online (max, sum of 2^((x - max) * log2 e)) and greedy index; a
+        // padded frame (argmax only) skips the exponentials
         RowStat st;
         st.m = -INFINITY; st.s = 0.f; st.bv = -INFINITY; st.bi = 0x7fffffff;
+        if (m.kind == 0) {
 #pragma unroll 4
-        for (int i = lane; i < n4; i += 32) {
-            const float4 v = row4[i];
-            st.m = fmaxf(st.m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-            fold<ARGMAX>(st, v.x, 4 * i);
-            fold<ARGMAX>(st, v.y, 4 * i + 1);
-            fold<ARGMAX>(st, v.z, 4 * i + 2);
-            fold<ARGMAX>(st, v.w, 4 * i + 3);
+            for (int i = lane; i < n4; i += 32) fold4<ARGMAX>(st, row4[i], 4 * i);
+        } else {
+#pragma unroll 4
+            for (int i = lane; i < n4; i += 32) {
+                const float4 v = row4[i];
+                fold<ARGMAX>(st, v.x, 4 * i);
+                fold<ARGMAX>(st, v.y, 4 * i + 1);
+                fold<ARGMAX>(st, v.z, 4 * i + 2);
+                fold<ARGMAX>(st, v.w, 4 * i + 3);
+            }
         }
         if (ARGMAX) {
             float bv = st.bv; int bi = st.bi;
@@ -418,34 +447,38 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
         }
         if (m.kind == 0) {
             const float mx = warp_max(st.m);
-            // pass 2: sum of 2^((x - max) * log2 e)
-            const float c = -mx * LOG2E_HI;
-            float sum = 0.f;
-#pragma unroll 4
-            for (int i = lane; i < n4; i += 32) {
-                const float4 v = row4[i];
-                sum += (ex2_approx(fmaf(v.x, LOG2E_HI, c)) + ex2_approx(fmaf(v.y, LOG2E_HI, c))) +
-                       (ex2_approx(fmaf(v.z, LOG2E_HI, c)) + ex2_approx(fmaf(v.w, LOG2E_HI, c)));
-            }
+            float sum = st.m == -INFINITY ? 0.f : st.s * ex2_approx((st.m - mx) * LOG2E_HI);
             sum = warp_sum(sum);
             float la, lb;
             split_lse2(mx, sum, la, lb);
             if (lane == 0) lse_out[(size_t)m.b * d.T + m.t] = la + lb;
-            // gather from the staged row: column 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams
-            int Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
-            Lb = max(0, min(Lb, d.Lmax));
             float2 *lprow = lp_out + ((size_t)m.b * d.T + m.t) * w.W;
-            const int32_t *lab = d.labels + (size_t)m.b * d.Lmax;
-            const int32_t *big = d.kind == 1 ? d.bigrams + (size_t)m.b * d.Lmax : nullptr;
-            const int ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
-            for (int cidx = lane; cidx < ncol; cidx += 32) {
-                int sym;
-                if (cidx == 0) sym = d.blank;
-                else if (cidx <= d.Lmax) sym = (cidx - 1 < Lb) ? __ldg(lab + cidx - 1) : -1;
-                else sym = __ldg(big + cidx - 1 - d.Lmax);
-                float2 v = make_float2(0.f, SENT);
-                if (sym >= 0 && sym < d.V) v = emission_pair(row[sym], la, lb);
-                lprow[cidx] = v;
+            if (early) {
+                // The usual case.  Only the activations at the emitted ids are still needed from the row: fetch them,
+                // hand the slot back to the producer, and only then do the arithmetic and the global stores.  A slot
+                // held by a consumer is a row NOT in flight from HBM, and the ring is what covers the memory latency.
+                float xv[kGatherRegs];
+                bool ok[kGatherRegs];
+#pragma unroll
+                for (int k = 0; k < kGatherRegs; ++k) {
+                    ok[k] = syms[k] >= 0 && syms[k] < d.V;
+                    xv[k] = ok[k] ? row[syms[k]] : 0.f;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ring.empty[s]);
+                released = true;
+#pragma unroll
+                for (int k = 0; k < kGatherRegs; ++k) {
+                    const int cidx = lane + 32 * k;
+                    if (cidx < ncol) lprow[cidx] = ok[k] ? emission_pair(xv[k], la, lb) : make_float2(0.f, SENT);
+                }
+            } else {
+                for (int cidx = lane; cidx < ncol; cidx += 32) {
+                    const int sym = symbol_of(cidx);
+                    float2 v = make_float2(0.f, SENT);
+                    if (sym >= 0 && sym < d.V) v = emission_pair(row[sym], la, lb);
+                    lprow[cidx] = v;
+                }
             }
             __syncwarp();
             if (signalling && lane == 0) fifo_push(fifo, warp - 1, pushed, m.b, m.t);
@@ -473,7 +506,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ring.empty[s]);
+        if (lane == 0 && !released) mbar_arrive(&ring.empty[s]);
     }
     if (signalling && lane == 0) fifo_push(fifo, warp - 1, pushed, -1, 0);
     if (GRAD && lane == 0) bulk_wait_all<0>();
