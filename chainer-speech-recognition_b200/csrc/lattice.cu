@@ -65,6 +65,7 @@ namespace {
 // chunk), and a stage is CH rows.
 constexpr int kMaxStages = 24;
 constexpr int kMaxWarpsPerDir = 16;
+constexpr int kGenericMaxWarps = 8;   // Gram-CTC lattices of up to 256 nodes run one node per lane (K = 1)
 
 // Reversed direction: q <-> j = Nb - 1 - q, so the reversed CTC lattice has the same shape as the forward one
 // (even q = blank, odd q = label) and a lane's two nodes are j-1 (label), j (blank) with j even.  The beta rows
@@ -82,6 +83,8 @@ struct LaneState {
     int ci[K];               // column of each node's symbol in the emission row (0 = blank)
     float openoff[K];        // 0 when the "ids differ" edge into slot r is open, SENT when it is closed
     uint32_t valid;          // bit r: node index < Nb
+    int dk[3];               // K == 1 only (one node per lane, its type known at run time): how many lanes back the
+                             // three predecessors besides the node itself sit; 0 = no such edge
 };
 
 // shared-memory view of the pipeline (32-bit shared-space addresses: no generic-pointer conversion inside the
@@ -233,6 +236,36 @@ template <int K, bool GRAM, bool REV>
 __device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, bool has_next,
                                              uint32_t bin, uint32_t bout, uint32_t lprow, float2 *out) {
     constexpr int PAD = Geo<K, GRAM>::PAD;
+    if constexpr (K == 1) {
+        // One node per lane: the Gram-CTC lattice of a usual utterance (181 nodes at L = 60) then spreads over six
+        // warps instead of two, and a step is ~50 instructions instead of ~120.  The node types alternate along the
+        // lanes, so the predecessors are fetched with per-lane source lanes (SHFL.IDX); the first lanes of a warp
+        // take them from the previous warp's boundary record.
+        const float m0 = st.m[0], e0 = st.e[0];
+        float vm[3], ve[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int src = lane - st.dk[k];
+            const float sm_ = __shfl_sync(0xffffffffu, m0, src & 31);
+            const float se_ = __shfl_sync(0xffffffffu, e0, src & 31);
+            const float2 bv = lds_f2(bin + 8u * (uint32_t)max(0, min(PAD - 1, PAD + src)));
+            const bool edge = src < 0;
+            vm[k] = edge ? bv.x : sm_;
+            ve[k] = st.dk[k] == 0 ? SENT : (edge ? bv.y : se_);
+        }
+        if (has_next && lane >= 32 - PAD) sts_f2(bout + 8u * (uint32_t)(lane - (32 - PAD)), m0, e0);
+        const float E = fmaxf(fmaxf(e0, ve[0]), fmaxf(ve[1], ve[2]));
+        float sum = m0 * pow2_nonpos(e0 - E);
+        sum = fmaf(vm[0], pow2_nonpos(ve[0] - E), sum);
+        sum = fmaf(vm[1], pow2_nonpos(ve[1] - E), sum);
+        sum = fmaf(vm[2], pow2_nonpos(ve[2] - E), sum);
+        const float2 em = lds_f2(lprow + 8u * (uint32_t)st.ci[0]);
+        const float nm = sum * em.x, ne = E + em.y;
+        st.m[0] = nm;
+        st.e[0] = ne;
+        if (st.valid & 1u) *out = REV ? make_float2(sum, E) : make_float2(nm, ne);
+        return;
+    }
     float xm[Geo<K, GRAM>::EXT], xe[Geo<K, GRAM>::EXT];
     gather_ext<K, GRAM>(st, xm, xe, lane, bin);
     // leave my last PAD nodes' old values for warp w+1 (predicated stores, no branch)
@@ -412,6 +445,19 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const ProblemD
         }
         st.ci[r] = ci;
         st.openoff[r] = open ? 0.f : SENT;
+        if constexpr (K == 1 && GRAM) {
+            // predecessor table of the header comment, as lanes back; the starred edge only when `open`
+            const int t3 = (K * gl + r) % 3;             // position type in this direction's coordinates
+            if (!rev) {
+                st.dk[0] = t3 == 2 ? 5 : 1;
+                st.dk[1] = t3 == 2 ? 7 : 2;
+                st.dk[2] = t3 == 0 ? 0 : (open ? (t3 == 1 ? 3 : 6) : 0);
+            } else {
+                st.dk[0] = t3 == 2 ? 2 : 1;
+                st.dk[1] = t3 == 0 ? 5 : (t3 == 1 ? 2 : 7);
+                st.dk[2] = t3 == 0 ? 0 : (open ? (t3 == 1 ? 6 : 3) : 0);
+            }
+        }
     }
 }
 
@@ -612,7 +658,8 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     // lattice would not fit 16 warps
     int K;
     if (kind == 0) K = (Nmax <= 32 * 2 * kMaxWarpsPerDir) ? 2 : 4;
-    else K = (Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6;
+    else K = (Nmax <= 32 * kGenericMaxWarps) ? 1 : ((Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6);
+    if (kind == 1 && getenv("B200CTC_GRAM_K3") && K == 1) K = 3;                  // experiment knob
     const int W = (Nmax + 32 * K - 1) / (32 * K);
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
@@ -623,7 +670,10 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     const int want = W + ahead < kMaxStages ? W + ahead : kMaxStages;
     int CH = W <= 7 ? 16 : 8;
     const int CHmin = W <= 3 ? 16 : (W <= 7 ? 8 : 4);
-    while (CH > CHmin && plan_smem(p.w.W, W, want, PAD, CH).total > kLatticeSmemBudget) CH >>= 1;
+    // next to the softmax/gather kernel every byte here is taken from that kernel's ring: stay below 64 KB if a
+    // shorter chunk allows it
+    const size_t budget = concurrent ? (size_t)64 * 1024 : kLatticeSmemBudget;
+    while (CH > CHmin && plan_smem(p.w.W, W, want, PAD, CH).total > budget) CH >>= 1;
     int S = want;
     if (const char *e = getenv("B200CTC_LAT_STAGES")) S = atoi(e);               // experiment knob
     while (S > 2 && plan_smem(p.w.W, W, S, PAD, CH).total > kLatticeSmemBudget) --S;
@@ -638,6 +688,7 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     if (smem_out) *smem_out = smem;
     if (!launch) return cudaSuccess;
     if (kind == 0) return K == 2 ? launch_one<2, false>(p, CH, smem, stream) : launch_one<4, false>(p, CH, smem, stream);
+    if (K == 1) return launch_one<1, true>(p, CH, smem, stream);
     return K == 3 ? launch_one<3, true>(p, CH, smem, stream) : launch_one<6, true>(p, CH, smem, stream);
 }
 

@@ -10,13 +10,22 @@ import b200ctc
 synth = importlib.import_module("chainer-speech-recognition_b200.synth")
 lib = b200ctc._lib.load()
 lib.b200ctc_debug_timeline.argtypes = [ctypes.c_void_p]
-prob = synth.ctc_problem(64, 800, 3500, 80, seed=0)
+kind = sys.argv[1] if len(sys.argv) > 1 else "ctc"          # ctc | gram | joint  [B T V L]
+dims = [int(v) for v in sys.argv[2:6]] if len(sys.argv) >= 6 else None
+if kind == "ctc":
+    prob = synth.ctc_problem(*(dims or [64, 800, 3500, 80]), seed=0)
+else:
+    prob = synth.gram_problem(*(dims or [32, 600, 8000, 60]), seed=0)
 dev = torch.device("cuda:0")
 x = torch.tensor(prob["x"], device=dev, requires_grad=True)
 lab = torch.tensor(prob["labels"], device=dev); il = torch.tensor(prob["input_length"], device=dev); ll = torch.tensor(prob["label_length"], device=dev)
+big = torch.tensor(prob["bigrams"], device=dev) if kind != "ctc" else None
 def step():
     x.grad = None
-    b200ctc.ctc(x, lab, 0, il, ll, reduce="mean").backward()
+    if kind == "ctc":
+        b200ctc.ctc(x, lab, 0, il, ll, reduce="mean").backward()
+    else:
+        b200ctc.gram_ctc(x, lab, big, 0, il, ll, reduce="mean", joint_ctc=(kind == "joint")).backward()
 for _ in range(5): step()
 torch.cuda.synchronize()
 BIG = np.iinfo(np.int64).max
