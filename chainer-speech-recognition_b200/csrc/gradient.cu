@@ -38,23 +38,6 @@ __device__ __forceinline__ void zero_row(float *__restrict__ g, int V, int lane)
     if (tail0 + lane < V) g[tail0 + lane] = 0.f;
 }
 
-// Frame-local normaliser.  With the reference's beta convention (beta_t excludes the emission at t, gram_ctc.py:171-175)
-// sum_j alpha_t[j] * beta_t[j] = P at EVERY frame, so a frame's posteriors can be normalised by the frame's own sum
-// instead of the utterance total read off the end of the alpha recursion: the gradient of a frame then depends on
-// nothing but that frame's alpha and beta rows (and is normalised to rounding: the posteriors of a frame sum to 1).
-// a, b: the frame's alpha and beta rows ((m, e) pairs; b already shifted by WsLayout::boff), n nodes.  Returns
-// (Ph, Pinv) for node_posterior(): sum = 2^Ph / Pinv.  All-zero rows (infeasible alignment) give Pinv = 0.
-__device__ __forceinline__ void frame_normaliser(const float2 *a, const float2 *b, int n, int lane, float &Ph, float &Pinv) {
-    float E = 2.f * SENT;
-    for (int j = lane; j < n; j += 32) E = fmaxf(E, a[j].y + b[j].y);
-    E = warp_max(E);
-    float S = 0.f;
-    for (int j = lane; j < n; j += 32) S += (a[j].x * b[j].x) * ex2_approx((a[j].y + b[j].y) - E);
-    S = warp_sum(S);
-    Ph = E;
-    Pinv = S > 0.f ? 1.f / S : (S == 0.f ? 0.f : S);          // a NaN stays a NaN
-}
-
 // joint Gram-CTC + CTC: the plain-CTC node that carries the same symbol occurrence as Gram-CTC node j -- unigram
 // node 3i+1 <-> CTC label node 2i+1 (blank nodes are summed separately, bigram nodes have no partner)
 __device__ __forceinline__ float joint_partner(const float *e2_sm, int j, int Nb2) {
@@ -92,6 +75,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;        // [Np]   alpha*beta/P of this frame
     float *post_sm = e_sm + w.Np;                                    // [Umax] merged posterior * sc, by sorted id
     float *e2_sm = post_sm + ((w.Umax + 3) & ~3);                    // [Np2]  joint: the same for the plain-CTC lattice
+    const UttInfo *utt2 = reinterpret_cast<const UttInfo *>(ws + w.off_utt2);
     const float2 *av2_all = reinterpret_cast<const float2 *>(ws + w.off_av2);
     const float2 *bv2_all = reinterpret_cast<const float2 *>(ws + w.off_bv2);
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
@@ -128,22 +112,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         const float2 *arow = av_all + ((size_t)b * d.T + t) * w.Np;
         const float2 *brow = bv_all + ((size_t)b * d.T + t) * w.Np;
         float blank_part = 0.f;
-        float Ph, Pinv;
-        frame_normaliser(arow, brow + w.boff, ui.Nb, lane, Ph, Pinv);
         for (int j = lane; j < ui.Nb; j += 32) {
             const float2 a = __ldg(arow + j), bb = __ldg(brow + j + w.boff);
-            const float e = node_posterior(a, bb, Ph, Pinv);
+            const float e = node_posterior(a, bb, ui.Ph, ui.Pl);
             e_sm[j] = e;
             if (j % per == 0) blank_part += e;
         }
         const int Nb2 = w.joint ? 2 * ui.Lb + 1 : 0;
         if (w.joint) {                                                       // posteriors of the plain-CTC lattice
+            const UttInfo u2 = utt2[b];
             const float2 *a2row = av2_all + ((size_t)b * d.T + t) * w.Np2;
             const float2 *b2row = bv2_all + ((size_t)b * d.T + t) * w.Np2;
-            float Ph2, Pinv2;
-            frame_normaliser(a2row, b2row + 1, Nb2, lane, Ph2, Pinv2);
             for (int j = lane; j < Nb2; j += 32) {
-                const float e = node_posterior(__ldg(a2row + j), __ldg(b2row + j + 1), Ph2, Pinv2);
+                const float e = node_posterior(__ldg(a2row + j), __ldg(b2row + j + 1), u2.Ph, u2.Pl);
                 e2_sm[j] = e;
                 if ((j & 1) == 0) blank_part += e;
             }
@@ -334,14 +315,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         const float c = -lse2;
 
         float blank_part = 0.f;
-        float Ph, Pinv;
-        frame_normaliser(a_sm, b_sm + w.boff, ui.Nb, lane, Ph, Pinv);
         for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
             const int j = j0 + lane;
             float e = 0.f;
             if (j < ui.Nb) {
                 const float2 a = a_sm[j], bb = b_sm[j + w.boff];
-                e = node_posterior(a, bb, Ph, Pinv);
+                e = node_posterior(a, bb, ui.Ph, ui.Pl);
             }
             __syncwarp();                                                    // e_sm aliases the alpha row: reads first
             if (j < ui.Nb) e_sm[j] = e;
@@ -349,8 +328,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         }
         const int Nb2 = w.joint ? 2 * ui.Lb + 1 : 0;
         if (w.joint) {
-            float Ph2, Pl2;
-            frame_normaliser(a2_sm, b2_sm + 1, Nb2, lane, Ph2, Pl2);
+            const UttInfo *utt2 = reinterpret_cast<const UttInfo *>(ws + w.off_utt2);
+            const float Ph2 = utt2[b].Ph, Pl2 = utt2[b].Pl;
             for (int j0 = 0; j0 < Nb2; j0 += 32) {
                 const int j = j0 + lane;
                 float e = 0.f;
@@ -478,21 +457,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(Grad
             auto finish = [&](int t, const PatchLoads &L) {
                 float *grow = gbase + (int64_t)t * gp.gstride_t;
                 float blank_part = 0.f;
-                float Ph = 2.f * SENT, Pinv = 0.f;                             // frame-local normaliser (see above)
-#pragma unroll
-                for (int k = 0; k < kPatchNodeIters; ++k)
-                    if (lane + 32 * k < ui.Nb) Ph = fmaxf(Ph, L.av[k].y + L.bv[k].y);
-                Ph = warp_max(Ph);
-#pragma unroll
-                for (int k = 0; k < kPatchNodeIters; ++k)
-                    if (lane + 32 * k < ui.Nb) Pinv += (L.av[k].x * L.bv[k].x) * ex2_approx((L.av[k].y + L.bv[k].y) - Ph);
-                Pinv = warp_sum(Pinv);
-                Pinv = Pinv > 0.f ? 1.f / Pinv : (Pinv == 0.f ? 0.f : Pinv);
 #pragma unroll
                 for (int k = 0; k < kPatchNodeIters; ++k) {
                     const int j = lane + 32 * k;
                     if (j < ui.Nb) {
-                        const float e = node_posterior(L.av[k], L.bv[k], Ph, Pinv);
+                        const float e = node_posterior(L.av[k], L.bv[k], ui.Ph, ui.Pl);
                         e_sm[j] = e;                                            // alpha*beta/P
                         if (j % per == 0) blank_part += e;
                     }
@@ -524,11 +493,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(Grad
                 const float2 *arow = arow0 + (size_t)t * w.Np, *brow = brow0 + (size_t)t * w.Np;
                 float *grow = gbase + (int64_t)t * gp.gstride_t;
                 float blank_part = 0.f;
-                float Ph, Pinv;
-                frame_normaliser(arow, brow + w.boff, ui.Nb, lane, Ph, Pinv);
                 for (int j = lane; j < ui.Nb; j += 32) {
                     const float2 a = __ldg(arow + j), bb = __ldg(brow + j + w.boff);
-                    const float e = node_posterior(a, bb, Ph, Pinv);
+                    const float e = node_posterior(a, bb, ui.Ph, ui.Pl);
                     e_sm[j] = e;
                     if (j % per == 0) blank_part += e;
                 }
