@@ -300,3 +300,25 @@ def test_pipelined_forward_backward_equals_separate_calls(pkg, kind, monkeypatch
         monkeypatch.setenv("B200CTC_FUSED", "0")
         d = run_cuda(pkg, prob, kind, reduce="mean")
         assert np.array_equal(c[1], d[1])
+
+
+@pytest.mark.parametrize("kind", ["ctc", "gram", "joint"])
+def test_large_batch_runs_the_kernels_back_to_back(pkg, kind):
+    """B >= #SMs: the lattice kernel is not launched next to the softmax/gather kernel (api.cu) -- same results."""
+    B, T, V, L = 160, 40, 64, 6
+    s = synth()
+    prob = s.ctc_problem(B, T, V, L, seed=31) if kind == "ctc" else s.gram_problem(B, T, V, L, seed=31, n_unigram=20)
+    loss, grad, _ = run_cuda(pkg, prob, kind)
+    loss_ref, grad_ref, _ = run_oracle(prob, kind)
+    assert np.all(np.abs(loss - loss_ref) <= LOSS_RTOL * np.maximum(np.abs(loss_ref), 1.0))
+    assert np.abs(grad - grad_ref).max() <= (2 if kind == "joint" else 1) * GRAD_ATOL
+
+
+def test_concurrent_and_serial_forward_agree_bitwise(pkg, monkeypatch):
+    """The lattice kernel next to the softmax/gather kernel (default) vs behind it (B200CTC_NO_CONCURRENT): the same
+    arithmetic in the same order per utterance, so identical bits."""
+    prob = synth().ctc_problem(24, 300, 512, 30, seed=33)
+    a = run_cuda(pkg, prob, "ctc")
+    monkeypatch.setenv("B200CTC_NO_CONCURRENT", "1")
+    b = run_cuda(pkg, prob, "ctc")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
