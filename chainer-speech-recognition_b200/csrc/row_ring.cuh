@@ -23,7 +23,7 @@ constexpr int kRingThreads = 32 * (1 + kRingConsumers);
 constexpr int kTicketBatch = 8;       // frames per ticket; one producer lane per frame of the batch
 constexpr int kMinSlots = 4;
 constexpr int kMaxSlots = 16;
-constexpr size_t kRingSmemBudget = 200 * 1024;
+constexpr size_t kRingSmemBudget = 224 * 1024;
 
 struct RowMeta {
     int b, t;
