@@ -277,6 +277,10 @@ __device__ __forceinline__ void bulk_wait_all() {
 }
 // order generic-proxy accesses against async-proxy (bulk copy) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the same, restricted to one state space: shared memory written by this thread and then read by a bulk store, or
+// global memory written with ordinary stores and then read by a bulk load
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
     float4 v;

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
     float *post_all = zero_row + d.V;
     for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
-    fence_proxy_async();
+    fence_proxy_async_smem();
     __syncthreads();
 
     if (warp == 0) {
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         }
         __syncwarp();
         for (int u = lane; u < ui.Ub; u += 32) row[__ldg(usym + u)] -= post_sm[u];     // distinct columns (:290)
-        fence_proxy_async();
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
             bulk_s2g(gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b, row, row_bytes);

@@ -318,7 +318,7 @@ __device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c,
             }
         }
         if (lane == 0) {
-            fence_proxy_async();                              // rows written through the generic proxy, read by the copy engine
+            fence_proxy_async_global();                       // rows written through the generic proxy, read by the copy engine
             mbar_arrive_expect_tx(&pp.full[stage], row_bytes * cnt);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              pp.lp + (uint32_t)stage * stage_bytes),

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     if (threadIdx.x < kRingConsumers) { fifo->head[threadIdx.x] = 0u; fifo->tail[threadIdx.x] = 0u; }
     if (GRAD) {
         for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
-        fence_proxy_async();
+        fence_proxy_async_smem();
     }
     __syncthreads();
     if (warp == kRingConsumers + 1) {                     // ===== signal warp =====
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
                     v.w = ex2_approx(fmaf(v.w, LOG2E_HI, cc)) * go.scale;
                     w4[i] = v;
                 }
-                fence_proxy_async();
+                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     bulk_s2g(go.grad + (int64_t)m.t * go.gstride_t + (int64_t)m.b * go.gstride_b, ring.slot(s), row_bytes);
