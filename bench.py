@@ -155,7 +155,7 @@ def cpu_baseline(prob, threads, budget_s=12.0):
     return B * T * reps / dt, dt, reps
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     """--impl reference: the CPU implementation alone, all host threads, rank 0 only."""
     if rank != 0:
         return
@@ -173,7 +173,7 @@ def run_reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     value = sample_b * W["T"] * args.steps / dt
     sample = "oracle C port (oracle/ctc_oracle.c, float64, OpenMP x%d), all %d utterances of the workload per step" % (threads, sample_b)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -197,12 +197,21 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    # Exactly ONE line goes to stdout: the JSON.  Libraries write banners there (NCCL prints its version on the first
+    # collective), so everything else -- at file-descriptor level -- is sent to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import torch
@@ -216,6 +225,8 @@ def main():
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"                      # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
@@ -310,7 +321,7 @@ def main():
     # ---- the same step captured once in a CUDA graph and replayed (single GPU): identical kernels on identical
     #      buffers, minus the host launch path and the launch/dependency gaps between the kernels ----
     graph_ms = None
-    if world == 1 and not args.no_graph:
+    if world == 1 and not args.no_graph:          # (capturing the NCCL all-reduce of the multi-GPU step hung: eager there)
         try:
             del loss                                    # drop the eager autograd graph (its AccumulateGrad node is bound to
             x.grad = None                               # the default stream, which would invalidate the capture)
@@ -323,21 +334,31 @@ def main():
             graph = torch.cuda.CUDAGraph()
             x.grad = None
             with torch.cuda.graph(graph):
-                gloss = b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean")
+                gloss = b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean", **kw)
                 gloss.backward()
             for _ in range(args.warmup):
                 graph.replay()
-            torch.cuda.synchronize()
+            barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
             for _ in range(args.steps):
                 graph.replay()
             g1.record()
-            torch.cuda.synchronize()
-            if abs(float(gloss.item()) - loss_value) <= 1e-6 * abs(loss_value):
-                graph_ms = g0.elapsed_time(g1) / args.steps
+            barrier()
+            ok = abs(float(gloss.item()) - loss_value) <= 1e-6 * abs(loss_value)
+            gt = torch.tensor([g0.elapsed_time(g1) / args.steps, 0.0 if ok else 1.0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(gt, op=dist.ReduceOp.MAX)          # slowest rank; any rank's mismatch disables it
+            if float(gt[1].item()) == 0.0:
+                graph_ms = float(gt[0].item())
         except Exception as exc:                                   # capture unsupported: the eager number stands
             sys.stderr.write("bench.py: CUDA graph capture skipped (%s)\n" % exc)
+            if world > 1:                                          # keep the ranks' collectives in step
+                gt = torch.tensor([0.0, 1.0], device=dev, dtype=torch.float64)
+                try:
+                    dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+                except Exception:
+                    pass
 
     # ---- end to end: host (pinned) buffers through the host-array entry point (asr/loss/host.py):
     #      activations H2D, loss + gradient, gradient and loss D2H, all inside the timed region ----
@@ -411,7 +432,7 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": "oracle C port (oracle/ctc_oracle.c, float64, OpenMP x%d): %d passes over the "
                                          "same 64-utterance workload, %.1f s of CPU work" % (threads, reps, secs)}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
