@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not also time the step as a CUDA graph replay")
+    ap.add_argument("--no-kernel-loop", action="store_true",
+                    help="skip the kernel-only loop of the dominant kernel (for ncu launch lists: steps only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -285,6 +287,8 @@ def main():
     #      workspace of one forward, bracketed by CUDA events on the launching stream ----
     k3_ms = None
     try:
+        if args.no_kernel_loop:
+            raise RuntimeError("--no-kernel-loop")
         L = b200ctc._lib
         lib = L.load()
         xd = x.detach()
