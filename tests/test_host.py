@@ -89,3 +89,32 @@ def test_synthetic_inputs_are_deterministic():
         assert ((g["bigrams"][b, :n] == -1) | (g["bigrams"][b, :n] >= 119)).all()
         assert (g["bigrams"][b, n:] == 0).all()                # asr/data/processing.py:125-126
     assert (g["input_length"] >= 3 * g["label_length"] + 1).all()
+
+
+def test_expansion_table_is_the_reference_string_round_trip(pkg):
+    """asr/error.py:49-53: predicted ids -> token strings -> convert_sentence_to_unigram_ids, tabulated per id."""
+    ids = {"_": 0, "a": 1, "b": 2, "c": 3, "ab": 4, "ca": 5}
+    inv = {v: k for k, v in ids.items()}
+    t = pkg.build_expansion_table(ids, inv).numpy()
+    assert t.shape == (6, 2) and t.dtype == np.int32
+    assert t.tolist() == [[0, -1], [1, -1], [2, -1], [3, -1], [1, 2], [3, 1]]
+    # with the reference's own vocabulary and tokeniser, where the reference is mounted
+    from oracle import ref_stub
+    if ref_stub.available():
+        _, vocab = ref_stub.load_error_module()
+        rids, rinv = vocab.get_unigram_ids()
+        first, second = vocab.UNIGRAM_TOKENS[70], vocab.UNIGRAM_TOKENS[3]      # a two-character mora + a plain one
+        rids[first + second] = len(rids)
+        rinv[rids[first + second]] = first + second
+        rt = pkg.build_expansion_table(rids, rinv, convert=vocab.convert_sentence_to_unigram_ids).numpy()
+        assert rt.shape[1] == 2
+        assert rt[rids[first + second]].tolist() == [rids[first], rids[second]]
+        assert all(rt[i, 0] == i and rt[i, 1] == -1 for i in range(1, 1 + len(vocab.UNIGRAM_TOKENS)))
+
+
+def test_error_functions_refuse_to_run_without_a_gpu(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        pkg.compute_minibatch_error(np.zeros((1, 3), np.int64), np.zeros((1, 2), np.int32), 0, {"_": 0}, {0: "_"})
