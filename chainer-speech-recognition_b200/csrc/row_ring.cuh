@@ -18,7 +18,7 @@
 
 namespace b200ctc {
 
-constexpr int kRingConsumers = 8;
+constexpr int kRingConsumers = 8;      // gradient kernel (the softmax/gather kernel runs kK1Consumers, softmax_gather.cu)
 constexpr int kRingThreads = 32 * (1 + kRingConsumers);
 constexpr int kTicketBatch = 8;       // frames per ticket; one producer lane per frame of the batch
 constexpr int kMinSlots = 4;
@@ -46,7 +46,7 @@ inline size_t ring_budget() {
 
 // smem_reserve: shared memory to leave free on the SM for a CTA of another kernel that is meant to run next to
 // this one (the lattice kernel next to the softmax/gather kernel); 0 = none.
-inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes, size_t smem_reserve = 0) {
+inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes, size_t smem_reserve = 0, int consumers = kRingConsumers) {
     RingLayout r;
     r.slot_bytes = align_up(slot_payload, 128);
     const size_t fixed = (size_t)kMaxSlots * (sizeof(RowMeta) + 16) + extra_bytes + 256;
@@ -59,7 +59,7 @@ inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes, size_t smem
     if (n > kMaxSlots) n = kMaxSlots;
     r.slots = (int)(n < 0 ? 0 : n);
     r.batch = r.slots < kTicketBatch ? r.slots : kTicketBatch;
-    r.consumers = r.slots < kRingConsumers ? r.slots : kRingConsumers;
+    r.consumers = r.slots < consumers ? r.slots : consumers;
     size_t o = r.slot_bytes * (size_t)r.slots;
     r.off_meta = o;  o += sizeof(RowMeta) * kMaxSlots;
     r.off_full = o;  o += 8 * kMaxSlots;

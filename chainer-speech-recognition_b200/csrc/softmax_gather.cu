@@ -256,13 +256,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
 // consumer warp that was 28 us of a 105 us kernel.  So the consumers only note finished rows in a small
 // shared-memory FIFO (CTA-scope ordering, cheap) and one extra warp drains all FIFOs with ONE GPU-scope fence per
 // sweep, then bumps the progress counters (the __syncthreads / thread 0 fences / atomic pattern of a grid barrier).
-constexpr int kK1Threads = kRingThreads + 32;          // producer + consumers + signal warp
+constexpr int kK1Consumers = 10;                       // this kernel is bound by its consumers' arithmetic, not by HBM:
+                                                       // two more of them buy 4 us (12 would leave the ring no slack)
+constexpr int kK1Threads = 32 * (1 + kK1Consumers + 1);   // producer + consumers + signal warp
 constexpr int kGatherRegs = 4;                         // emitted ids per lane on the early-release path (<= 128 columns)
 constexpr int kFifoDepth = 4;
 struct SignalFifo {
-    int2 entry[kRingConsumers][kFifoDepth];            // (b, t); b < 0 = this consumer is done
-    unsigned head[kRingConsumers];                     // rows pushed by consumer c
-    unsigned tail[kRingConsumers];                     // rows taken by the signal warp
+    int2 entry[kK1Consumers][kFifoDepth];            // (b, t); b < 0 = this consumer is done
+    unsigned head[kK1Consumers];                     // rows pushed by consumer c
+    unsigned tail[kK1Consumers];                     // rows taken by the signal warp
 };
 constexpr size_t kFifoBytes = (sizeof(SignalFifo) + 127) / 128 * 128;
 
@@ -325,13 +327,13 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     SignalFifo *fifo = reinterpret_cast<SignalFifo *>(smem_raw + rl.off_extra);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra + kFifoBytes);      // GRAD only: V zeros for padded frames
     const bool signalling = (d.progress & 1) != 0;
-    if (threadIdx.x < kRingConsumers) { fifo->head[threadIdx.x] = 0u; fifo->tail[threadIdx.x] = 0u; }
+    if (threadIdx.x < kK1Consumers) { fifo->head[threadIdx.x] = 0u; fifo->tail[threadIdx.x] = 0u; }
     if (GRAD) {
         for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
         fence_proxy_async_smem();
     }
     __syncthreads();
-    if (warp == kRingConsumers + 1) {                     // ===== signal warp =====
+    if (warp == kK1Consumers + 1) {                     // ===== signal warp =====
         if (signalling) signal_warp(fifo, ring.nc, lane, ws, w);
         return;
     }
@@ -566,7 +568,7 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
     const long long frames = (long long)d.B * d.T;
     if (frames == 0) return cudaSuccess;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
-    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes, smem_reserve);
+    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes, smem_reserve, kK1Consumers);
     if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) && !getenv("B200CTC_NO_TMA_K1")) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
         if (ctas > sm_count() - ring_sm_reserve()) ctas = sm_count() - ring_sm_reserve();
@@ -602,7 +604,7 @@ cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, 
     const long long frames = (long long)d.B * d.T;
     if (frames == 0) return cudaSuccess;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
-    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes + (size_t)d.V * 4);
+    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes + (size_t)d.V * 4, 0, kK1Consumers);
     if (!ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) || !ring_usable(grad, gstride_t, gstride_b, d.V, rl) ||
         getenv("B200CTC_NO_TMA_K1"))
         return cudaErrorNotSupported;
