@@ -258,7 +258,8 @@ def main():
 
     # ---- timed region: device time, CUDA events on the stream the kernels are launched on ----
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:                                    # one nvidia-smi poller per job, not per rank: at 8 ranks the host
+        sampler.start()                              # cores are what the eager launch path is short of
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -381,7 +382,7 @@ def main():
         e2e_loss = e2e_step()
     s1.record()
     barrier()
-    clocks = sampler.stop()           # sampled over both timed regions (device-resident steps and end-to-end steps)
+    clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (device-resident and end-to-end steps)
     t2 = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
