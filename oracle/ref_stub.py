@@ -136,3 +136,32 @@ def load_error_module():
             mods[name] = mod
         _error_modules = (mods["error"], mods["vocab"])
     return _error_modules
+
+
+_processing_module = None
+
+
+def load_processing_module():
+    """The reference's asr/data/processing.py, UNMODIFIED.  It imports chainer (stubbed above), jaconv, acoustics and
+    asr/fft.py (python_speech_features): none of them is needed by ``Processor.features_to_minibatch``, so empty
+    stand-ins are registered.  Returns the module."""
+    global _processing_module
+    if _processing_module is None:
+        _install_chainer_stub()
+        load_error_module()                                   # registers _refasr, _refasr.utils, _refasr.vocab
+        for name in ("jaconv", "acoustics"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        fft = types.ModuleType("_refasr.fft")
+        fft.get_filterbanks = lambda **kw: None                # Processor.__init__ (:65) builds a mel filterbank: unused here
+        sys.modules.setdefault("_refasr.fft", fft)
+        sys.modules["_refasr"].fft = sys.modules["_refasr.fft"]
+        data = types.ModuleType("_refasr.data")
+        data.__path__ = [os.path.join(REFERENCE_ROOT, "asr", "data")]
+        sys.modules["_refasr.data"] = data
+        spec = importlib.util.spec_from_file_location("_refasr.data.processing",
+                                                      os.path.join(REFERENCE_ROOT, "asr", "data", "processing.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_refasr.data.processing"] = mod
+        spec.loader.exec_module(mod)
+        _processing_module = mod
+    return _processing_module
