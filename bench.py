@@ -39,6 +39,16 @@ WORKLOAD = {"B": 64, "T": 800, "V": 3500, "L": 80}
 METRIC = "CTC fwd+bwd utterance-frames/sec at B=64,T=800,V=3500"
 UNIT = "frames/s"
 FALLBACK_HBM_GBS = 6650.0
+REF_SAMPLE_UTTS = 4        # utterances of the workload the reference's NumPy path processes per timed step (~1.5 s)
+
+
+def config_dict(world):
+    """`config` of the JSON line: identical in both arms (the driver compares them)."""
+    B = WORKLOAD["B"]
+    return {"workload": "CTC fwd+bwd B=64,T=800,V=3500,L<=80 per GPU, variable lengths "
+                        "(BASELINE configs[1]; N GPUs = batch-sharded configs[3])",
+            "global_batch": world * B, "parallelism": "batch-sharded dp%d, 1 scalar all-reduce" % world,
+            "layout": "(T,B,V) float32", "l2": "inputs (717 MB) and outputs exceed the 126 MB L2; no flush needed"}
 
 
 def synth():
@@ -58,7 +68,9 @@ def profiled_traffic(kernel):
     """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture of this workload
     (profiles/r1_ncu_full_summary.json, written by tools/ncu_summary.py); None if there is no capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")) as f:
+        names = [n for n in ("r2_ncu_full_summary.json", "r1_ncu_full_summary.json")
+                 if os.path.exists(os.path.join(ROOT, "profiles", n))]
+        with open(os.path.join(ROOT, "profiles", names[0])) as f:
             for k in json.load(f):
                 if kernel in k["kernel"]:
                     def to_bytes(v):
@@ -138,8 +150,9 @@ def algorithmic_bytes(V, in_len, B, T):
     return k1, k3
 
 
-def cpu_baseline(prob, threads, budget_s=12.0):
-    """Oracle C port, forward+backward over the WHOLE 64-utterance workload, repeated for ~budget_s seconds."""
+def port_baseline(prob, threads, budget_s=6.0):
+    """Oracle C port (banded restatement of the reference algorithm, float64, OpenMP), forward+backward over the WHOLE
+    64-utterance workload, repeated for ~budget_s seconds."""
     from oracle import c_oracle
     args = (0, prob["x"], prob["labels"], None, prob["input_length"], prob["label_length"], prob["blank"])
     c_oracle.run(*args, nthreads=threads)                      # warm-up: page in, spin up the thread pool
@@ -155,34 +168,117 @@ def cpu_baseline(prob, threads, budget_s=12.0):
     return B * T * reps / dt, dt, reps
 
 
+class ReferenceSample(object):
+    """The reference's own implementation (asr/loss/gram_ctc.py, unmodified, NumPy path under oracle/ref_stub.py;
+    every bigram id -1 = plain CTC) on the first REF_SAMPLE_UTTS utterances of the workload.  One step =
+    GramCTC.forward + GramCTC.backward, exactly what a training step of the reference runs.  Its cost is linear in the
+    number of utterances (every op is per utterance), so frames/s of the sample is frames/s of the
+    workload.  Available wherever the reference's files are: /root/reference, or oracle/_ref on the GPU box."""
+
+    def __init__(self, prob, n=REF_SAMPLE_UTTS):
+        from oracle import ref_stub
+        self.ok = ref_stub.available()
+        if not self.ok:
+            return
+        self.ref = ref_stub.load()
+        self.n = n
+        T = prob["x"].shape[0]
+        xs = tuple(np.ascontiguousarray(prob["x"][t, :n]) for t in range(T))
+        lab = np.ascontiguousarray(prob["labels"][:n], np.int32)
+        self.inputs = (np.asarray(prob["input_length"][:n], np.int32), np.asarray(prob["label_length"][:n], np.int32),
+                       lab, np.full_like(lab, -1)) + xs
+        self.frames = n * T
+        self.threads = 1                                     # NumPy elementwise/reduction code: one thread
+
+    def step(self):
+        f = self.ref.GramCTC(0, "mean")                      # fresh object: backward mutates the saved softmax (:290-296)
+        t0 = time.perf_counter()
+        loss = f.forward(self.inputs)[0]
+        t1 = time.perf_counter()
+        f.backward(self.inputs, (np.float32(1.0),))
+        t2 = time.perf_counter()
+        return float(loss), t1 - t0, t2 - t1
+
+    def describe(self):
+        return ("the reference itself: asr/loss/gram_ctc.py unmodified, NumPy path (bigram ids -1 = plain CTC), "
+                "forward+backward of the first %d of the 64 utterances per step; cost is linear in utterances" % self.n)
+
+
+def torch_cpu_ctc(prob, steps=2):
+    """Secondary CPU line: torch.nn.functional.ctc_loss on the host, float32, all threads."""
+    import torch
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    x = torch.tensor(prob["x"], requires_grad=True)
+    lab = torch.tensor(prob["labels"], dtype=torch.long)
+    il = torch.tensor(prob["input_length"], dtype=torch.long)
+    ll = torch.tensor(prob["label_length"], dtype=torch.long)
+
+    def one():
+        x.grad = None
+        lp = torch.log_softmax(x, dim=2)
+        torch.nn.functional.ctc_loss(lp, lab, il, ll, blank=0, reduction="none").mean().backward()
+    one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    T, B = prob["x"].shape[0], prob["x"].shape[1]
+    return {"value": B * T / dt, "unit": UNIT, "threads": threads, "ms_per_step": 1e3 * dt,
+            "what": "torch.nn.functional.ctc_loss + log_softmax, CPU float32, whole workload (cross-check, not the reference)"}
+
+
 def run_reference_arm(args, rank, world, emit):
-    """--impl reference: the CPU implementation alone, all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation alone, rank 0 only."""
     if rank != 0:
         return
-    from oracle import c_oracle
-    threads = host_threads()
     W = WORKLOAD
-    sample_b = W["B"]
-    prob = synth().ctc_problem(sample_b, W["T"], W["V"], W["L"], seed=0)
-    xargs = (0, prob["x"], prob["labels"], None, prob["input_length"], prob["label_length"], prob["blank"])
-    for _ in range(max(args.warmup, 1)):
-        c_oracle.run(*xargs, nthreads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        c_oracle.run(*xargs, nthreads=threads)
-    dt = time.perf_counter() - t0
-    value = sample_b * W["T"] * args.steps / dt
-    sample = "oracle C port (oracle/ctc_oracle.c, float64, OpenMP x%d), all %d utterances of the workload per step" % (threads, sample_b)
-    emit(({
+    prob = synth().ctc_problem(W["B"], W["T"], W["V"], W["L"], seed=0)
+    ref = ReferenceSample(prob)
+    threads = host_threads()
+    if ref.ok:
+        for _ in range(max(min(args.warmup, 2), 1)):
+            ref.step()
+        fwd = bwd = 0.0
+        for _ in range(args.steps):
+            _, f, b = ref.step()
+            fwd += f; bwd += b
+        dt = fwd + bwd
+        value = ref.frames * args.steps / dt
+        kind, cores, sample, dtype = "reference", ref.threads, ref.describe(), "f32"
+        extra = {"fwd_ms": 1e3 * fwd / args.steps, "bwd_ms": 1e3 * bwd / args.steps}
+    else:                                                     # no reference files on this machine: the banded C port
+        from oracle import c_oracle
+        xargs = (0, prob["x"], prob["labels"], None, prob["input_length"], prob["label_length"], prob["blank"])
+        for _ in range(max(args.warmup, 1)):
+            c_oracle.run(*xargs, nthreads=threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            c_oracle.run(*xargs, nthreads=threads)
+        dt = time.perf_counter() - t0
+        value = W["B"] * W["T"] * args.steps / dt
+        kind, cores, dtype = "port", threads, "f64"
+        sample = "oracle C port (oracle/ctc_oracle.c, float64, OpenMP x%d), all 64 utterances of the workload per step" % threads
+        extra = {}
+    out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "CTC fwd+bwd B=64,T=800,V=3500,L<=80, variable lengths (BASELINE configs[1]); "
-                               "CPU arm: the same %d utterances per step" % sample_b},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": config_dict(max(args.gpus, 1)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
+        "gpu_launches": 0, "host_cores": threads,
+    }
+    out.update(extra)
+    if ref.ok:                                               # the faster CPU restatements beside it, for context
+        v, secs, reps = port_baseline(prob, threads, budget_s=4.0)
+        out["port_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "oracle C port (banded O(T*N) restatement, float64, OpenMP x%d), whole workload, %d passes" % (threads, reps)}
+        try:
+            out["torch_cpu_ctc"] = torch_cpu_ctc(prob)
+        except Exception as exc:
+            sys.stderr.write("bench.py: torch CPU line skipped (%s)\n" % exc)
+    emit(out)
 
 
 def main():
@@ -239,13 +335,22 @@ def main():
     labels = torch.tensor(prob["labels"], device=dev)
     in_len = torch.tensor(prob["input_length"], device=dev)
     lab_len = torch.tensor(prob["label_length"], device=dev)
-    kw = {"group": group} if group is not None else {}
+    # Batch-sharded step: every rank scales its partial loss sum by 1/B_global in-kernel
+    # (batch_global), the gradient needs no communication, and the ONE collective of the path -- a scalar NCCL
+    # all-reduce of the loss -- is issued after the gradient kernel has been enqueued, so no rank's backward ever
+    # waits for a peer's forward.
+    kw = {"batch_global": world * B} if world > 1 else {}
+
+    def reduce_loss(loss):
+        if world > 1:
+            dist.all_reduce(loss.detach(), op=dist.ReduceOp.SUM, group=group)
+        return loss
 
     def step():
         x.grad = None
         loss = b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean", **kw)
         loss.backward()
-        return loss
+        return reduce_loss(loss)
 
     def barrier():
         if world > 1:
@@ -272,6 +377,7 @@ def main():
         ev[k][1].record()
         loss.backward()
         ev[k][2].record()
+        reduce_loss(loss)
     e1.record()
     host_ms = (time.perf_counter() - h0) * 1e3 / args.steps     # host time to ENQUEUE one step (no sync inside the loop)
     barrier()
@@ -326,11 +432,10 @@ def main():
     # ---- the same step captured once in a CUDA graph and replayed (single GPU): identical kernels on identical
     #      buffers, minus the host launch path and the launch/dependency gaps between the kernels ----
     graph_ms = None
-    # Single GPU: always tried.  Several GPUs: capturing the step INCLUDING the NCCL all-reduce hung on this image, so the
-    # multi-GPU variant captures the step without the collective (batch_global makes the in-kernel scale right) and
-    # all-reduces the graph's loss output eagerly after every replay; it is opt-in (B200CTC_BENCH_GRAPH_MULTI=1) until
-    # it has been run on a multi-GPU box.
-    multi = world > 1 and os.environ.get("B200CTC_BENCH_GRAPH_MULTI") == "1"
+    # Several GPUs: the graph holds the rank-local part of the step (capturing the NCCL all-reduce hung on this image);
+    # the scalar all-reduce of the graph's loss output is issued eagerly after every replay, as in the eager step.
+    # B200CTC_BENCH_GRAPH_MULTI=0 switches the multi-GPU replay off.
+    multi = world > 1 and os.environ.get("B200CTC_BENCH_GRAPH_MULTI", "1") == "1"
     if (world == 1 or multi) and not args.no_graph:
         graph, gloss, captured = None, None, 1.0
         try:
@@ -419,11 +524,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CTC fwd+bwd B=64,T=800,V=3500,L<=80 per GPU, variable lengths "
-                               "(BASELINE configs[1]; N GPUs = batch-sharded configs[3])",
-                   "global_batch": world * B, "parallelism": "batch-sharded dp%d, 1 scalar all-reduce" % world,
-                   "layout": "(T,B,V) float32", "l2": "inputs (717 MB) and outputs exceed the 126 MB L2; no flush needed",
-                   "valid_frames_per_step": int(np.sum(prob["input_length"])), "loss": loss_value},
+        "config": config_dict(world),
+        "valid_frames_per_step": int(np.sum(prob["input_length"])), "loss": loss_value,
         "valid_frames_per_s": world * int(np.sum(prob["input_length"])) / (ms_per_step * 1e-3),
         "launch": (("CUDA graph replay of the public-API step (loss forward + backward captured once)" +
                     ("; the scalar all-reduce issued eagerly after each replay" if world > 1 else ""))
@@ -443,15 +545,27 @@ def main():
                 "h2d_bytes_per_step": int(np.sum(prob["input_length"])) * V * 4, "d2h_bytes_per_step": int(g_host.numel() * 4 + 4),
                 "ms_per_step": e2e_ms / args.e2e_steps, "loss": e2e_loss,
                 "api": "b200ctc.ctc_host: 16 utterance groups, H2D (valid frames only) / kernels / D2H on three streams, pinned host buffers"},
-        "gpu_launches": 4 * args.steps,          # per step: header reset, softmax/gather, lattice(+prep), gradient
+        "gpu_launches": 5 * args.steps,          # per step: header reset, softmax/gather, lattice(+prep), zero rows, gradient
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        v, secs, reps = cpu_baseline(prob, threads)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": "oracle C port (oracle/ctc_oracle.c, float64, OpenMP x%d): %d passes over the "
-                                         "same 64-utterance workload, %.1f s of CPU work" % (threads, reps, secs)}
+        ref = ReferenceSample(prob)
+        v, secs, reps = port_baseline(prob, threads)
+        port = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "oracle C port (oracle/ctc_oracle.c, banded restatement, float64, OpenMP x%d): %d passes over the "
+                          "same 64-utterance workload, %.1f s of CPU work" % (threads, reps, secs)}
+        if ref.ok:                                   # ~12 s: warm-up + 6 timed steps of the reference's own NumPy path
+            ref.step()
+            n, tot = 6, 0.0
+            for _ in range(n):
+                _, f, b = ref.step()
+                tot += f + b
+            out["cpu_baseline"] = {"value": ref.frames * n / tot, "unit": UNIT, "cores": ref.threads, "kind": "reference",
+                                   "sample": ref.describe() + "; %d steps, %.1f s of CPU work; host has %d cores" % (n, tot, threads)}
+            out["port_baseline"] = port
+        else:
+            out["cpu_baseline"] = port
     emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -10,6 +10,7 @@ from . import _build
 
 OK, INVALID_ARGUMENT, UNSUPPORTED, CUDA_ERROR, WORKSPACE_TOO_SMALL, OUT_OF_MEMORY = range(6)
 KIND_CTC, KIND_GRAM, KIND_JOINT = 0, 1, 2
+FLAG_NONE, FLAG_SERIAL = 0, 1
 
 _lib = None
 
@@ -34,16 +35,11 @@ def _bind(lib):
         c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p,
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_float,
         c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_void_p]
-    lib.b200ctc_fused_workspace_bytes.restype = c.c_int
-    lib.b200ctc_fused_workspace_bytes.argtypes = [c.c_int] * 6 + [c.POINTER(c.c_size_t)]
-    lib.b200ctc_forward_backward.restype = c.c_int
-    lib.b200ctc_forward_backward.argtypes = [
+    lib.b200ctc_forward_train.restype = c.c_int
+    lib.b200ctc_forward_train.argtypes = [
         c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
-        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_float, c.c_float,
-        c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
-    lib.b200ctc_rescale_grad.restype = c.c_int
-    lib.b200ctc_rescale_grad.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_int, c.c_int, c.c_void_p,
-                                         c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p]
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_float, c.c_void_p,
+        c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_uint, c.c_void_p]
     lib.b200ctc_greedy_argmax.restype = c.c_int
     lib.b200ctc_greedy_argmax.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_int, c.c_int,
                                           c.c_void_p, c.c_void_p]
@@ -66,7 +62,12 @@ def library_path():
 
 
 def load():
-    """Load (building first if the in-tree .so is missing or stale and nvcc exists)."""
+    """Load the in-tree library, building it first if it is missing or stale and nvcc exists.
+
+    Several processes may get here at once (one rank per GPU under torchrun): the build goes to a temporary file
+    under an exclusive file lock and is moved into place atomically (``_build.build``).  A stale library that
+    cannot be rebuilt (no nvcc on this machine) is refused rather than loaded silently -- unless
+    ``B200CTC_ALLOW_STALE=1`` says the caller knows."""
     global _lib
     if _lib is not None:
         return _lib
@@ -77,6 +78,10 @@ def load():
         elif not os.path.exists(path):
             raise B200CTCError("libb200ctc.so is missing and nvcc is unavailable; run __graft_entry__.build() "
                                "-- there is no CPU fallback")
+        elif os.environ.get("B200CTC_ALLOW_STALE") != "1":
+            raise B200CTCError("libb200ctc.so does not match csrc/ (stale build stamp) and nvcc is unavailable to "
+                               "rebuild it; run __graft_entry__.build() where nvcc exists, or set "
+                               "B200CTC_ALLOW_STALE=1 to load it anyway")
     _lib = _bind(ctypes.CDLL(path))
     return _lib
 
@@ -98,12 +103,6 @@ def check(status):
         import torch
         raise torch.cuda.OutOfMemoryError(msg)
     raise B200CTCError(msg)
-
-
-def fused_workspace_bytes(kind, B, T, V, Lmax, groups):
-    out = ctypes.c_size_t(0)
-    check(load().b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, groups, ctypes.byref(out)))
-    return int(out.value)
 
 
 def workspace_bytes(kind, B, T, V, Lmax):

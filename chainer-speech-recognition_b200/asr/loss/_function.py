@@ -15,16 +15,40 @@ import torch
 from ... import _lib
 
 
-def pipeline_groups(B):
-    """1 = use the one-call forward+gradient path (b200ctc_forward_backward, "one-read" schedule) when the activations
-    need a gradient, 0 = separate forward / backward calls (default).  Measured on B200 at B=64,T=800,V=3500 the
-    one-read schedule is only 3 % faster (0.458 vs 0.471 ms): it saves the second read of the activations, but the
-    label-column patch that replaces it is bound by random 32-byte DRAM accesses (86 us).  B200CTC_FUSED=1 enables it."""
-    return 1 if os.environ.get("B200CTC_FUSED", "0") == "1" else 0
+def _flags():
+    """B200CTC_NO_CONCURRENT=1: run the lattice kernel behind the softmax/gather kernel instead of next to it
+    (include/b200ctc.h, B200CTC_FLAG_SERIAL); read per call so that tests can toggle it."""
+    return _lib.FLAG_SERIAL if os.environ.get("B200CTC_NO_CONCURRENT") else _lib.FLAG_NONE
+
+
+def as_device_tensor(a, name="array"):
+    """Any CUDA array -> torch tensor WITHOUT a copy: torch tensors pass through; CuPy arrays and anything else that
+    exposes ``__cuda_array_interface__`` are wrapped in place; a Chainer ``Variable`` contributes its ``.array`` /
+    ``.data`` (gram_ctc.py:312-313 builds Variables around the same arrays).  This is what lets the reference's own
+    training scripts hand their CuPy activations to this library.  Anything else (NumPy arrays,
+    lists) is returned unchanged for the caller to convert."""
+    if isinstance(a, torch.Tensor):
+        return a
+    if hasattr(a, "__cuda_array_interface__"):
+        return torch.as_tensor(a, device=torch.device("cuda", torch.cuda.current_device()))
+    for attr in ("array", "data"):
+        inner = getattr(a, attr, None)
+        if isinstance(inner, torch.Tensor) or hasattr(inner, "__cuda_array_interface__"):
+            return as_device_tensor(inner, name)
+    return a
 
 
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _CaiBlock(object):
+    """A (T,B,V) float32 block of device memory described for torch.as_tensor; keeps the frame owners alive."""
+
+    def __init__(self, ptr, shape, strides_bytes, owners):
+        self.owners = owners
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(int(v) for v in shape),
+                                         "strides": tuple(int(v) for v in strides_bytes), "typestr": "<f4", "version": 2}
 
 
 def stack_frames(xs):
@@ -46,7 +70,17 @@ def stack_frames(xs):
             if step > 0 and all(xs[t].storage_offset() == x0.storage_offset() + t * step for t in range(T)):
                 return torch.as_strided(x0, (T,) + tuple(x0.shape), (step,) + tuple(x0.stride()),
                                         x0.storage_offset())
-    except (RuntimeError, AttributeError):
+        if not any(x.requires_grad for x in xs) and x0.is_cuda and x0.dtype == torch.float32:
+            # frames wrapped one by one from foreign arrays (CuPy views of one model output): separate storage
+            # objects over equally spaced addresses -- describe the whole block through __cuda_array_interface__
+            step_b = xs[1].data_ptr() - x0.data_ptr()
+            if step_b > 0 and step_b % 4 == 0 and all(
+                    x.shape == x0.shape and x.stride() == x0.stride() and x.data_ptr() == x0.data_ptr() + t * step_b
+                    for t, x in enumerate(xs)):
+                holder = _CaiBlock(x0.data_ptr(), (T,) + tuple(x0.shape),
+                                   (step_b,) + tuple(4 * st for st in x0.stride()), xs)
+                return torch.as_tensor(holder, device=x0.device)
+    except (RuntimeError, AttributeError, TypeError, ValueError):
         pass
     return torch.stack(tuple(xs), dim=0)
 
@@ -54,6 +88,7 @@ def stack_frames(xs):
 def _as_int32(a, device, name):
     if a is None:
         return None
+    a = as_device_tensor(a, name)
     if isinstance(a, torch.Tensor):
         if a.dtype.is_floating_point or a.dtype == torch.bool:
             raise TypeError("%s must be an integer array (int32 in the reference), got %s" % (name, a.dtype))
@@ -79,32 +114,30 @@ class LatticeLossFunction(torch.autograd.Function):
         loss_red = torch.empty((), dtype=torch.float32, device=dev)
         loss_scale = 1.0 / float(batch_global) if reduce == "mean" else 1.0     # gram_ctc.py:280-281
         argmax = torch.empty((B, T), dtype=torch.int64, device=dev) if want_argmax else None
-        groups = pipeline_groups(B) if (ctx.needs_input_grad[0] and not want_argmax and kind != _lib.KIND_JOINT) else 0
         ptr = lambda t: t.data_ptr() if t is not None else None
-        if groups > 0:
-            # training step: loss and gradient in one pipelined call (include/b200ctc.h, b200ctc_forward_backward)
+        nbytes = _lib.workspace_bytes(kind, B, T, V, Lmax)
+        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        # A training step (the activations want a gradient): allocate the gradient buffer now, so that the forward
+        # call can write the zero rows of the padded frames while the lattice recursion is finishing
+        # (include/b200ctc.h, b200ctc_forward_train); backward fills the rest of the same buffer.
+        grad = None
+        if ctx.needs_input_grad[0] and input_length is not None and B * T > 0:
             grad = torch.empty_like(acts)
             if grad.stride(2) != 1:
                 grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
-            nbytes = _lib.fused_workspace_bytes(kind, B, T, V, Lmax, groups)
-            workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
-                _lib.check(lib.b200ctc_forward_backward(
+        with torch.cuda.device(dev):
+            if grad is not None:
+                _lib.check(lib.b200ctc_forward_train(
                     kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
                     ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
-                    loss_scale, loss_scale, grad.data_ptr(), grad.stride(0), grad.stride(1), groups,
-                    workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
-            ctx.fused_grad = grad
-        else:
-            nbytes = _lib.workspace_bytes(kind, B, T, V, Lmax)
-            workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
+                    loss_scale, ptr(argmax), grad.data_ptr(), grad.stride(0), grad.stride(1),
+                    workspace.data_ptr(), workspace.numel(), _flags(), _stream_ptr(dev)))
+            else:
                 _lib.check(lib.b200ctc_forward(
                     kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
                     ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
-                    loss_scale, ptr(argmax), workspace.data_ptr(), workspace.numel(), 0, _stream_ptr(dev)))
-            ctx.fused_grad = None
-        ctx.groups, ctx.backward_calls = groups, 0
+                    loss_scale, ptr(argmax), workspace.data_ptr(), workspace.numel(), _flags(), _stream_ptr(dev)))
+        ctx.prefilled_grad = grad
         ctx.kind, ctx.blank, ctx.reduce, ctx.dims = kind, blank, reduce, (B, T, V, Lmax)
         ctx.batch_global = batch_global
         ctx.save_for_backward(acts, labels, bigrams if bigrams is not None else labels, workspace)
@@ -132,22 +165,15 @@ class LatticeLossFunction(torch.autograd.Function):
         gy = gy.to(device=dev, dtype=torch.float32).contiguous()
         per_utt = 0 if ctx.reduce == "mean" else 1
         scale = 1.0 / float(ctx.batch_global) if ctx.reduce == "mean" else 1.0     # :291-294
-        ctx.backward_calls += 1
         big_ptr = bigrams.data_ptr() if ctx.has_bigrams else None
-        if ctx.groups > 0 and ctx.backward_calls == 1:
-            # the gradient was produced at forward time for a unit upstream gradient: apply gy (no-op if it is 1)
-            grad, ctx.fused_grad = ctx.fused_grad, None          # hand over ownership: autograd may keep it as x.grad
-            with torch.cuda.device(dev):
-                _lib.check(lib.b200ctc_rescale_grad(grad.data_ptr(), grad.stride(0), grad.stride(1), B, T, V,
-                                                    gy.data_ptr(), per_utt, ctx.groups, ctx.kind, Lmax,
-                                                    workspace.data_ptr(), workspace.numel(), _stream_ptr(dev)))
-            return (grad,) + (None,) * 10
-        grad = torch.empty_like(acts)
-        if grad.stride(2) != 1:
-            grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
+        # first backward: the buffer whose padded rows the forward call has already zeroed (ownership passes to
+        # autograd, which may keep it as x.grad); a retained graph differentiated again gets a fresh one
+        grad, ctx.prefilled_grad = ctx.prefilled_grad, None
+        if grad is None:
+            grad = torch.empty_like(acts)
+            if grad.stride(2) != 1:
+                grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
         with torch.cuda.device(dev):
-            # (also serves a retained graph differentiated again after the one-call path: its workspace starts
-            #  with a regular workspace)
             _lib.check(lib.b200ctc_backward(
                 ctx.kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), big_ptr,
                 ctx.blank, B, T, V, Lmax, gy.data_ptr(), per_utt, scale, grad.data_ptr(), grad.stride(0),
@@ -163,6 +189,10 @@ def lattice_loss(kind, xs, labels, bigrams, blank_symbol, input_length, label_le
     if isinstance(blank_symbol, bool) or not isinstance(blank_symbol, (int, np.integer)):   # :303-304
         raise TypeError("blank_symbol must be non-negative integer.")
     blank_symbol = int(blank_symbol)
+    if not isinstance(xs, (torch.Tensor, collections.abc.Sequence)):
+        xs = as_device_tensor(xs, "xs")                          # CuPy array / Chainer Variable / DLPack capsule owner
+    elif not isinstance(xs, torch.Tensor) and len(xs) > 0 and not isinstance(xs[0], torch.Tensor):
+        xs = [as_device_tensor(x, "xs[t]") for x in xs]
     if isinstance(xs, torch.Tensor):
         if xs.dim() != 3:
             raise TypeError("xs must be a sequence of (B,V) tensors or one 3-D tensor")
@@ -194,8 +224,11 @@ def lattice_loss(kind, xs, labels, bigrams, blank_symbol, input_length, label_le
             raise ValueError("label_bigram must have the shape of label_unigram")
     else:
         bigrams = None
-    if input_length is None:                                     # :310-313: both default together
-        label_length = None if kind != _lib.KIND_CTC or label_length is None else label_length
+    if input_length is None:
+        # gram_ctc.py:310-313 (and Chainer's CTC, which it derives from): when input_length is omitted BOTH lengths
+        # default to the full padded widths -- a label_length passed without an input_length is ignored there, so it
+        # is ignored here
+        label_length = None
     input_length = _as_int32(input_length, dev, "input_length")
     label_length = _as_int32(label_length, dev, "label_length")
     for name, v in (("input_length", input_length), ("label_length", label_length)):
@@ -203,9 +236,13 @@ def lattice_loss(kind, xs, labels, bigrams, blank_symbol, input_length, label_le
             raise ValueError("%s must have shape (B,)" % name)
     if batch_global is None:
         batch_global = B
-        if group is not None:
+        if group is not None and reduce == "mean":
+            # shards may differ in size (distributed.shard_range): the mean's denominator is the sum of the local
+            # batch sizes, agreed on with one small all-reduce (a host sync -- pass batch_global to avoid it)
             import torch.distributed as dist
-            batch_global = B * dist.get_world_size(group)
+            n = torch.tensor([B], dtype=torch.int64, device=dev)
+            dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+            batch_global = int(n.item())
     return LatticeLossFunction.apply(acts, kind, labels, bigrams, input_length, label_length, blank_symbol,
                                      reduce, batch_global, group, return_argmax)
 

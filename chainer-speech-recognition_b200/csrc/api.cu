@@ -14,26 +14,45 @@ using namespace b200ctc;
 
 namespace {
 
-// zeroes the workspace header (ticket counters) and the frame-progress counters in stream order
-__global__ void zero_header_kernel(WsHeader *h, unsigned *prog, int nprog) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; h->k2b_done = 0u; }
+// zeroes the workspace header (ticket counters, gradient prefill note) and the frame-progress counters in stream order
+__global__ void zero_header_kernel(WsHeader *h, unsigned *prog, int nprog, float *prefill, long long ps_t, long long ps_b) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; h->k2b_done = 0u;
+        h->prefill_valid = prefill ? 1u : 0u;
+        h->prefill_grad = (unsigned long long)reinterpret_cast<uintptr_t>(prefill);
+        h->prefill_stride_t = ps_t; h->prefill_stride_b = ps_b;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) prog[i] = 0u;
 }
 
 // Side stream on which the lattice kernel runs next to the softmax/gather kernel (fork/join by events, so the
 // caller still sees one stream; capturable into a CUDA graph).  One per host thread and device, created on first
-// use and kept: the only state the library holds besides the last-error string.
+// use and destroyed with the thread: the only state the library holds besides the last-error string and the
+// host-side lookup caches (host_cache.cu).
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
 constexpr int kMaxDevices = 64;
-thread_local SideStream g_side[kMaxDevices];
+struct SideStreams {
+    SideStream s[kMaxDevices];
+    ~SideStreams() {
+        for (int i = 0; i < kMaxDevices; ++i) {
+            if (!s[i].stream) continue;
+            // at process exit the runtime may already be gone: every call below then fails harmlessly
+            cudaEventDestroy(s[i].fork);
+            cudaEventDestroy(s[i].join);
+            cudaStreamDestroy(s[i].stream);
+            (void)cudaGetLastError();
+        }
+    }
+};
+thread_local SideStreams g_side;
 
 SideStream *side_stream() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
-    SideStream &s = g_side[dev];
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return nullptr;
+    SideStream &s = g_side.s[dev];
     if (!s.stream) {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { s.stream = nullptr; return nullptr; }
         if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -44,31 +63,6 @@ SideStream *side_stream() {
         }
     }
     return &s;
-}
-
-// gradient *= gy / applied, in place, skipped entirely when the ratio is 1 (the usual loss.backward()):
-// used by the pipelined path, which computes the gradient with a unit upstream gradient at forward time.
-__global__ void rescale_grad_kernel(float *grad, int64_t stride_t, int64_t stride_b, int B, int T, int V,
-                                    const float *gy, int per_utterance, const float *applied) {
-    for (int b = blockIdx.y; b < B; b += gridDim.y) {
-        const float want = per_utterance ? gy[b] : gy[0];
-        const float have = applied[per_utterance ? b : 0];
-        if (want == have) continue;
-        const float r = want / have;
-        for (int t = blockIdx.x; t < T; t += gridDim.x) {
-            float *row = grad + (int64_t)t * stride_t + (int64_t)b * stride_b;
-            for (int v = threadIdx.x; v < V; v += blockDim.x) row[v] *= r;
-        }
-    }
-}
-__global__ void rescale_commit_kernel(const float *gy, int per_utterance, int B, float *applied) {
-    const int n = per_utterance ? B : 1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) applied[i] = gy[i];
-}
-__global__ void fused_init_kernel(WsHeader *h, float *applied, int n, unsigned *prog, int nprog) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; h->k2b_done = 0u; }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) applied[i] = 1.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) prog[i] = 0u;
 }
 
 thread_local char g_err[512] = "";
@@ -100,23 +94,131 @@ int validate(int kind, int B, int T, int V, int Lmax, int blank, bool need_blank
     return B200CTC_OK;
 }
 
+int forward_impl(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
+                 const int32_t *bigrams, const int32_t *input_lengths, const int32_t *label_lengths, int blank, int B, int T,
+                 int V, int Lmax, float *loss_per_utt, float *loss_reduced, float loss_scale, int64_t *argmax_out,
+                 float *grad_prefill, int64_t gstride_t, int64_t gstride_b, void *workspace, size_t workspace_bytes,
+                 unsigned flags, void *stream_) {
+    int rc = validate(kind, B, T, V, Lmax, blank, true);
+    if (rc) return rc;
+    if (!acts && (size_t)B * T > 0) return fail(B200CTC_INVALID_ARGUMENT, "acts is NULL%s");
+    if (!labels && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "labels is NULL%s");
+    if (kind != B200CTC_KIND_CTC && !bigrams && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "bigrams is NULL for Gram-CTC%s");
+    if (!loss_per_utt || !loss_reduced || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "output or workspace pointer is NULL%s");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
+    if ((reinterpret_cast<uintptr_t>(acts) & 3) != 0) return fail(B200CTC_INVALID_ARGUMENT, "acts must be 4-byte aligned%s");
+    if ((reinterpret_cast<uintptr_t>(grad_prefill) & 3) != 0) return fail(B200CTC_INVALID_ARGUMENT, "grad_out must be 4-byte aligned%s");
+    const WsLayout w = make_layout(kind, B, T, V, Lmax);
+    if (workspace_bytes < w.total)
+        return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s: %lld < %lld bytes", "", (long long)workspace_bytes,
+                    (long long)w.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0) return check_cuda(cudaMemsetAsync(loss_reduced, 0, sizeof(float), stream), "memset");
+
+    ProblemDesc d;
+    d.kind = kind == B200CTC_KIND_CTC ? 0 : 1; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
+    d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
+    d.labels = labels; d.bigrams = kind != B200CTC_KIND_CTC ? bigrams : nullptr;
+    d.input_lengths = input_lengths; d.label_lengths = label_lengths;
+    d.progress = 0;
+    // rows of padded frames only exist when the caller gives per-utterance lengths
+    const bool prefill = grad_prefill != nullptr && input_lengths != nullptr && T > 0;
+
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const int nprog = B * w.nblk;
+    zero_header_kernel<<<(nprog + 255) / 256 > 0 ? (nprog + 255) / 256 : 1, 256, 0, stream>>>(
+        reinterpret_cast<WsHeader *>(ws + w.off_hdr), reinterpret_cast<unsigned *>(ws + w.off_prog), nprog,
+        prefill ? grad_prefill : nullptr, (long long)gstride_t, (long long)gstride_b);
+    if ((rc = check_cuda(cudaGetLastError(), "workspace header reset"))) return rc;
+
+    LatticeParams lp;
+    lp.d = d; lp.w = w; lp.ws = ws;
+    lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
+    lp.W = 0; lp.S = 0; lp.second = 0; lp.dbg_nostore = 0;
+    int st = 0;
+    // joint Gram-CTC + CTC: the plain-CTC lattice is a second launch behind the Gram-CTC one (same stream), on the
+    // same emission rows; it adds its loss to loss_per_utt and reduces the batch
+    LatticeParams lp2 = lp;
+    if (w.joint) {
+        lp2.d.kind = 0; lp2.d.bigrams = nullptr;
+        lp2.w = ctc_view_of_joint(w);
+        lp2.second = 1;
+    }
+
+    // The lattice kernel runs NEXT TO the softmax/gather kernel, on a side stream: the recursion is a latency-bound
+    // dependent chain that needs a few warps per utterance, the softmax a bandwidth-bound stream over all SMs, and
+    // the first feeds the second frame by frame through the progress counters (common.cuh).  Tickets walk the
+    // frames from both ends, so alpha and beta both find their next rows ready; what remains exposed is the second
+    // half of each direction after the last row has been produced -- and that window is when a training step's
+    // gradient buffer gets the zero rows of its padded frames (pure HBM writes that need nothing from the lattice).
+    // No deadlock: the softmax kernel never waits on the lattice kernel, and the concurrent mode is only chosen when
+    // every SM keeps room for a ring CTA whatever the lattice CTAs do: 2*B lattice CTAs can close an SM to the ring
+    // kernel only two at a time (launch_softmax_gather sizes its ring for ONE lattice CTA beside it), so 2*B/2 < #SMs
+    // leaves at least one SM per missing pair, and the ring kernel is persistent (any number of its CTAs makes progress).
+    SideStream *side = nullptr;
+    size_t lat_smem = 0;
+    if (B < sm_count() && T > 0 && !(flags & B200CTC_FLAG_SERIAL)) {
+        if ((rc = check_cuda(launch_lattice(lp, stream, &st, true, &lat_smem, false), "lattice kernel"))) return rc;
+        if (!st) side = side_stream();
+        st = 0;
+    }
+    if (side) {
+        d.progress = 3;
+#ifdef B200CTC_EXPERIMENT
+        if (knobs().dbg_progress >= 0) d.progress = knobs().dbg_progress;
+#endif
+        lp.d = d;
+        if ((rc = check_cuda(cudaEventRecord(side->fork, stream), "fork event"))) return rc;
+        if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, lat_smem, stream), "softmax/gather kernel"))) return rc;
+        if ((rc = check_cuda(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait"))) return rc;
+        if ((rc = check_cuda(launch_lattice(lp, side->stream, &st, true), "lattice kernel"))) return rc;
+        if (w.joint && !st) {
+            lp2.d.progress = d.progress;
+            if ((rc = check_cuda(launch_lattice(lp2, side->stream, &st, false), "CTC lattice kernel"))) return rc;
+        }
+        if ((rc = check_cuda(cudaEventRecord(side->join, side->stream), "join event"))) return rc;
+        // behind the softmax kernel, beside the lattice tail
+        if (prefill && (rc = check_cuda(launch_zero_padded_rows(d, grad_prefill, gstride_t, gstride_b, stream), "zero-row kernel"))) return rc;
+        if ((rc = check_cuda(cudaStreamWaitEvent(stream, side->join, 0), "join wait"))) return rc;
+    } else {
+        if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, 0, stream), "softmax/gather kernel"))) return rc;
+        SideStream *zs = prefill ? side_stream() : nullptr;
+        if (zs) {            // the zero rows go beside the lattice kernel here too
+            if ((rc = check_cuda(cudaEventRecord(zs->fork, stream), "fork event"))) return rc;
+            if ((rc = check_cuda(cudaStreamWaitEvent(zs->stream, zs->fork, 0), "fork wait"))) return rc;
+            if ((rc = check_cuda(launch_zero_padded_rows(d, grad_prefill, gstride_t, gstride_b, zs->stream), "zero-row kernel"))) return rc;
+            if ((rc = check_cuda(cudaEventRecord(zs->join, zs->stream), "join event"))) return rc;
+        } else if (prefill) {
+            if ((rc = check_cuda(launch_zero_padded_rows(d, grad_prefill, gstride_t, gstride_b, stream), "zero-row kernel"))) return rc;
+        }
+        if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
+        if (w.joint && !st && (rc = check_cuda(launch_lattice(lp2, stream, &st), "CTC lattice kernel"))) return rc;
+        if (zs && (rc = check_cuda(cudaStreamWaitEvent(stream, zs->join, 0), "join wait"))) return rc;
+    }
+    if (st) return fail(B200CTC_UNSUPPORTED, "lattice of %s%lld nodes does not fit the kernel's shared-memory pipeline", "", w.Nmax);
+    return B200CTC_OK;
+}
+
 }  // namespace
 
+#ifdef B200CTC_EXPERIMENT
 namespace b200ctc {
 void lattice_set_debug(long long *p);
 void lattice_set_timeline(long long *p);
 void softmax_set_timeline(long long *p);
 void gradient_set_timeline(long long *p);
 }
+#endif
 
 extern "C" {
 
+#ifdef B200CTC_EXPERIMENT
+/* profiling hooks of the experiment build (tools/step_timeline.py, tools/lattice_timeline.py); not part of the ABI */
 void b200ctc_debug_lattice(long long *p) { b200ctc::lattice_set_debug(p); }
-/* profiling hook (tools/step_timeline.py): 8 device long longs = [start, end] globaltimer ns of the softmax/gather
- * kernel, the alpha CTAs, the beta CTAs and the gradient kernel; caller presets starts to LLONG_MAX and ends to 0 */
 void b200ctc_debug_timeline(long long *p) {
     b200ctc::softmax_set_timeline(p); b200ctc::lattice_set_timeline(p); b200ctc::gradient_set_timeline(p);
 }
+#endif
 
 int b200ctc_version(void) { return B200CTC_VERSION; }
 
@@ -134,85 +236,19 @@ int b200ctc_forward(int kind, const float *acts, int64_t stride_t, int64_t strid
                     const int32_t *bigrams, const int32_t *input_lengths, const int32_t *label_lengths, int blank,
                     int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_reduced, float loss_scale,
                     int64_t *argmax_out, void *workspace, size_t workspace_bytes, unsigned flags, void *stream_) {
-    (void)flags;
-    int rc = validate(kind, B, T, V, Lmax, blank, true);
-    if (rc) return rc;
-    if (!acts && (size_t)B * T > 0) return fail(B200CTC_INVALID_ARGUMENT, "acts is NULL%s");
-    if (!labels && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "labels is NULL%s");
-    if (kind != B200CTC_KIND_CTC && !bigrams && Lmax > 0) return fail(B200CTC_INVALID_ARGUMENT, "bigrams is NULL for Gram-CTC%s");
-    if (!loss_per_utt || !loss_reduced || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "output or workspace pointer is NULL%s");
-    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
-    if ((reinterpret_cast<uintptr_t>(acts) & 3) != 0) return fail(B200CTC_INVALID_ARGUMENT, "acts must be 4-byte aligned%s");
-    const WsLayout w = make_layout(kind, B, T, V, Lmax);
-    if (workspace_bytes < w.total)
-        return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s: %lld < %lld bytes", "", (long long)workspace_bytes,
-                    (long long)w.total);
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (B == 0) return check_cuda(cudaMemsetAsync(loss_reduced, 0, sizeof(float), stream), "memset");
+    return forward_impl(kind, acts, stride_t, stride_b, labels, bigrams, input_lengths, label_lengths, blank, B, T, V, Lmax,
+                        loss_per_utt, loss_reduced, loss_scale, argmax_out, nullptr, 0, 0, workspace, workspace_bytes, flags,
+                        stream_);
+}
 
-    ProblemDesc d;
-    d.kind = kind == B200CTC_KIND_CTC ? 0 : 1; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
-    d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
-    d.labels = labels; d.bigrams = kind != B200CTC_KIND_CTC ? bigrams : nullptr;
-    d.input_lengths = input_lengths; d.label_lengths = label_lengths;
-    d.progress = 0;
-
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
-    const int nprog = B * w.nblk;
-    zero_header_kernel<<<(nprog + 255) / 256 > 0 ? (nprog + 255) / 256 : 1, 256, 0, stream>>>(
-        reinterpret_cast<WsHeader *>(ws + w.off_hdr), reinterpret_cast<unsigned *>(ws + w.off_prog), nprog);
-    if ((rc = check_cuda(cudaGetLastError(), "workspace header reset"))) return rc;
-
-    LatticeParams lp;
-    lp.d = d; lp.w = w; lp.ws = ws;
-    lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
-    lp.W = 0; lp.S = 0; lp.second = 0;
-    int st = 0;
-    // joint Gram-CTC + CTC: the plain-CTC lattice is a second launch behind the Gram-CTC one (same stream), on the
-    // same emission rows; it adds its loss to loss_per_utt and reduces the batch
-    LatticeParams lp2 = lp;
-    if (w.joint) {
-        lp2.d.kind = 0; lp2.d.bigrams = nullptr;
-        lp2.w = ctc_view_of_joint(w);
-        lp2.second = 1;
-    }
-
-    // The lattice kernel runs NEXT TO the softmax/gather kernel, on a side stream: the recursion is a latency-bound
-    // dependent chain that needs a few warps per utterance, the softmax a bandwidth-bound stream over all SMs, and
-    // the first feeds the second frame by frame through the progress counters (common.cuh).  Tickets walk the
-    // frames from both ends, so alpha and beta both find their next rows ready; what remains exposed is the second
-    // half of each direction after the last row has been produced.
-    // No deadlock: the softmax kernel never waits on the lattice kernel, and with B < #SMs the spinning lattice
-    // CTAs (2 per utterance) cannot occupy every SM's shared memory (an SM is closed to a ring CTA only when it
-    // holds two of them), so ring CTAs always find room.  Larger batches run the two kernels back to back.
-    SideStream *side = nullptr;
-    size_t lat_smem = 0;
-    if (B < sm_count() && T > 0 && !getenv("B200CTC_NO_CONCURRENT")) {
-        if ((rc = check_cuda(launch_lattice(lp, stream, &st, true, &lat_smem, false), "lattice kernel"))) return rc;
-        if (!st) side = side_stream();
-        st = 0;
-    }
-    if (side) {
-        d.progress = 3;
-        if (const char *e = getenv("B200CTC_DBG_PROGRESS")) d.progress = atoi(e);      // experiment knob
-        lp.d = d;
-        if ((rc = check_cuda(cudaEventRecord(side->fork, stream), "fork event"))) return rc;
-        if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, lat_smem, stream), "softmax/gather kernel"))) return rc;
-        if ((rc = check_cuda(cudaStreamWaitEvent(side->stream, side->fork, 0), "fork wait"))) return rc;
-        if ((rc = check_cuda(launch_lattice(lp, side->stream, &st, true), "lattice kernel"))) return rc;
-        if (w.joint && !st) {
-            lp2.d.progress = d.progress;
-            if ((rc = check_cuda(launch_lattice(lp2, side->stream, &st, false), "CTC lattice kernel"))) return rc;
-        }
-        if ((rc = check_cuda(cudaEventRecord(side->join, side->stream), "join event"))) return rc;
-        if ((rc = check_cuda(cudaStreamWaitEvent(stream, side->join, 0), "join wait"))) return rc;
-    } else {
-        if ((rc = check_cuda(launch_softmax_gather(d, w, ws, argmax_out, 0, stream), "softmax/gather kernel"))) return rc;
-        if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
-        if (w.joint && !st && (rc = check_cuda(launch_lattice(lp2, stream, &st), "CTC lattice kernel"))) return rc;
-    }
-    if (st) return fail(B200CTC_UNSUPPORTED, "lattice of %s%lld nodes does not fit the kernel's shared-memory pipeline", "", w.Nmax);
-    return B200CTC_OK;
+int b200ctc_forward_train(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
+                          const int32_t *bigrams, const int32_t *input_lengths, const int32_t *label_lengths, int blank,
+                          int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_reduced, float loss_scale,
+                          int64_t *argmax_out, float *grad_out, int64_t gstride_t, int64_t gstride_b, void *workspace,
+                          size_t workspace_bytes, unsigned flags, void *stream_) {
+    return forward_impl(kind, acts, stride_t, stride_b, labels, bigrams, input_lengths, label_lengths, blank, B, T, V, Lmax,
+                        loss_per_utt, loss_reduced, loss_scale, argmax_out, grad_out, gstride_t, gstride_b, workspace,
+                        workspace_bytes, flags, stream_);
 }
 
 int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
@@ -223,6 +259,8 @@ int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stri
     if (rc) return rc;
     if ((size_t)B * T == 0) return B200CTC_OK;
     if (!acts || !grad_loss || !grad_out || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
+    if (((reinterpret_cast<uintptr_t>(acts) | reinterpret_cast<uintptr_t>(grad_out)) & 3) != 0)
+        return fail(B200CTC_INVALID_ARGUMENT, "acts and grad_out must be 4-byte aligned%s");
     const WsLayout w = make_layout(kind, B, T, V, Lmax);
     if (workspace_bytes < w.total) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
     GradParams g;
@@ -233,89 +271,6 @@ int b200ctc_backward(int kind, const float *acts, int64_t stride_t, int64_t stri
     g.grad_loss = grad_loss; g.per_utterance = per_utterance; g.scale = scale;
     g.grad_out = grad_out; g.gstride_t = gstride_t; g.gstride_b = gstride_b;
     return check_cuda(launch_gradient(g, w, workspace, static_cast<cudaStream_t>(stream_)), "gradient kernel");
-}
-
-size_t fused_applied_offset(int kind, int B, int T, int V, int Lmax) {
-    return align_up(make_layout(kind, B, T, V, Lmax).total, 256);
-}
-
-int b200ctc_fused_workspace_bytes(int kind, int B, int T, int V, int Lmax, int groups, size_t *bytes_out) {
-    (void)groups;
-    if (!bytes_out) return fail(B200CTC_INVALID_ARGUMENT, "bytes_out is NULL%s");
-    int rc = validate(kind, B, T, V, Lmax, 0, false);
-    if (rc) return rc;
-    // [regular workspace][upstream gradient already applied, per utterance]
-    *bytes_out = fused_applied_offset(kind, B, T, V, Lmax) + align_up(sizeof(float) * (size_t)(B > 0 ? B : 1), 256);
-    return B200CTC_OK;
-}
-
-int b200ctc_forward_backward(int kind, const float *acts, int64_t stride_t, int64_t stride_b, const int32_t *labels,
-                             const int32_t *bigrams, const int32_t *input_lengths, const int32_t *label_lengths,
-                             int blank, int B, int T, int V, int Lmax, float *loss_per_utt, float *loss_reduced,
-                             float loss_scale, float grad_scale, float *grad_out, int64_t gstride_t, int64_t gstride_b,
-                             int groups, void *workspace, size_t workspace_bytes, void *stream_) {
-    (void)groups;
-    int rc = validate(kind, B, T, V, Lmax, blank, true);
-    if (rc) return rc;
-    if (!loss_per_utt || !loss_reduced || !workspace || !grad_out) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
-    if (kind == B200CTC_KIND_JOINT) return fail(B200CTC_UNSUPPORTED, "the one-call path does not take the joint loss%s");
-    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return fail(B200CTC_INVALID_ARGUMENT, "workspace must be 16-byte aligned%s");
-    size_t need = 0;
-    b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, 1, &need);
-    if (workspace_bytes < need) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (B == 0 || T == 0) return check_cuda(cudaMemsetAsync(loss_reduced, 0, sizeof(float), stream), "memset");
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
-    float *applied = reinterpret_cast<float *>(ws + fused_applied_offset(kind, B, T, V, Lmax));
-    const WsLayout w = make_layout(kind, B, T, V, Lmax);
-
-    ProblemDesc d;
-    d.kind = kind; d.B = B; d.T = T; d.V = V; d.Lmax = Lmax; d.blank = blank;
-    d.acts = acts; d.stride_t = stride_t; d.stride_b = stride_b;
-    d.labels = labels; d.bigrams = kind == B200CTC_KIND_GRAM ? bigrams : nullptr;
-    d.input_lengths = input_lengths; d.label_lengths = label_lengths;
-    d.progress = 0;
-
-    fused_init_kernel<<<(B * w.nblk + 255) / 256, 256, 0, stream>>>(reinterpret_cast<WsHeader *>(ws + w.off_hdr), applied, B,
-                                                                   reinterpret_cast<unsigned *>(ws + w.off_prog), B * w.nblk);
-    if ((rc = check_cuda(cudaGetLastError(), "workspace header reset"))) return rc;
-    // one-read path: the softmax/gather kernel also writes softmax * scale as the gradient row while the
-    // activation row is in shared memory; after the lattice only the label columns are patched
-    cudaError_t e = launch_softmax_gather_grad(d, w, ws, grad_out, gstride_t, gstride_b, grad_scale, stream);
-    const bool one_read = (e == cudaSuccess);
-    if (e == cudaErrorNotSupported) e = launch_softmax_gather(d, w, ws, nullptr, 0, stream);   // unaligned / huge rows
-    if ((rc = check_cuda(e, "softmax/gather kernel"))) return rc;
-    LatticeParams lp;
-    lp.d = d; lp.w = w; lp.ws = ws;
-    lp.loss_per_utt = loss_per_utt; lp.loss_reduced = loss_reduced; lp.loss_scale = loss_scale;
-    lp.W = 0; lp.S = 0; lp.second = 0;
-    int st = 0;
-    if ((rc = check_cuda(launch_lattice(lp, stream, &st), "lattice kernel"))) return rc;
-    if (st) return fail(B200CTC_UNSUPPORTED, "lattice does not fit the kernel's shared-memory pipeline%s");
-    GradParams gp;
-    gp.d = d; gp.d.input_lengths = nullptr; gp.d.label_lengths = nullptr;
-    gp.grad_loss = applied; gp.per_utterance = 0; gp.scale = grad_scale;              // unit upstream gradient
-    gp.grad_out = grad_out; gp.gstride_t = gstride_t; gp.gstride_b = gstride_b;
-    if (one_read) return check_cuda(launch_posterior_patch(gp, w, ws, stream), "posterior patch kernel");
-    return check_cuda(launch_gradient(gp, w, ws, stream), "gradient kernel");
-}
-
-int b200ctc_rescale_grad(float *grad, int64_t gstride_t, int64_t gstride_b, int B, int T, int V, const float *grad_loss,
-                         int per_utterance, int groups, int kind, int Lmax, void *workspace, size_t workspace_bytes,
-                         void *stream_) {
-    if (!grad || !grad_loss || !workspace) return fail(B200CTC_INVALID_ARGUMENT, "NULL pointer%s");
-    size_t need = 0;
-    int rc = b200ctc_fused_workspace_bytes(kind, B, T, V, Lmax, groups, &need);
-    if (rc) return rc;
-    if (workspace_bytes < need) return fail(B200CTC_WORKSPACE_TOO_SMALL, "workspace too small%s");
-    if ((size_t)B * T == 0) return B200CTC_OK;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
-    float *applied = reinterpret_cast<float *>(ws + fused_applied_offset(kind, B, T, V, Lmax));
-    dim3 grid(T < 64 ? T : 64, B < 128 ? B : 128);
-    rescale_grad_kernel<<<grid, 256, 0, stream>>>(grad, gstride_t, gstride_b, B, T, V, grad_loss, per_utterance, applied);
-    rescale_commit_kernel<<<1, 256, 0, stream>>>(grad_loss, per_utterance, B, applied);
-    return check_cuda(cudaGetLastError(), "rescale kernel");
 }
 
 int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,

@@ -18,8 +18,13 @@
 
 namespace b200ctc {
 
+#ifdef B200CTC_EXPERIMENT
 __device__ long long *g_tl_k3 = nullptr;      // timeline hook, see common.cuh
 void gradient_set_timeline(long long *p) { cudaMemcpyToSymbol(g_tl_k3, &p, sizeof(p)); }
+#define B200CTC_TL_K3(end) timeline_mark(g_tl_k3, 3, end)
+#else
+#define B200CTC_TL_K3(end) ((void)0)
+#endif
 
 namespace {
 
@@ -36,6 +41,28 @@ __device__ __forceinline__ void zero_row(float *__restrict__ g, int V, int lane)
     for (int i = lane; i < n4; i += 32) stg_stream4(g4 + i, z);
     const int tail0 = head + 4 * n4;
     if (tail0 + lane < V) g[tail0 + lane] = 0.f;
+}
+
+// Did the training-step forward already zero the padded rows of exactly this gradient buffer (WsHeader, api.cu)?
+__device__ __forceinline__ bool padded_rows_prefilled(const WsHeader *hdr, const GradParams &gp) {
+    return hdr->prefill_valid != 0u && hdr->prefill_grad == (unsigned long long)reinterpret_cast<uintptr_t>(gp.grad_out) &&
+           hdr->prefill_stride_t == (long long)gp.gstride_t && hdr->prefill_stride_b == (long long)gp.gstride_b;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) zero_padded_rows_kernel(ProblemDesc d, float *grad, int64_t gstride_t,
+                                                                            int64_t gstride_b, int b_major) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const long long warps_total = (long long)gridDim.x * kWarpsPerCta;
+    const long long frames = (long long)d.B * d.T;
+    for (long long f = warp_global; f < frames; f += warps_total) {
+        int b, t;
+        if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
+        else { t = (int)(f / d.B); b = (int)(f % d.B); }
+        int Tb = d.input_lengths ? __ldg(d.input_lengths + b) : d.T;
+        Tb = max(0, min(Tb, d.T));
+        if (t >= Tb) zero_row(grad + (int64_t)t * gstride_t + (int64_t)b * gstride_b, d.V, lane);      // gram_ctc.py:296
+    }
 }
 
 // joint Gram-CTC + CTC: the plain-CTC node that carries the same symbol occurrence as Gram-CTC node j -- unigram
@@ -89,6 +116,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     const int *pc_all = reinterpret_cast<const int *>(ws + w.off_pc);
     const int per = d.kind == 0 ? 2 : 3;
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
+    const bool prefilled = padded_rows_prefilled(hdr, gp);
 
     for (;;) {
         unsigned f = 0;
@@ -100,7 +128,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         else { t = (int)(f / d.B); b = (int)(f % d.B); }
         float *grow = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
         const UttInfo ui = utt[b];
-        if (t >= ui.Tb) { zero_row(grow, d.V, lane); continue; }             // :296
+        if (t >= ui.Tb) { if (!prefilled) zero_row(grow, d.V, lane); continue; }             // :296
 
         const float *row = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
         const float lse2 = lse_all[(size_t)b * d.T + t];
@@ -196,18 +224,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     if (lane == 0) {
         __threadfence();
         const unsigned done = atomicAdd(&hdr->k3_done, 1u) + 1u;
-        if (done == gridDim.x * kWarpsPerCta) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; }
+        if (done == gridDim.x * kWarpsPerCta) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; hdr->prefill_valid = 0u; }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernel 3, TMA row-ring variant (see row_ring.cuh).  The producer bulk-copies the activation row AND
-// the frame's gamma row into a ring slot; a consumer warp turns the row into the gradient in place
+// the frame's alpha and beta rows into a ring slot; a consumer warp turns the row into the gradient in place
 // (softmax * sc, then subtracts the merged posteriors at the <= L+1 label columns -- a plain scatter in
 // shared memory, no bitmap needed) and hands it back to the TMA engine as one bulk store.  Padded frames
-// never touch a consumer: the producer bulk-stores a zero row for them.
-// Slot layout: [V floats row][Np float2 alpha row][Np float2 beta row].
+// never touch a consumer: the producer bulk-stores a zero row for them -- unless the training-step forward has
+// already zeroed them in this very buffer (WsHeader::prefill_*), in which case they are skipped altogether.
+// Slot layout: [16-byte aligned span around the V-float row][Np float2 alpha row][Np float2 beta row].
 // ---------------------------------------------------------------------------------------------
+// Store a row image that sits in shared memory at the same 16-byte phase as its destination: the aligned body as
+// one bulk copy, the <= 3 floats in front of and behind it with ordinary stores.  Called by one lane.
+__device__ __forceinline__ void store_row_image(float *dst, const float *src_sm, int V) {
+    const int head = min(V, (4 - row_misalignment(dst)) & 3);
+    const int body = (V - head) & ~3;
+    for (int i = 0; i < head; ++i) dst[i] = src_sm[i];
+    for (int i = head + body; i < V; ++i) dst[i] = src_sm[i];
+    if (body > 0) bulk_s2g(dst + head, src_sm + head, (uint32_t)body * 4u);
+    bulk_commit();
+}
+
 __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradParams gp, WsLayout w, unsigned char *ws,
                                                                        int b_major, RingLayout rl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -218,15 +258,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
-    const uint32_t row_bytes = (uint32_t)d.V * 4u;
+    const uint32_t span_max = (uint32_t)ring_row_bytes(d.V);             // where the alpha row starts in a slot
     const uint32_t ab_bytes = (uint32_t)w.Np * 8u;
     const uint32_t ab2_bytes = w.joint ? (uint32_t)w.Np2 * 8u : 0u;      // joint: + the plain-CTC lattice's alpha/beta rows
-    // extra region: [V floats of zeros][per consumer: Umax floats posterior]
-    timeline_mark(g_tl_k3, 3, false);
+    // extra region: [V + 4 floats of zeros][per consumer: Umax floats posterior]
+    B200CTC_TL_K3(false);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
-    float *post_all = zero_row + d.V;
-    for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
+    float *post_all = zero_row + ((d.V + 4 + 3) & ~3);
+    for (int i = threadIdx.x; i < d.V + 4; i += blockDim.x) zero_row[i] = 0.f;
     fence_proxy_async_smem();
+    const bool prefilled = padded_rows_prefilled(hdr, gp);
     __syncthreads();
 
     if (warp == 0) {
@@ -245,8 +286,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                 if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
                 else { t = (int)(f / d.B); b = (int)(f % d.B); }
                 if (t >= utt[b].Tb) {                                                // :296 -- zeros, straight from smem
-                    bulk_s2g(gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b, zero_row, row_bytes);
-                    bulk_commit();
+                    if (!prefilled) {
+                        float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
+                        store_row_image(dst, zero_row + row_misalignment(dst), d.V);
+                    }
                 } else {
                     need = true;
                 }
@@ -255,30 +298,33 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             if (need) {
                 const unsigned myq = q + (unsigned)__popc(mask & ((1u << lane) - 1u));
                 const int s = ring_claim(ring, myq);
-                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0;
+                const float *src = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
+                const int off = row_misalignment(src);
+                const uint32_t span = row_span_bytes(off, d.V);
+                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0; ring.meta[s].off = off;
                 ring_publish(ring, s, myq);
-                mbar_arrive_expect_tx(&ring.full[s], row_bytes + 2 * ab_bytes + 2 * ab2_bytes);
-                bulk_g2s(ring.slot(s), d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b, row_bytes,
-                         &ring.full[s]);
-                bulk_g2s(ring.slot(s) + row_bytes, av_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
-                bulk_g2s(ring.slot(s) + row_bytes + ab_bytes, bv_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
+                mbar_arrive_expect_tx(&ring.full[s], span + 2 * ab_bytes + 2 * ab2_bytes);
+                bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
+                bulk_g2s(ring.slot(s) + span_max, av_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
+                bulk_g2s(ring.slot(s) + span_max + ab_bytes, bv_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
                 if (w.joint) {
                     const float2 *av2 = reinterpret_cast<const float2 *>(ws + w.off_av2) + ((size_t)b * d.T + t) * w.Np2;
                     const float2 *bv2 = reinterpret_cast<const float2 *>(ws + w.off_bv2) + ((size_t)b * d.T + t) * w.Np2;
-                    bulk_g2s(ring.slot(s) + row_bytes + 2 * ab_bytes, av2, ab2_bytes, &ring.full[s]);
-                    bulk_g2s(ring.slot(s) + row_bytes + 2 * ab_bytes + ab2_bytes, bv2, ab2_bytes, &ring.full[s]);
+                    bulk_g2s(ring.slot(s) + span_max + 2 * ab_bytes, av2, ab2_bytes, &ring.full[s]);
+                    bulk_g2s(ring.slot(s) + span_max + 2 * ab_bytes + ab2_bytes, bv2, ab2_bytes, &ring.full[s]);
                 }
             }
             q += (unsigned)__popc(mask);
         }
         ring_stop(ring, q, lane);
         bulk_wait_all<0>();
-        timeline_mark(g_tl_k3, 3, true);
-        // re-arm the queue for a possible second backward over the same workspace
+        B200CTC_TL_K3(true);
+        // re-arm the queue for a possible second backward over the same workspace; the prefill note was good for
+        // this one pass only (the buffer now belongs to the caller)
         if (lane == 0) {
             __threadfence();
             const unsigned done = atomicAdd(&hdr->k3_done, 1u) + 1u;
-            if (done == gridDim.x) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; }
+            if (done == gridDim.x) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; hdr->prefill_valid = 0u; }
         }
         return;
     }
@@ -290,7 +336,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
     float *post_sm = post_all + (size_t)(warp - 1) * ((w.Umax + 3) & ~3);
     const int per = d.kind == 0 ? 2 : 3;
-    const int n4 = d.V >> 2;
     if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
     for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
         const int s = ring_acquire(ring, q);
@@ -301,10 +346,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             break;
         }
         const int b = m.b, t = m.t;
-        float *row = reinterpret_cast<float *>(ring.slot(s));
-        const float2 *a_sm = reinterpret_cast<const float2 *>(row + d.V);       // alpha row
+        float *slotf = reinterpret_cast<float *>(ring.slot(s));
+        float *row = slotf + m.off;                                          // element v of the frame
+        const int n4 = (m.off + d.V + 3) >> 2;                               // float4s of the aligned span
+        const float2 *a_sm = reinterpret_cast<const float2 *>(ring.slot(s) + span_max);   // alpha row
         const float2 *b_sm = a_sm + w.Np;                                    // beta row
-        float *e_sm = reinterpret_cast<float *>(row + d.V);                  // alpha*beta/P, written over the alpha row
+        float *e_sm = reinterpret_cast<float *>(const_cast<float2 *>(a_sm)); // alpha*beta/P, written over the alpha row
         const float2 *a2_sm = b_sm + w.Np;                                   // joint: plain-CTC alpha row, beta row
         const float2 *b2_sm = a2_sm + w.Np2;
         float *e2_sm = reinterpret_cast<float *>(const_cast<float2 *>(a2_sm));
@@ -355,8 +402,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             post_sm[u] = post * sc;
         }
         const float sc_soft = w.joint ? 2.f * sc : sc;                       // two losses, two softmax terms
-        // softmax * sc in place
-        float4 *row4 = reinterpret_cast<float4 *>(row);
+        // softmax * sc in place, over the whole aligned span (what lies outside the row is never stored)
+        float4 *row4 = reinterpret_cast<float4 *>(slotf);
 #pragma unroll 4
         for (int i = lane; i < n4; i += 32) {
             float4 v = row4[i];
@@ -371,8 +418,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            bulk_s2g(gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b, row, row_bytes);
-            bulk_commit();
+            store_row_image(gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b, row, d.V);
             bulk_wait_read<0>();                 // the TMA engine has read the slot: hand it back to the producer
             mbar_arrive(&ring.empty[s]);
         }
@@ -380,161 +426,17 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     if (lane == 0) bulk_wait_all<0>();
 }
 
-// ---------------------------------------------------------------------------------------------
-// One-read path, second half: the gradient rows already hold softmax * scale (written by the softmax/gather
-// kernel while the row was in shared memory); subtract the merged posterior at the <= L+1 columns the lattice
-// can emit (gram_ctc.py:180-217, :290).  One warp per valid frame; reads the alpha/beta rows (coalesced), merges
-// per id in a fixed order (deterministic), then one read-modify-write per emitted id.
-// ---------------------------------------------------------------------------------------------
-constexpr int kPatchNodeIters = 8;    // lattice nodes per lane held in registers: up to 256 nodes on the fast path
-constexpr int kPatchSymIters = 4;     // emitted ids per lane on the fast path: up to 128 distinct ids
-constexpr int kPatchFrames = 8;       // consecutive frames of one utterance per work item
-
-struct PatchLoads {
-    float2 av[kPatchNodeIters], bv[kPatchNodeIters];
-    float gold[kPatchSymIters];
-};
-
-// Work item = 8 consecutive frames of one utterance: the utterance's tables (emitted ids, node lists, log P) are
-// fetched once per item, and the DRAM loads of frame i+1 (alpha/beta rows, the gradient values to patch) are in
-// flight while frame i is merged -- the kernel is otherwise a chain of dependent L2/DRAM latencies.
-__global__ void __launch_bounds__(kWarpsPerCta * 32) posterior_patch_kernel(GradParams gp, WsLayout w, unsigned char *ws,
-                                                                            int b_major, int sm_floats_per_warp) {
-    extern __shared__ float sm_all[];
-    (void)b_major;
-    const ProblemDesc &d = gp.d;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    float *e_sm = sm_all + (size_t)warp * sm_floats_per_warp;
-    WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
-    const UttInfo *utt = reinterpret_cast<const UttInfo *>(ws + w.off_utt);
-    const float2 *av_all = reinterpret_cast<const float2 *>(ws + w.off_av);
-    const float2 *bv_all = reinterpret_cast<const float2 *>(ws + w.off_bv);
-    const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
-    const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
-    const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
-    const int per = d.kind == 0 ? 2 : 3;
-    const unsigned chunks = (unsigned)((d.T + kPatchFrames - 1) / kPatchFrames);
-    const unsigned items = (unsigned)d.B * chunks;
-    for (;;) {
-        unsigned it = 0;
-        if (lane == 0) it = atomicAdd(&hdr->k3_ticket, 1u);      // the gradient kernel's counter, unused on this path
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= items) break;
-        const int b = (int)(it / chunks);
-        const int t0 = (int)(it % chunks) * kPatchFrames;
-        const UttInfo ui = utt[b];
-        const int t1 = min(t0 + kPatchFrames, ui.Tb);
-        if (t0 >= t1) continue;
-        const float gy = gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss);
-        const float sc = gy * gp.scale;
-        const float2 *arow0 = av_all + (size_t)b * d.T * w.Np;
-        const float2 *brow0 = bv_all + (size_t)b * d.T * w.Np;
-        const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
-        const int *unode = unode_all + (size_t)b * w.Nmax;
-        const int *usym = usym_all + (size_t)b * w.Nmax;
-        float *gbase = gp.grad_out + (int64_t)b * gp.gstride_b;
-        if (ui.Nb <= 32 * kPatchNodeIters && ui.Ub <= 32 * kPatchSymIters) {
-            int sym[kPatchSymIters], n0[kPatchSymIters], n1[kPatchSymIters];
-#pragma unroll
-            for (int k = 0; k < kPatchSymIters; ++k) {
-                const int u = lane + 32 * k;
-                sym[k] = -1; n0[k] = 0; n1[k] = 0;
-                if (u < ui.Ub) { sym[k] = __ldg(usym + u); n0[k] = __ldg(uoff + u); n1[k] = __ldg(uoff + u + 1); }
-            }
-            auto load = [&](int t, PatchLoads &L) {
-                const float2 *arow = arow0 + (size_t)t * w.Np, *brow = brow0 + (size_t)t * w.Np;
-                const float *grow = gbase + (int64_t)t * gp.gstride_t;
-#pragma unroll
-                for (int k = 0; k < kPatchNodeIters; ++k) {
-                    const int j = lane + 32 * k;
-                    L.av[k] = make_float2(0.f, SENT); L.bv[k] = make_float2(0.f, SENT);
-                    if (j < ui.Nb) { L.av[k] = __ldg(arow + j); L.bv[k] = __ldg(brow + j + w.boff); }
-                }
-#pragma unroll
-                for (int k = 0; k < kPatchSymIters; ++k) L.gold[k] = sym[k] >= 0 ? grow[sym[k]] : 0.f;
-            };
-            auto finish = [&](int t, const PatchLoads &L) {
-                float *grow = gbase + (int64_t)t * gp.gstride_t;
-                float blank_part = 0.f;
-#pragma unroll
-                for (int k = 0; k < kPatchNodeIters; ++k) {
-                    const int j = lane + 32 * k;
-                    if (j < ui.Nb) {
-                        const float e = node_posterior(L.av[k], L.bv[k], ui.Ph, ui.Pl);
-                        e_sm[j] = e;                                            // alpha*beta/P
-                        if (j % per == 0) blank_part += e;
-                    }
-                }
-                blank_part = warp_sum(blank_part);
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < kPatchSymIters; ++k) {
-                    if (sym[k] < 0) continue;
-                    float post = (lane + 32 * k == ui.ublank) ? blank_part : 0.f;
-                    for (int n = n0[k]; n < n1[k]; ++n) {
-                        const int j = __ldg(unode + n);
-                        if (j < ui.Nb) post += e_sm[j];
-                    }
-                    grow[sym[k]] = L.gold[k] - __fmul_rn(post, sc);        // distinct columns; no FMA contraction, so the
-                }                                                          // result equals the separate gradient kernel's
-                __syncwarp();
-            };
-            PatchLoads A, Bf;
-            load(t0, A);
-            for (int t = t0; t < t1; t += 2) {
-                if (t + 1 < t1) load(t + 1, Bf);
-                finish(t, A);
-                if (t + 2 < t1) load(t + 2, A);
-                if (t + 1 < t1) finish(t + 1, Bf);
-            }
-        } else {
-            for (int t = t0; t < t1; ++t) {
-                const float2 *arow = arow0 + (size_t)t * w.Np, *brow = brow0 + (size_t)t * w.Np;
-                float *grow = gbase + (int64_t)t * gp.gstride_t;
-                float blank_part = 0.f;
-                for (int j = lane; j < ui.Nb; j += 32) {
-                    const float2 a = __ldg(arow + j), bb = __ldg(brow + j + w.boff);
-                    const float e = node_posterior(a, bb, ui.Ph, ui.Pl);
-                    e_sm[j] = e;
-                    if (j % per == 0) blank_part += e;
-                }
-                blank_part = warp_sum(blank_part);
-                __syncwarp();
-                for (int u = lane; u < ui.Ub; u += 32) {
-                    const int m0 = __ldg(uoff + u), m1 = __ldg(uoff + u + 1);
-                    float post = (u == ui.ublank) ? blank_part : 0.f;
-                    for (int n = m0; n < m1; ++n) {
-                        const int j = __ldg(unode + n);
-                        if (j < ui.Nb) post += e_sm[j];
-                    }
-                    float *p = grow + __ldg(usym + u);
-                    *p = *p - __fmul_rn(post, sc);
-                }
-                __syncwarp();
-            }
-        }
-    }
-}
-
 }  // namespace
 
-cudaError_t launch_posterior_patch(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream) {
-    const long long frames = (long long)g.d.B * g.d.T;
-    if (frames == 0) return cudaSuccess;
-    unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
-    const int per_warp = w.Np;
-    const size_t smem = sizeof(float) * (size_t)per_warp * kWarpsPerCta;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(posterior_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    const long long items = (long long)g.d.B * ((g.d.T + kPatchFrames - 1) / kPatchFrames);
-    long long ctas = (items + kWarpsPerCta - 1) / kWarpsPerCta;
-    const long long cap = (long long)sm_count() * 8;
+cudaError_t launch_zero_padded_rows(const ProblemDesc &d, float *grad, int64_t gstride_t, int64_t gstride_b,
+                                    cudaStream_t stream) {
+    const long long frames = (long long)d.B * d.T;
+    if (frames == 0 || !d.input_lengths) return cudaSuccess;
+    long long ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long cap = (long long)sm_count() * 4;
     if (ctas > cap) ctas = cap;
-    const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
-    posterior_patch_kernel<<<(int)ctas, kWarpsPerCta * 32, smem, stream>>>(g, w, wsb, b_major, per_warp);
+    const int b_major = gstride_b > gstride_t ? 1 : 0;
+    zero_padded_rows_kernel<<<(int)ctas, kWarpsPerCta * 32, 0, stream>>>(d, grad, gstride_t, gstride_b, b_major);
     return cudaGetLastError();
 }
 
@@ -543,25 +445,22 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
     if (frames == 0) return cudaSuccess;
     unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
     const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
-    const size_t extra = sizeof(float) * ((size_t)g.d.V + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
-    const RingLayout rl = make_ring(sizeof(float) * ((size_t)g.d.V + 4 * (size_t)w.Np + (w.joint ? 4 * (size_t)w.Np2 : 0)), extra);
+    const size_t extra = sizeof(float) * ((size_t)((g.d.V + 4 + 3) & ~3) + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
+    const RingLayout rl = make_ring(ring_row_bytes(g.d.V) + sizeof(float) * (4 * (size_t)w.Np + (w.joint ? 4 * (size_t)w.Np2 : 0)), extra);
     if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
-        ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl) && !getenv("B200CTC_NO_TMA_K3")) {
+        ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl) && !knobs().no_tma_k3) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
-        if (ctas > sm_count() - ring_sm_reserve()) ctas = sm_count() - ring_sm_reserve();
+        if (ctas > sm_count()) ctas = sm_count();
         if (ctas < 1) ctas = 1;
-        cudaError_t e = cudaFuncSetAttribute(gradient_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+        cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(gradient_ring_kernel), rl.total);
         if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(gradient_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         gradient_ring_kernel<<<(int)ctas, kRingThreads, rl.total, stream>>>(g, w, wsb, b_major, rl);
         return cudaGetLastError();
     }
     const int per_warp = w.Np + ((w.Umax + 3) & ~3) + (w.joint ? w.Np2 : 0);
     const size_t smem = sizeof(float) * (size_t)per_warp * kWarpsPerCta;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(gradient_kernel), smem);
+    if (e != cudaSuccess) return e;
     long long ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
     const long long cap = (long long)sm_count() * 8;
     if (ctas > cap) ctas = cap;

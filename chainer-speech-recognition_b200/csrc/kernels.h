@@ -20,18 +20,26 @@ struct ProblemDesc {
 // smem_reserve: shared memory to leave free per SM for a lattice CTA running next to this kernel (0 = none)
 cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
                                   size_t smem_reserve, cudaStream_t stream);
-cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, void *ws, float *grad, int64_t gstride_t,
-                                       int64_t gstride_b, float scale, cudaStream_t stream);
 cudaError_t launch_argmax(const float *acts, int64_t stride_t, int64_t stride_b, int B, int T, int V,
                           int64_t *argmax_out, cudaStream_t stream);
 
 // shared by the two row-streaming kernels (defined in softmax_gather.cu)
 struct RingLayout;
 bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl);
-int sm_count();
-// SMs the ring kernels leave free (the pipelined forward+gradient path runs lattice CTAs next to them)
-int ring_sm_reserve();
-void set_ring_sm_reserve(int n);
+
+// ---- host-side caches (host_cache.cu): nothing below costs a driver call after its first use ----
+int current_device();
+int sm_count();                                                        // per device
+// opt-in dynamic shared memory + maximum carve-out for `func`; cudaFuncSetAttribute only when more is needed than before
+cudaError_t ensure_dynamic_smem(const void *func, size_t bytes);
+// environment switches, read once per process.  B200CTC_NO_TMA forces the plain-LDG row kernels (tests of the fallback);
+// the rest are experiment knobs that only exist in -DB200CTC_EXPERIMENT builds (tools/), never in the product library
+struct Knobs {
+    bool no_tma = false;
+    bool no_tma_k1 = false, no_tma_k3 = false, gram_k3 = false, lat_nostore = false;
+    int lat_stages = 0, ring_kb = 0, dbg_progress = -1;
+};
+const Knobs &knobs();
 
 // kernel 2: alpha/beta lattice recursion (+ symbol-table CTAs, + batch loss reduction by the last CTA)
 struct LatticeParams {
@@ -67,8 +75,10 @@ struct GradParams {
     int64_t gstride_t, gstride_b;
 };
 cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream);
-// one-read path: subtract the merged posteriors at the label columns of a gradient that already holds softmax * scale
-cudaError_t launch_posterior_patch(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream);
+// zero rows of the padded frames (t >= input_lengths[b]) of a gradient buffer (gram_ctc.py:296); launched by the
+// training-step forward while the lattice recursion is finishing, see api.cu
+cudaError_t launch_zero_padded_rows(const ProblemDesc &d, float *grad, int64_t gstride_t, int64_t gstride_b,
+                                    cudaStream_t stream);
 
 // evaluation path: greedy collapse + gram expansion + edit distance + error rate (greedy_error.cu)
 cudaError_t launch_greedy_error(const int64_t *argmax, const int32_t *input_lengths, int B, int T, const int32_t *labels,

@@ -52,10 +52,15 @@
 
 namespace b200ctc {
 
+#ifdef B200CTC_EXPERIMENT
 __device__ long long *g_tl_k2 = nullptr;      // timeline hook, see common.cuh
 void lattice_set_timeline(long long *p) { cudaMemcpyToSymbol(g_tl_k2, &p, sizeof(p)); }
 __device__ long long *g_lat_dbg = nullptr;   // profiling hook (tools/lattice_timeline.py): per-warp cycle breakdown
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define B200CTC_TL_K2(slot, end) timeline_mark(g_tl_k2, slot, end)
+#else
+#define B200CTC_TL_K2(slot, end) ((void)0)
+#endif
 
 namespace {
 
@@ -355,8 +360,13 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
     int stage = 0;
     uint32_t wrap = 0;
     bool early = false;                                       // the wait for the coming chunk already succeeded
+#ifdef B200CTC_EXPERIMENT
     long long acc_wait = 0, acc_work = 0, acc_tail = 0;
     const bool prof = (g_lat_dbg != nullptr) && lane == 0 && blockIdx.x < 64;
+#else
+    constexpr bool prof = false;
+    long long acc_wait = 0, acc_work = 0, acc_tail = 0;
+#endif
     for (int ch = 0; ch < nchunks; ++ch) {
         const int cnt = min(CH, n - ch * CH);
         long long tq0 = 0, tq1 = 0, tq2 = 0;
@@ -399,11 +409,15 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
         stage = nstage; wrap = nwrap;
         if (prof) acc_tail += clock64() - tq2;
     }
+#ifdef B200CTC_EXPERIMENT
     if (prof) {
         long long *o = g_lat_dbg + ((size_t)blockIdx.x * 32 + w) * 8;
         o[0] = acc_wait; o[1] = 0; o[2] = 0; o[3] = acc_work; o[4] = acc_tail; o[5] = nchunks;
         o[6] = gtime();
     }
+#else
+    (void)acc_wait; (void)acc_work; (void)acc_tail;
+#endif
 }
 
 template <int K, bool GRAM>
@@ -496,7 +510,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
     }
     const int b = blockIdx.x >> 1;
     const int dir = blockIdx.x & 1;                        // 0: alpha, 1: beta
-    timeline_mark(g_tl_k2, 1 + dir, false);
+    B200CTC_TL_K2(1 + dir, false);
     const int W = p.W, S = p.S;
     // warps [0,W): recursion, warp W: I/O.  Read through a shuffle so that the compiler knows the value is
     // warp-uniform: every branch below is then a uniform branch, and the recursion's shuffles need no divergence
@@ -546,14 +560,16 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         } else {
             LaneState<K, GRAM> st;
             init_lane<K, GRAM>(st, d, b, Lb, Nb, dir == 1, 32 * w + lane);
+#ifdef B200CTC_EXPERIMENT
             if (p.dbg_nostore) st.valid = 0u;            // timing experiment only (B200CTC_LAT_NOSTORE): results are garbage
+#endif
             if (dir == 0) run_direction<K, GRAM, false, CH>(st, pp, c, 0, Tb, w, lane);         // alpha: frames 0 .. Tb-1
             else          run_direction<K, GRAM, true, CH>(st, pp, c, Tb - 1, Tb, w, lane);     // beta:  frames Tb-1 .. 0
         }
     }
     if (dir == 1) {                                        // the beta CTA is done
         __syncthreads();
-        timeline_mark(g_tl_k2, 2, true);
+        B200CTC_TL_K2(2, true);
         return;
     }
     __threadfence_block();
@@ -610,17 +626,16 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) *p.loss_reduced = (float)(acc * (double)p.loss_scale);
     }
-    timeline_mark(g_tl_k2, 1, true);
+    B200CTC_TL_K2(1, true);
 }
 
 template <int K, bool GRAM, int MAXW, int CH>
 cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
     auto kern = lattice_kernel<K, GRAM, MAXW, CH>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     // the SM's L1/shared split is chosen per kernel: ask for the maximum so that a lattice CTA and a ring CTA of the
     // softmax/gather kernel (which asks for the same) can share an SM
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+    if (e != cudaSuccess) return e;
     kern<<<(p.second ? 2 : 3) * p.d.B, 32 * (p.W + 1), smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -645,7 +660,9 @@ WsLayout ctc_view_of_joint(const WsLayout &w) {
     return v;
 }
 
+#ifdef B200CTC_EXPERIMENT
 void lattice_set_debug(long long *p) { cudaMemcpyToSymbol(g_lat_dbg, &p, sizeof(p)); }
+#endif
 
 int lattice_max_nodes(int kind) { return kind == 0 ? 32 * 4 * kMaxWarpsPerDir : 32 * 6 * kMaxWarpsPerDir; }
 
@@ -659,7 +676,9 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     int K;
     if (kind == 0) K = (Nmax <= 32 * 2 * kMaxWarpsPerDir) ? 2 : 4;
     else K = (Nmax <= 32 * kGenericMaxWarps) ? 1 : ((Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6);
-    if (kind == 1 && getenv("B200CTC_GRAM_K3") && K == 1) K = 3;                  // experiment knob
+#ifdef B200CTC_EXPERIMENT
+    if (kind == 1 && knobs().gram_k3 && K == 1) K = 3;
+#endif
     const int W = (Nmax + 32 * K - 1) / (32 * K);
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
@@ -675,7 +694,9 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     const size_t budget = concurrent ? (size_t)64 * 1024 : kLatticeSmemBudget;
     while (CH > CHmin && plan_smem(p.w.W, W, want, PAD, CH).total > budget) CH >>= 1;
     int S = want;
-    if (const char *e = getenv("B200CTC_LAT_STAGES")) S = atoi(e);               // experiment knob
+#ifdef B200CTC_EXPERIMENT
+    if (knobs().lat_stages >= 2) S = knobs().lat_stages;
+#endif
     while (S > 2 && plan_smem(p.w.W, W, S, PAD, CH).total > kLatticeSmemBudget) --S;
     const SmemPlan sp = plan_smem(p.w.W, W, S, PAD, CH);
     if (sp.total > kLatticeSmemBudget) { *status = 2; return cudaSuccess; }
@@ -684,7 +705,10 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     if (prep > smem) smem = prep;
     if (smem > 227 * 1024) { *status = 2; return cudaSuccess; }
     p.W = W; p.S = S;
-    p.dbg_nostore = getenv("B200CTC_LAT_NOSTORE") ? 1 : 0;
+    p.dbg_nostore = 0;
+#ifdef B200CTC_EXPERIMENT
+    p.dbg_nostore = knobs().lat_nostore ? 1 : 0;
+#endif
     if (smem_out) *smem_out = smem;
     if (!launch) return cudaSuccess;
     if (kind == 0) return K == 2 ? launch_one<2, false>(p, CH, smem, stream) : launch_one<4, false>(p, CH, smem, stream);

@@ -10,11 +10,17 @@
 //             the copy queue instead of by resident warps;
 //   consumer  warp c handles row sequence numbers c, c+NC, c+2NC, ...: waits for the slot's "full"
 //             barrier, works on the row out of shared memory, then releases the slot ("empty").
-// Requirements (checked by the host dispatcher, which otherwise uses the plain LDG kernels):
-// rows 16-byte aligned, V % 4 == 0, and at least kMinSlots rows fit in shared memory.
+// Rows need only be 4-byte aligned (the reference's real vocabulary is 119 unigram ids + however many bigrams pass
+// the count filter, asr/vocab.py:62-97 -- not a multiple of 4 in general): the producer copies the 16-byte aligned
+// span that covers the row, RowMeta::off says where in the slot element 0 sits, and whoever stores a row back
+// (gradient kernel) writes the unaligned ends with ordinary stores.  The span may reach up to 12 bytes in front of
+// the first row and behind the last one: inside the allocation's own 256-byte granule, read only.
+// Requirement (checked by the host dispatcher, which otherwise uses the plain LDG kernels): at least kMinSlots
+// such spans fit in shared memory.
 #pragma once
 #include <stdlib.h>
 #include "common.cuh"
+#include "kernels.h"
 
 namespace b200ctc {
 
@@ -29,7 +35,15 @@ struct RowMeta {
     int b, t;
     int kind;      // 0: full work, 1: argmax only (padded frame), -1: stop
     unsigned seq;  // row sequence number currently occupying the slot (published before the barrier is armed)
+    int off;       // the row's element 0 sits `off` floats into the slot (0..3: misalignment of the row in global memory)
 };
+
+// bytes a slot needs for a row of V floats wherever it starts
+__host__ __device__ inline size_t ring_row_bytes(int V) { return ((size_t)V * 4 + 12 + 15) & ~(size_t)15; }
+#ifdef __CUDACC__
+__device__ __forceinline__ int row_misalignment(const float *row) { return (int)((reinterpret_cast<uintptr_t>(row) >> 2) & 3); }
+__device__ __forceinline__ uint32_t row_span_bytes(int off, int V) { return (uint32_t)(((off + V) * 4 + 15) & ~15); }
+#endif
 
 struct RingLayout {
     int consumers;         // active consumer warps = min(kRingConsumers, slots), see ring_acquire
@@ -40,7 +54,9 @@ struct RingLayout {
 };
 
 inline size_t ring_budget() {
-    if (const char *e = getenv("B200CTC_RING_KB")) return (size_t)atoi(e) * 1024;      // experiment knob
+#ifdef B200CTC_EXPERIMENT
+    if (knobs().ring_kb > 0) return (size_t)knobs().ring_kb * 1024;
+#endif
     return kRingSmemBudget;
 }
 

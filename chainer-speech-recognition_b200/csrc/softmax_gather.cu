@@ -15,8 +15,13 @@
 
 namespace b200ctc {
 
+#ifdef B200CTC_EXPERIMENT
 __device__ long long *g_tl_k1 = nullptr;      // timeline hook, see common.cuh
 void softmax_set_timeline(long long *p) { cudaMemcpyToSymbol(g_tl_k1, &p, sizeof(p)); }
+#define B200CTC_TL_K1(end) timeline_mark(g_tl_k1, 0, end)
+#else
+#define B200CTC_TL_K1(end) ((void)0)
+#endif
 
 namespace {
 
@@ -247,17 +252,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
 // take two cheap passes (max/argmax, then sum of exponentials) and the label gather reads shared
 // memory instead of going back to L2.
 // ---------------------------------------------------------------------------------------------
-// GRAD: the one-read variant used by b200ctc_forward_backward.  While the row is still in shared memory the
-// consumer also turns it into softmax * scale and hands it to the TMA engine as the gradient row; the few label
-// columns get their posterior subtracted later by posterior_patch_kernel (gradient.cu).  The activations are then
-// read from HBM once per step instead of twice.
 // "Row written" signals for a concurrently running lattice kernel (common.cuh, signal_frame_done).  A signal must
 // be a release at GPU scope, and such a fence costs ~1.5 us on this part whatever is outstanding -- per row and
 // consumer warp that was 28 us of a 105 us kernel.  So the consumers only note finished rows in a small
 // shared-memory FIFO (CTA-scope ordering, cheap) and one extra warp drains all FIFOs with ONE GPU-scope fence per
 // sweep, then bumps the progress counters (the __syncthreads / thread 0 fences / atomic pattern of a grid barrier).
-constexpr int kK1Consumers = 10;                       // this kernel is bound by its consumers' arithmetic, not by HBM:
-                                                       // two more of them buy 4 us (12 would leave the ring no slack)
+constexpr int kK1Consumers = 10;
 constexpr int kK1Threads = 32 * (1 + kK1Consumers + 1);   // producer + consumers + signal warp
 constexpr int kGatherRegs = 4;                         // emitted ids per lane on the early-release path (<= 128 columns)
 constexpr int kFifoDepth = 4;
@@ -306,32 +306,55 @@ __device__ __forceinline__ void signal_warp(SignalFifo *f, int nc, int lane, uns
     }
 }
 
-struct GradOut {
-    float *grad;
-    int64_t gstride_t, gstride_b;
-    float scale;
-};
+// Sum of exponentials of a staged row WITHOUT a running maximum: every lane takes the largest of its first four
+// elements as its own reference (an integer in log2 units), so the loop body is load / FFMA / MUFU.EX2 / FADD with
+// four independent accumulators -- no loop-carried maximum, no rescaling branch.  The references are aligned at the
+// end with exact powers of two.  A reference that is not the maximum only moves the intermediate sums along the
+// float32 exponent range (no precision is lost); what it cannot absorb is an element more than ~2^100 above a
+// lane's reference -- the sum then overflows to +inf (or a NaN / all -inf row shows up) and the caller redoes the
+// row with the running-maximum scan below.  Returns false in that case.
+__device__ __forceinline__ bool fast_row_lse(const float4 *__restrict__ row4, int n4, int lane, float &la, float &lb) {
+    float ref = -INFINITY, nr = 0.f;
+    if (lane < n4) {
+        const float4 v = row4[lane];
+        const float cm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));       // NaNs are dropped here and caught by the sum
+        if (cm > -INFINITY) { ref = rintf(cm * LOG2E_HI); nr = -ref; } else ref = 0.f;
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+        const float4 v = row4[i];
+        s0 += ex2_approx(fmaf(v.x, LOG2E_HI, nr));
+        s1 += ex2_approx(fmaf(v.y, LOG2E_HI, nr));
+        s2 += ex2_approx(fmaf(v.z, LOG2E_HI, nr));
+        s3 += ex2_approx(fmaf(v.w, LOG2E_HI, nr));
+    }
+    const float sl = (s0 + s1) + (s2 + s3);
+    const float R = warp_max(ref);
+    const float S = warp_sum(sl * ex2_approx(ref - R));                  // ref - R: integer <= 0 (or -inf for an empty lane)
+    if (!(S > 0.f && S < INFINITY && fabsf(R) < 4194304.f)) return false;    // warp-uniform
+    const float lg = log2f(S);
+    const float a = R + lg;                                              // TwoSum(R, lg)
+    const float bb = a - R;
+    la = a;
+    lb = (R - (a - bb)) + (lg - bb);
+    return true;
+}
 
-template <bool ARGMAX, bool GRAD>
+template <bool ARGMAX>
 __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(ProblemDesc d, WsLayout w,
                                                                               unsigned char *ws,
-                                                                              int64_t *argmax_out, RingLayout rl, GradOut go) {
+                                                                              int64_t *argmax_out, RingLayout rl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ring ring = ring_setup(smem_raw, rl);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
-    const uint32_t row_bytes = (uint32_t)d.V * 4u;
-    timeline_mark(g_tl_k1, 0, false);
+    B200CTC_TL_K1(false);
     SignalFifo *fifo = reinterpret_cast<SignalFifo *>(smem_raw + rl.off_extra);
-    float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra + kFifoBytes);      // GRAD only: V zeros for padded frames
     const bool signalling = (d.progress & 1) != 0;
     if (threadIdx.x < kK1Consumers) { fifo->head[threadIdx.x] = 0u; fifo->tail[threadIdx.x] = 0u; }
-    if (GRAD) {
-        for (int i = threadIdx.x; i < d.V; i += blockDim.x) zero_row[i] = 0.f;
-        fence_proxy_async_smem();
-    }
     __syncthreads();
     if (warp == kK1Consumers + 1) {                     // ===== signal warp =====
         if (signalling) signal_warp(fifo, ring.nc, lane, ws, w);
@@ -354,33 +377,30 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
                 Tb = max(0, min(Tb, d.T));
                 valid = t < Tb;
                 need = valid || ARGMAX;
-                if (GRAD && !valid) {                                                 // gram_ctc.py:296: zeros, straight from smem
-                    bulk_s2g(go.grad + (int64_t)t * go.gstride_t + (int64_t)b * go.gstride_b, zero_row, row_bytes);
-                    bulk_commit();
-                }
             }
             const unsigned mask = __ballot_sync(0xffffffffu, need);
             if (need) {
                 const unsigned myq = q + (unsigned)__popc(mask & ((1u << lane) - 1u));
                 const int s = ring_claim(ring, myq);
-                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = valid ? 0 : 1;
+                // the 16-byte aligned span that covers the row (rows themselves only need 4-byte alignment)
+                const float *src = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
+                const int off = row_misalignment(src);
+                const uint32_t span = row_span_bytes(off, d.V);
+                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = valid ? 0 : 1; ring.meta[s].off = off;
                 ring_publish(ring, s, myq);
-                mbar_arrive_expect_tx(&ring.full[s], row_bytes);
-                bulk_g2s(ring.slot(s), d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b, row_bytes,
-                         &ring.full[s]);
+                mbar_arrive_expect_tx(&ring.full[s], span);
+                bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
             }
             q += (unsigned)__popc(mask);
         }
         ring_stop(ring, q, lane);
-        if (GRAD) bulk_wait_all<0>();
-        timeline_mark(g_tl_k1, 0, true);
+        B200CTC_TL_K1(true);
         return;
     }
 
     // ===== consumers =====
     float *lse_out = reinterpret_cast<float *>(ws + w.off_lse);
     float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
-    const int n4 = d.V >> 2;
     if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
     unsigned pushed = 0;
     for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
@@ -391,8 +411,16 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             if (lane == 0) mbar_arrive(&ring.empty[s]);
             break;
         }
-        const float *row = reinterpret_cast<const float *>(ring.slot(s));
-        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        float *slotf = reinterpret_cast<float *>(ring.slot(s));
+        const float *row = slotf + m.off;                              // element v of the frame
+        const float4 *row4 = reinterpret_cast<const float4 *>(slotf);  // the aligned span, float4 by float4
+        const int n4 = (m.off + d.V + 3) >> 2;
+        if (m.off != 0 || (d.V & 3) != 0) {
+            // elements of the span outside the row: -inf, i.e. probability 0 and never a maximum
+            if (lane < m.off) slotf[lane] = -INFINITY;
+            if (m.off + d.V + lane < 4 * n4) slotf[m.off + d.V + lane] = -INFINITY;
+            __syncwarp();
+        }
         bool released = false;                  // the slot has already been handed back (early, see the gather)
         // Emitted ids of this lane's columns, requested now so that their latency hides behind the row scan:
         // column 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams (gram_ctc.py:24-32, :155)
@@ -410,49 +438,57 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
             Lb = max(0, min(Lb, d.Lmax));
             ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
-            early = !GRAD && ncol <= 32 * kGatherRegs;
+            early = ncol <= 32 * kGatherRegs;
             if (early) {
 #pragma unroll
                 for (int k = 0; k < kGatherRegs; ++k) syms[k] = (lane + 32 * k < ncol) ? symbol_of(lane + 32 * k) : -1;
             }
         }
-        // one pass over the staged row: per-lane online (max, sum of 2^((x - max) * log2 e)) and greedy index; a
-        // padded frame (argmax only) skips the exponentials
-        RowStat st;
-        st.m = -INFINITY; st.s = 0.f; st.bv = -INFINITY; st.bi = 0x7fffffff;
-        if (m.kind == 0) {
+        float la = 0.f, lb = 0.f;
+        bool have_lse = false;
+        if (!ARGMAX && m.kind == 0) have_lse = fast_row_lse(row4, n4, lane, la, lb);
+        if (!have_lse) {
+            // one pass with a per-lane running (max, sum of 2^((x - max) * log2 e)) and the greedy index; a padded
+            // frame (argmax only) skips the exponentials
+            RowStat st;
+            st.m = -INFINITY; st.s = 0.f; st.bv = -INFINITY; st.bi = 0x7fffffff;
+            if (m.kind == 0) {
 #pragma unroll 4
-            for (int i = lane; i < n4; i += 32) fold4<ARGMAX>(st, row4[i], 4 * i);
-        } else {
+                for (int i = lane; i < n4; i += 32) fold4<ARGMAX>(st, row4[i], 4 * i - m.off);
+            } else {
 #pragma unroll 4
-            for (int i = lane; i < n4; i += 32) {
-                const float4 v = row4[i];
-                fold<ARGMAX>(st, v.x, 4 * i);
-                fold<ARGMAX>(st, v.y, 4 * i + 1);
-                fold<ARGMAX>(st, v.z, 4 * i + 2);
-                fold<ARGMAX>(st, v.w, 4 * i + 3);
+                for (int i = lane; i < n4; i += 32) {
+                    const float4 v = row4[i];
+                    fold<ARGMAX>(st, v.x, 4 * i - m.off);
+                    fold<ARGMAX>(st, v.y, 4 * i - m.off + 1);
+                    fold<ARGMAX>(st, v.z, 4 * i - m.off + 2);
+                    fold<ARGMAX>(st, v.w, 4 * i - m.off + 3);
+                }
             }
-        }
-        if (ARGMAX) {
-            float bv = st.bv; int bi = st.bi;
+            if (ARGMAX) {
+                float bv = st.bv; int bi = st.bi;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const bool onan = (ov != ov), mnan = (bv != bv);
-                bool take;
-                if (onan || mnan) take = onan && (!mnan || oi < bi);
-                else take = (ov > bv) || (ov == bv && oi < bi);
-                if (take) { bv = ov; bi = oi; }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const bool onan = (ov != ov), mnan = (bv != bv);
+                    bool take;
+                    if (onan || mnan) take = onan && (!mnan || oi < bi);
+                    else take = (ov > bv) || (ov == bv && oi < bi);
+                    if (take) { bv = ov; bi = oi; }
+                }
+                // an element of the span in front of the row (index < 0, value -inf) can only "win" when every
+                // element of the row is -inf, and numpy.argmax of such a row is 0
+                if (lane == 0) argmax_out[(size_t)m.b * d.T + m.t] = bi < 0 ? 0 : bi;
             }
-            if (lane == 0) argmax_out[(size_t)m.b * d.T + m.t] = bi;
+            if (m.kind == 0) {
+                const float mx = warp_max(st.m);
+                float sum = st.m == -INFINITY ? 0.f : st.s * ex2_approx((st.m - mx) * LOG2E_HI);
+                sum = warp_sum(sum);
+                split_lse2(mx, sum, la, lb);
+            }
         }
         if (m.kind == 0) {
-            const float mx = warp_max(st.m);
-            float sum = st.m == -INFINITY ? 0.f : st.s * ex2_approx((st.m - mx) * LOG2E_HI);
-            sum = warp_sum(sum);
-            float la, lb;
-            split_lse2(mx, sum, la, lb);
             if (lane == 0) lse_out[(size_t)m.b * d.T + m.t] = la + lb;
             float2 *lprow = lp_out + ((size_t)m.b * d.T + m.t) * w.W;
             if (early) {
@@ -484,34 +520,11 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             }
             __syncwarp();
             if (signalling && lane == 0) fifo_push(fifo, warp - 1, pushed, m.b, m.t);
-            if (GRAD) {
-                // softmax * scale in place (same arithmetic as the gradient kernel), then one bulk store
-                __syncwarp();
-                const float cc = -(la + lb);
-                float4 *w4 = reinterpret_cast<float4 *>(ring.slot(s));
-#pragma unroll 4
-                for (int i = lane; i < n4; i += 32) {
-                    float4 v = w4[i];
-                    v.x = ex2_approx(fmaf(v.x, LOG2E_HI, cc)) * go.scale;
-                    v.y = ex2_approx(fmaf(v.y, LOG2E_HI, cc)) * go.scale;
-                    v.z = ex2_approx(fmaf(v.z, LOG2E_HI, cc)) * go.scale;
-                    v.w = ex2_approx(fmaf(v.w, LOG2E_HI, cc)) * go.scale;
-                    w4[i] = v;
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    bulk_s2g(go.grad + (int64_t)m.t * go.gstride_t + (int64_t)m.b * go.gstride_b, ring.slot(s), row_bytes);
-                    bulk_commit();
-                    bulk_wait_read<0>();
-                }
-            }
         }
         __syncwarp();
         if (lane == 0 && !released) mbar_arrive(&ring.empty[s]);
     }
     if (signalling && lane == 0) fifo_push(fifo, warp - 1, pushed, -1, 0);
-    if (GRAD && lane == 0) bulk_wait_all<0>();
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) argmax_kernel(const float *acts, int64_t stride_t,
@@ -534,11 +547,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) argmax_kernel(const float *
 }
 
 int grid_for_frames(long long frames) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
-    const long long cap = (long long)sms * 8;       // 8 CTAs x 8 warps = 64 resident warps per SM
+    const long long cap = (long long)sm_count() * 8;       // 8 CTAs x 8 warps = 64 resident warps per SM
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     return (int)ctas;
@@ -546,21 +556,12 @@ int grid_for_frames(long long frames) {
 
 }  // namespace
 
+// Rows qualify for the TMA ring when at least kMinSlots of them (each with room for the 16-byte aligned span around a
+// row that is only 4-byte aligned) fit in shared memory; base pointer and strides are in floats, so any of them do.
 bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl) {
-    if (getenv("B200CTC_NO_TMA")) return false;
-    return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride_t & 3) == 0 && (stride_b & 3) == 0 &&
-           (V & 3) == 0 && rl.slots >= kMinSlots;
-}
-
-namespace { thread_local int g_ring_reserve = 0; }
-int ring_sm_reserve() { return g_ring_reserve; }
-void set_ring_sm_reserve(int n) { g_ring_reserve = n; }
-
-int sm_count() {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
+    (void)stride_t; (void)stride_b; (void)V;
+    if (knobs().no_tma) return false;
+    return (reinterpret_cast<uintptr_t>(base) & 3) == 0 && rl.slots >= kMinSlots;
 }
 
 cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void *ws, int64_t *argmax_out,
@@ -568,23 +569,20 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
     const long long frames = (long long)d.B * d.T;
     if (frames == 0) return cudaSuccess;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
-    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes, smem_reserve, kK1Consumers);
-    if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) && !getenv("B200CTC_NO_TMA_K1")) {
+    const RingLayout rl = make_ring(ring_row_bytes(d.V), kFifoBytes, smem_reserve, kK1Consumers);
+    if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) && !knobs().no_tma_k1) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
-        if (ctas > sm_count() - ring_sm_reserve()) ctas = sm_count() - ring_sm_reserve();
+        if (ctas > sm_count()) ctas = sm_count();
         if (ctas < 1) ctas = 1;
-        const GradOut none = {nullptr, 0, 0, 0.f};
         cudaError_t e;
         if (argmax_out) {
-            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+            e = ensure_dynamic_smem(reinterpret_cast<const void *>(softmax_gather_ring_kernel<true>), rl.total);
             if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(softmax_gather_ring_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            softmax_gather_ring_kernel<true, false><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, argmax_out, rl, none);
+            softmax_gather_ring_kernel<true><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, argmax_out, rl);
         } else {
-            e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
+            e = ensure_dynamic_smem(reinterpret_cast<const void *>(softmax_gather_ring_kernel<false>), rl.total);
             if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(softmax_gather_ring_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            softmax_gather_ring_kernel<false, false><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, nullptr, rl, none);
+            softmax_gather_ring_kernel<false><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, nullptr, rl);
         }
         return cudaGetLastError();
     }
@@ -593,28 +591,6 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
         softmax_gather_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, argmax_out);
     else
         softmax_gather_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(d, w, wsb, nullptr);
-    return cudaGetLastError();
-}
-
-// One-read variant: statistics + gather + gradient row (softmax * scale) in the same pass.  Returns
-// cudaErrorNotSupported when the rows do not qualify for the TMA ring (the caller then falls back to the
-// separate gradient kernel).
-cudaError_t launch_softmax_gather_grad(const ProblemDesc &d, const WsLayout &w, void *ws, float *grad, int64_t gstride_t,
-                                       int64_t gstride_b, float scale, cudaStream_t stream) {
-    const long long frames = (long long)d.B * d.T;
-    if (frames == 0) return cudaSuccess;
-    unsigned char *wsb = static_cast<unsigned char *>(ws);
-    const RingLayout rl = make_ring((size_t)d.V * 4, kFifoBytes + (size_t)d.V * 4, 0, kK1Consumers);
-    if (!ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) || !ring_usable(grad, gstride_t, gstride_b, d.V, rl) ||
-        getenv("B200CTC_NO_TMA_K1"))
-        return cudaErrorNotSupported;
-    long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
-    if (ctas > sm_count()) ctas = sm_count();
-    const GradOut go = {grad, gstride_t, gstride_b, scale};
-    cudaError_t e = cudaFuncSetAttribute(softmax_gather_ring_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.total);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(softmax_gather_ring_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    softmax_gather_ring_kernel<false, true><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, nullptr, rl, go);
     return cudaGetLastError();
 }
 

@@ -12,12 +12,18 @@
  * Conventions
  *   - plain C types only; every pointer is a CUDA *device* pointer unless the name ends in _host;
  *   - the caller owns every buffer, including the workspace; the library keeps no device memory
- *     and no global state besides a thread-local last-error string and, per host thread and device,
+ *     and no global state besides a thread-local last-error string, host-side lookup caches (SM
+ *     count, per-kernel shared-memory opt-in, environment switches) and, per host thread and device,
  *     one internal side stream with two events (b200ctc_forward runs the lattice kernel on it next
- *     to the softmax kernel; forked from and joined back into `stream`, capturable in a CUDA graph);
+ *     to the softmax kernel; forked from and joined back into `stream`, capturable in a CUDA graph;
+ *     destroyed when the host thread exits);
  *   - every function returns a status code (B200CTC_OK == 0) and never throws;
- *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
- *     except the *_host convenience entry points;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises the
+ *     device or touches host copies of the data (host-array convenience wrappers live in the Python
+ *     package, asr/loss/host.py, on top of these entry points);
+ *   - activations and gradients need 4-byte alignment only: rows of any vocabulary size and pitch take
+ *     the TMA path (the reference's vocabulary is 119 unigram ids + the bigrams that pass a count
+ *     filter, asr/vocab.py:62-97 -- rarely a multiple of 4);
  *   - activations are float32, element (t, b, v) at acts[t*stride_t + b*stride_b + v] (vocabulary
  *     stride is 1), which covers the reference's stacked (T,B,V) layout (gram_ctc.py:272-273) and
  *     the decoder's (B,T,V) layout (asr/model/cnn.py:45-47) without a copy;
@@ -36,7 +42,7 @@
 extern "C" {
 #endif
 
-#define B200CTC_VERSION 100
+#define B200CTC_VERSION 200
 
 enum {
     B200CTC_OK = 0,
@@ -44,7 +50,10 @@ enum {
     B200CTC_UNSUPPORTED = 2,        /* shape outside what the kernels are instantiated for       */
     B200CTC_CUDA_ERROR = 3,         /* launch / runtime failure; message in b200ctc_last_error() */
     B200CTC_WORKSPACE_TOO_SMALL = 4,
-    B200CTC_OUT_OF_MEMORY = 5       /* host entry points only -> torch.cuda.OutOfMemoryError     */
+    B200CTC_OUT_OF_MEMORY = 5       /* cudaErrorMemoryAllocation from a launch -> torch.cuda.OutOfMemoryError
+                                       (buffers are the caller's, so this is rare; WORKSPACE_TOO_SMALL maps to the
+                                       same Python exception, which is what the reference's batch-size search
+                                       catches, run/ctc/cnn/train.py:204-211) */
 };
 
 /* JOINT: Gram-CTC loss + plain CTC loss of the same activations and unigram labels in one pass
@@ -55,7 +64,10 @@ enum { B200CTC_KIND_CTC = 0, B200CTC_KIND_GRAM = 1, B200CTC_KIND_JOINT = 2 };
 
 /* flags for b200ctc_forward */
 enum {
-    B200CTC_FLAG_NONE = 0
+    B200CTC_FLAG_NONE = 0,
+    B200CTC_FLAG_SERIAL = 1         /* run the lattice kernel behind the softmax/gather kernel instead of next to it
+                                       (same results bit for bit; for debugging and for callers that must not have
+                                       a second stream involved) */
 };
 
 int b200ctc_version(void);
@@ -102,29 +114,21 @@ int b200ctc_backward(int kind,
                      const void *workspace, size_t workspace_bytes, void *stream);
 
 /*
- * Forward + gradient in one call -- the fast path for a training step (GramCTC.forward immediately followed
- * by GramCTC.backward, asr/loss/gram_ctc.py:246-297, as optimizer.update does, run/ctc/cnn/train.py:200).
- * "One-read" schedule: while an activation row is staged in shared memory for the softmax statistics the same
- * kernel also writes softmax * grad_scale as that frame's gradient row; after the lattice recursion a small kernel
- * subtracts the merged posteriors at the <= L+1 label columns.  The activations are read from HBM once per step
- * instead of twice (8 instead of 12 bytes per element of algorithmic traffic).  The gradient is written for a
- * unit upstream gradient times grad_scale (1/B_global for 'mean'); b200ctc_rescale_grad applies the real upstream
- * gradient later and is a no-op when it is 1.  `groups` is reserved (pass 1).  Needs its own workspace size
- * (b200ctc_fused_workspace_bytes); that workspace also serves a later b200ctc_backward.
+ * Forward of a TRAINING step: b200ctc_forward plus one piece of the backward pass that needs nothing from the
+ * lattice.  `grad_out` is the buffer the following b200ctc_backward is going to fill; this call writes the zero rows
+ * of its padded frames (t >= input_lengths[b], gram_ctc.py:296) while the alpha/beta recursion is finishing and HBM is
+ * otherwise idle, and leaves a note in the workspace.  b200ctc_backward, when handed the same buffer and strides
+ * with that workspace, skips those rows (once: the note is cleared by the backward pass that uses it; any other
+ * buffer is filled completely as usual).  With grad_out == NULL or input_lengths == NULL it is b200ctc_forward.
  */
-int b200ctc_fused_workspace_bytes(int kind, int B, int T, int V, int Lmax, int groups, size_t *bytes_out);
-int b200ctc_forward_backward(int kind,
-                             const float *acts, int64_t stride_t, int64_t stride_b,
-                             const int32_t *labels, const int32_t *bigrams,
-                             const int32_t *input_lengths, const int32_t *label_lengths,
-                             int blank, int B, int T, int V, int Lmax,
-                             float *loss_per_utt, float *loss_reduced, float loss_scale, float grad_scale,
-                             float *grad_out, int64_t gstride_t, int64_t gstride_b,
-                             int groups, void *workspace, size_t workspace_bytes, void *stream);
-/* grad *= grad_loss / (what was applied before), in place; per_utterance as in b200ctc_backward. */
-int b200ctc_rescale_grad(float *grad, int64_t gstride_t, int64_t gstride_b, int B, int T, int V,
-                         const float *grad_loss, int per_utterance, int groups, int kind, int Lmax,
-                         void *workspace, size_t workspace_bytes, void *stream);
+int b200ctc_forward_train(int kind,
+                          const float *acts, int64_t stride_t, int64_t stride_b,
+                          const int32_t *labels, const int32_t *bigrams,
+                          const int32_t *input_lengths, const int32_t *label_lengths,
+                          int blank, int B, int T, int V, int Lmax,
+                          float *loss_per_utt, float *loss_reduced, float loss_scale, int64_t *argmax_out,
+                          float *grad_out, int64_t gstride_t, int64_t gstride_b,
+                          void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
 
 /* Greedy path alone (run/ctc/cnn/train.py:232 and its 9 sibling call sites): out (B,T) int64. */
 int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b,

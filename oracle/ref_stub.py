@@ -1,9 +1,11 @@
 """Run the reference's own ``asr/loss/gram_ctc.py`` UNMODIFIED on its NumPy path.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Works only where ``/root/reference`` is
-mounted (the build container); the GPU box never has it, so nothing under ``-m gpu`` tests,
-``smoke()`` or ``bench.py`` calls this.  It exists to (1) pin oracle/lattice.py and
-oracle/ctc_oracle.c and (2) generate the committed golden vectors (tests/golden/generate_golden.py).
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Needs the reference's files: ``/root/reference``
+in the build container, or the unmodified copies staged under ``oracle/_ref/`` by ``__graft_entry__.build()``
+(git-ignored) on the GPU box.  Nothing under ``-m gpu`` tests or ``smoke()`` calls this; ``bench.py`` uses it only
+as the timed CPU baseline (``--impl reference`` and the ``cpu_baseline`` leg).  It exists to (1) pin
+oracle/lattice.py and oracle/ctc_oracle.c, (2) generate the committed golden vectors
+(tests/golden/generate_golden.py) and (3) be that baseline.
 
 The reference file needs only a handful of Chainer symbols:
 ``chainer.is_debug`` (gram_ctc.py:255), ``chainer.cuda.get_array_module`` (:247,285,311),
@@ -21,7 +23,26 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("B200CTC_REFERENCE_ROOT", "/root/reference")
+# Where the reference lives: the mounted checkout in the build container; on the GPU box (no /root/reference) the
+# unmodified copies of the few files of the path that __graft_entry__.build() staged under oracle/_ref/ (git-ignored,
+# never part of the repository; it travels with the snapshot like the built .so files) -- bench.py's reference arm
+# times the reference's own NumPy path from there.
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("B200CTC_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/asr/loss/gram_ctc.py") else _STAGED)
+STAGED_FILES = ("asr/loss/gram_ctc.py", "asr/error.py", "asr/vocab.py", "asr/utils.py", "asr/nn/layernorm.py")
+
+
+def stage(src_root="/root/reference"):
+    """Copy the reference files of the path, unmodified, into oracle/_ref/ (build container only)."""
+    import shutil
+    if not os.path.isfile(os.path.join(src_root, "asr", "loss", "gram_ctc.py")):
+        return False
+    for rel in STAGED_FILES:
+        dst = os.path.join(_STAGED, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(src_root, rel), dst)
+    return True
 _REF_FILE = os.path.join(REFERENCE_ROOT, "asr", "loss", "gram_ctc.py")
 _module = None
 

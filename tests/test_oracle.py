@@ -120,3 +120,19 @@ def test_greedy_argmax_semantics():
     r = c_oracle.run(0, np.ascontiguousarray(y.transpose(1, 0, 2)), np.zeros((1, 1), np.int32), None, [3], [0], 0,
                      want_grad=False, want_argmax=True)
     assert r["argmax"].tolist() == [[1, 0, 0]]
+
+
+def test_oracle_matches_reference_on_baseline_config_0():
+    """BASELINE configs[0] (B=8, T=200, V=3500, L=40): the reference's own losses and a sample of its gradient
+    (tests/golden/generate_golden_cfg1.py) against the C oracle on the regenerated inputs."""
+    import importlib
+    synth = importlib.import_module("chainer-speech-recognition_b200.synth")
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "full", "cfg1_reference.npz"))
+    B, T, V, L, seed = [int(v) for v in z["shape_seed"]]
+    prob = synth.ctc_problem(B, T, V, L, seed=seed, trained=bool(z["trained"]))
+    r = c_oracle.run(0, prob["x"], prob["labels"], None, prob["input_length"], prob["label_length"], 0)
+    assert np.allclose(r["loss"], z["ref_loss"], rtol=1e-5)
+    # The reference evaluates alpha+beta-total in float32 at |log-probability| ~ 200 (ulp 1.5e-5), so ITS gradient sits
+    # up to ~6.4e-5 from the float64 evaluation of the same algorithm here (SURVEY.md section 0.5): 1e-4 is the
+    # reference's own noise floor at this size, not slack in the oracle.
+    assert np.abs(r["grad"].reshape(-1)[z["sample_index"]] - z["ref_grad_sample"]).max() <= 1e-4
