@@ -6,6 +6,7 @@ The directory name is not a Python identifier; import it with
 
     asr/loss/gram_ctc.py   gram_ctc(...)                                (reference: asr/loss/gram_ctc.py)
     asr/loss/ctc.py        connectionist_temporal_classification(...)   (reference: Chainer's, via run/ctc/*)
+    asr/loss/layernorm_loss.py  layernorm_ctc(...), layernorm_gram_ctc(...)   (reference: asr/nn/layernorm.py + asr/model/cnn.py:41-44 + the loss)
     asr/data/processing.py labels_to_minibatch(...)   (reference: asr/data/processing.py, label half of features_to_minibatch)
     asr/error.py           compute_minibatch_error(...), compute_character_error_rate(...)   (reference: asr/error.py)
     csrc/                  sm_100a kernels + the C ABI (include/b200ctc.h)
@@ -13,12 +14,13 @@ The directory name is not a Python identifier; import it with
 from . import _lib, distributed, synth
 from ._build import build
 from .asr.loss import (gram_ctc, joint_gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
-                       ConnectionistTemporalClassification, greedy_argmax, ctc_host, gram_ctc_host)
+                       ConnectionistTemporalClassification, greedy_argmax, ctc_host, gram_ctc_host,
+                       layernorm_ctc, layernorm_gram_ctc)
 
 from .asr.data import labels_to_minibatch
 from .asr.error import (compute_minibatch_error, compute_character_error_rate, build_expansion_table,
                         minibatch_error_details)
 
-__all__ = ["labels_to_minibatch", "joint_gram_ctc", "compute_minibatch_error", "compute_character_error_rate", "build_expansion_table", "minibatch_error_details",
+__all__ = ["layernorm_ctc", "layernorm_gram_ctc", "labels_to_minibatch", "joint_gram_ctc", "compute_minibatch_error", "compute_character_error_rate", "build_expansion_table", "minibatch_error_details",
            "gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
            "ConnectionistTemporalClassification", "greedy_argmax", "ctc_host", "gram_ctc_host", "build", "distributed", "synth"]

@@ -19,7 +19,7 @@ EXPERIMENT = os.environ.get("B200CTC_EXPERIMENT") == "1"
 _NAME = "libb200ctc_exp" if EXPERIMENT else "libb200ctc"
 SO_PATH = os.path.join(LIBDIR, _NAME + ".so")
 STAMP = os.path.join(LIBDIR, _NAME + ".stamp")
-SOURCES = ["api.cu", "host_cache.cu", "softmax_gather.cu", "lattice.cu", "gradient.cu", "greedy_error.cu"]
+SOURCES = ["api.cu", "host_cache.cu", "softmax_gather.cu", "lattice.cu", "gradient.cu", "greedy_error.cu", "layernorm_loss.cu"]
 HEADERS = ["common.cuh", "kernels.h", "row_ring.cuh", "prep.cuh", os.path.join("..", "..", "include", "b200ctc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"] + (["-DB200CTC_EXPERIMENT"] if EXPERIMENT else [])

@@ -35,11 +35,18 @@ def _bind(lib):
         c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p,
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_float,
         c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_void_p]
-    lib.b200ctc_forward_train.restype = c.c_int
-    lib.b200ctc_forward_train.argtypes = [
+    lib.b200ctc_ln_workspace_bytes.restype = c.c_int
+    lib.b200ctc_ln_workspace_bytes.argtypes = [c.c_int] * 5 + [c.POINTER(c.c_size_t)]
+    lib.b200ctc_ln_forward.restype = c.c_int
+    lib.b200ctc_ln_forward.argtypes = [
+        c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_float, c.c_void_p, c.c_size_t, c.c_uint,
+        c.c_void_p]
+    lib.b200ctc_ln_backward.restype = c.c_int
+    lib.b200ctc_ln_backward.argtypes = [
         c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
-        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_float, c.c_void_p,
-        c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_uint, c.c_void_p]
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_float,
+        c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p]
     lib.b200ctc_greedy_argmax.restype = c.c_int
     lib.b200ctc_greedy_argmax.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_int, c.c_int,
                                           c.c_void_p, c.c_void_p]
@@ -70,6 +77,10 @@ def load():
     ``B200CTC_ALLOW_STALE=1`` says the caller knows."""
     global _lib
     if _lib is not None:
+        return _lib
+    override = os.environ.get("B200CTC_LIB")                 # development: load a specific build of the library
+    if override:
+        _lib = _bind(ctypes.CDLL(override))
         return _lib
     path = _build.SO_PATH
     if not _build.is_current():
@@ -103,6 +114,12 @@ def check(status):
         import torch
         raise torch.cuda.OutOfMemoryError(msg)
     raise B200CTCError(msg)
+
+
+def ln_workspace_bytes(kind, B, T, V, Lmax):
+    out = ctypes.c_size_t(0)
+    check(load().b200ctc_ln_workspace_bytes(kind, B, T, V, Lmax, ctypes.byref(out)))
+    return int(out.value)
 
 
 def workspace_bytes(kind, B, T, V, Lmax):

@@ -117,27 +117,11 @@ class LatticeLossFunction(torch.autograd.Function):
         ptr = lambda t: t.data_ptr() if t is not None else None
         nbytes = _lib.workspace_bytes(kind, B, T, V, Lmax)
         workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
-        # A training step (the activations want a gradient): allocate the gradient buffer now, so that the forward
-        # call can write the zero rows of the padded frames while the lattice recursion is finishing
-        # (include/b200ctc.h, b200ctc_forward_train); backward fills the rest of the same buffer.
-        grad = None
-        if ctx.needs_input_grad[0] and input_length is not None and B * T > 0:
-            grad = torch.empty_like(acts)
-            if grad.stride(2) != 1:
-                grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
         with torch.cuda.device(dev):
-            if grad is not None:
-                _lib.check(lib.b200ctc_forward_train(
-                    kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
-                    ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
-                    loss_scale, ptr(argmax), grad.data_ptr(), grad.stride(0), grad.stride(1),
-                    workspace.data_ptr(), workspace.numel(), _flags(), _stream_ptr(dev)))
-            else:
-                _lib.check(lib.b200ctc_forward(
-                    kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
-                    ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
-                    loss_scale, ptr(argmax), workspace.data_ptr(), workspace.numel(), _flags(), _stream_ptr(dev)))
-        ctx.prefilled_grad = grad
+            _lib.check(lib.b200ctc_forward(
+                kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
+                ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
+                loss_scale, ptr(argmax), workspace.data_ptr(), workspace.numel(), _flags(), _stream_ptr(dev)))
         ctx.kind, ctx.blank, ctx.reduce, ctx.dims = kind, blank, reduce, (B, T, V, Lmax)
         ctx.batch_global = batch_global
         ctx.save_for_backward(acts, labels, bigrams if bigrams is not None else labels, workspace)
@@ -166,13 +150,9 @@ class LatticeLossFunction(torch.autograd.Function):
         per_utt = 0 if ctx.reduce == "mean" else 1
         scale = 1.0 / float(ctx.batch_global) if ctx.reduce == "mean" else 1.0     # :291-294
         big_ptr = bigrams.data_ptr() if ctx.has_bigrams else None
-        # first backward: the buffer whose padded rows the forward call has already zeroed (ownership passes to
-        # autograd, which may keep it as x.grad); a retained graph differentiated again gets a fresh one
-        grad, ctx.prefilled_grad = ctx.prefilled_grad, None
-        if grad is None:
-            grad = torch.empty_like(acts)
-            if grad.stride(2) != 1:
-                grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
+        grad = torch.empty_like(acts)
+        if grad.stride(2) != 1:
+            grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.b200ctc_backward(
                 ctx.kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), big_ptr,

@@ -42,12 +42,6 @@ struct WsHeader {
     unsigned int k3_done;      // gradient warps that ran out of work (last one re-arms the queue)
     unsigned int k2_done;      // lattice CTAs that have published their loss (last one reduces the batch)
     unsigned int k2b_done;     // same for the second (plain CTC) lattice of a joint Gram-CTC + CTC call
-    // b200ctc_forward_train: the rows of padded frames of THIS gradient buffer were zeroed at forward time (while the
-    // lattice recursion was finishing).  The gradient kernel skips them when it is asked to fill exactly this buffer,
-    // and clears the note when it is done: it is good for one backward pass.
-    unsigned int prefill_valid;
-    unsigned long long prefill_grad;
-    long long prefill_stride_t, prefill_stride_b;
 };
 
 // Workspace carve-up (all offsets in bytes from a 16-byte aligned base).

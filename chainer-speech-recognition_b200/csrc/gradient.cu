@@ -43,28 +43,6 @@ __device__ __forceinline__ void zero_row(float *__restrict__ g, int V, int lane)
     if (tail0 + lane < V) g[tail0 + lane] = 0.f;
 }
 
-// Did the training-step forward already zero the padded rows of exactly this gradient buffer (WsHeader, api.cu)?
-__device__ __forceinline__ bool padded_rows_prefilled(const WsHeader *hdr, const GradParams &gp) {
-    return hdr->prefill_valid != 0u && hdr->prefill_grad == (unsigned long long)reinterpret_cast<uintptr_t>(gp.grad_out) &&
-           hdr->prefill_stride_t == (long long)gp.gstride_t && hdr->prefill_stride_b == (long long)gp.gstride_b;
-}
-
-__global__ void __launch_bounds__(kWarpsPerCta * 32) zero_padded_rows_kernel(ProblemDesc d, float *grad, int64_t gstride_t,
-                                                                            int64_t gstride_b, int b_major) {
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const long long warps_total = (long long)gridDim.x * kWarpsPerCta;
-    const long long frames = (long long)d.B * d.T;
-    for (long long f = warp_global; f < frames; f += warps_total) {
-        int b, t;
-        if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
-        else { t = (int)(f / d.B); b = (int)(f % d.B); }
-        int Tb = d.input_lengths ? __ldg(d.input_lengths + b) : d.T;
-        Tb = max(0, min(Tb, d.T));
-        if (t >= Tb) zero_row(grad + (int64_t)t * gstride_t + (int64_t)b * gstride_b, d.V, lane);      // gram_ctc.py:296
-    }
-}
-
 // joint Gram-CTC + CTC: the plain-CTC node that carries the same symbol occurrence as Gram-CTC node j -- unigram
 // node 3i+1 <-> CTC label node 2i+1 (blank nodes are summed separately, bigram nodes have no partner)
 __device__ __forceinline__ float joint_partner(const float *e2_sm, int j, int Nb2) {
@@ -116,7 +94,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     const int *pc_all = reinterpret_cast<const int *>(ws + w.off_pc);
     const int per = d.kind == 0 ? 2 : 3;
     const unsigned frames = (unsigned)d.B * (unsigned)d.T;
-    const bool prefilled = padded_rows_prefilled(hdr, gp);
 
     for (;;) {
         unsigned f = 0;
@@ -128,7 +105,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
         else { t = (int)(f / d.B); b = (int)(f % d.B); }
         float *grow = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
         const UttInfo ui = utt[b];
-        if (t >= ui.Tb) { if (!prefilled) zero_row(grow, d.V, lane); continue; }             // :296
+        if (t >= ui.Tb) { zero_row(grow, d.V, lane); continue; }             // :296
 
         const float *row = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
         const float lse2 = lse_all[(size_t)b * d.T + t];
@@ -224,7 +201,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
     if (lane == 0) {
         __threadfence();
         const unsigned done = atomicAdd(&hdr->k3_done, 1u) + 1u;
-        if (done == gridDim.x * kWarpsPerCta) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; hdr->prefill_valid = 0u; }
+        if (done == gridDim.x * kWarpsPerCta) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; }
     }
 }
 
@@ -233,8 +210,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
 // the frame's alpha and beta rows into a ring slot; a consumer warp turns the row into the gradient in place
 // (softmax * sc, then subtracts the merged posteriors at the <= L+1 label columns -- a plain scatter in
 // shared memory, no bitmap needed) and hands it back to the TMA engine as one bulk store.  Padded frames
-// never touch a consumer: the producer bulk-stores a zero row for them -- unless the training-step forward has
-// already zeroed them in this very buffer (WsHeader::prefill_*), in which case they are skipped altogether.
+// never touch a consumer: the producer bulk-stores a zero row for them.
 // Slot layout: [16-byte aligned span around the V-float row][Np float2 alpha row][Np float2 beta row].
 // ---------------------------------------------------------------------------------------------
 // Store a row image that sits in shared memory at the same 16-byte phase as its destination: the aligned body as
@@ -267,7 +243,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     float *post_all = zero_row + ((d.V + 4 + 3) & ~3);
     for (int i = threadIdx.x; i < d.V + 4; i += blockDim.x) zero_row[i] = 0.f;
     fence_proxy_async_smem();
-    const bool prefilled = padded_rows_prefilled(hdr, gp);
     __syncthreads();
 
     if (warp == 0) {
@@ -286,45 +261,50 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                 if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
                 else { t = (int)(f / d.B); b = (int)(f % d.B); }
                 if (t >= utt[b].Tb) {                                                // :296 -- zeros, straight from smem
-                    if (!prefilled) {
-                        float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
-                        store_row_image(dst, zero_row + row_misalignment(dst), d.V);
-                    }
+                    float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
+                    store_row_image(dst, zero_row + row_misalignment(dst), d.V);
                 } else {
                     need = true;
                 }
             }
             const unsigned mask = __ballot_sync(0xffffffffu, need);
-            if (need) {
-                const unsigned myq = q + (unsigned)__popc(mask & ((1u << lane) - 1u));
-                const int s = ring_claim(ring, myq);
-                const float *src = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
-                const int off = row_misalignment(src);
-                const uint32_t span = row_span_bytes(off, d.V);
-                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0; ring.meta[s].off = off;
-                ring_publish(ring, s, myq);
-                mbar_arrive_expect_tx(&ring.full[s], span + 2 * ab_bytes + 2 * ab2_bytes);
-                bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
-                bulk_g2s(ring.slot(s) + span_max, av_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
-                bulk_g2s(ring.slot(s) + span_max + ab_bytes, bv_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
-                if (w.joint) {
-                    const float2 *av2 = reinterpret_cast<const float2 *>(ws + w.off_av2) + ((size_t)b * d.T + t) * w.Np2;
-                    const float2 *bv2 = reinterpret_cast<const float2 *>(ws + w.off_bv2) + ((size_t)b * d.T + t) * w.Np2;
-                    bulk_g2s(ring.slot(s) + span_max + 2 * ab_bytes, av2, ab2_bytes, &ring.full[s]);
-                    bulk_g2s(ring.slot(s) + span_max + 2 * ab_bytes + ab2_bytes, bv2, ab2_bytes, &ring.full[s]);
+            const unsigned myq = q + (unsigned)__popc(mask & ((1u << lane) - 1u));
+            // every lane issues its row as soon as ITS slot is free, in whatever order the consumers hand slots back
+            bool pending = need;
+            while (__any_sync(0xffffffffu, pending)) {
+                bool issued = false;
+                if (pending && ring_slot_free(ring, myq)) {
+                    const int s = (int)(myq % (unsigned)ring.slots);
+                    const float *src = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
+                    const int off = row_misalignment(src);
+                    const uint32_t span = row_span_bytes(off, d.V);
+                    ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0; ring.meta[s].off = off;
+                    ring_publish(ring, s, myq);
+                    mbar_arrive_expect_tx(&ring.full[s], span + 2 * ab_bytes + 2 * ab2_bytes);
+                    bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
+                    bulk_g2s(ring.slot(s) + span_max, av_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
+                    bulk_g2s(ring.slot(s) + span_max + ab_bytes, bv_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
+                    if (w.joint) {
+                        const float2 *av2 = reinterpret_cast<const float2 *>(ws + w.off_av2) + ((size_t)b * d.T + t) * w.Np2;
+                        const float2 *bv2 = reinterpret_cast<const float2 *>(ws + w.off_bv2) + ((size_t)b * d.T + t) * w.Np2;
+                        bulk_g2s(ring.slot(s) + span_max + 2 * ab_bytes, av2, ab2_bytes, &ring.full[s]);
+                        bulk_g2s(ring.slot(s) + span_max + 2 * ab_bytes + ab2_bytes, bv2, ab2_bytes, &ring.full[s]);
+                    }
+                    pending = false;
+                    issued = true;
                 }
+                if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
             }
             q += (unsigned)__popc(mask);
         }
         ring_stop(ring, q, lane);
         bulk_wait_all<0>();
         B200CTC_TL_K3(true);
-        // re-arm the queue for a possible second backward over the same workspace; the prefill note was good for
-        // this one pass only (the buffer now belongs to the caller)
+        // re-arm the queue for a possible second backward over the same workspace
         if (lane == 0) {
             __threadfence();
             const unsigned done = atomicAdd(&hdr->k3_done, 1u) + 1u;
-            if (done == gridDim.x) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; hdr->prefill_valid = 0u; }
+            if (done == gridDim.x) { hdr->k3_ticket = 0u; hdr->k3_done = 0u; }
         }
         return;
     }
@@ -415,30 +395,28 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         }
         __syncwarp();
         for (int u = lane; u < ui.Ub; u += 32) row[__ldg(usym + u)] -= post_sm[u];     // distinct columns (:290)
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            store_row_image(gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b, row, d.V);
-            bulk_wait_read<0>();                 // the TMA engine has read the slot: hand it back to the producer
-            mbar_arrive(&ring.empty[s]);
+        float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
+        if (row_misalignment(dst) == m.off) {                                // warp-uniform
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                store_row_image(dst, row, d.V);
+                bulk_wait_read<0>();             // the TMA engine has read the slot: hand it back to the producer
+                mbar_arrive(&ring.empty[s]);
+            }
+        } else {
+            // activation row and gradient row sit at different 16-byte phases (different pitches): the image in the
+            // slot cannot be bulk-stored, the warp writes it with ordinary coalesced stores
+            __syncwarp();
+            for (int i = lane; i < d.V; i += 32) dst[i] = row[i];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[s]);
         }
     }
     if (lane == 0) bulk_wait_all<0>();
 }
 
 }  // namespace
-
-cudaError_t launch_zero_padded_rows(const ProblemDesc &d, float *grad, int64_t gstride_t, int64_t gstride_b,
-                                    cudaStream_t stream) {
-    const long long frames = (long long)d.B * d.T;
-    if (frames == 0 || !d.input_lengths) return cudaSuccess;
-    long long ctas = (frames + kWarpsPerCta - 1) / kWarpsPerCta;
-    const long long cap = (long long)sm_count() * 4;
-    if (ctas > cap) ctas = cap;
-    const int b_major = gstride_b > gstride_t ? 1 : 0;
-    zero_padded_rows_kernel<<<(int)ctas, kWarpsPerCta * 32, 0, stream>>>(d, grad, gstride_t, gstride_b, b_major);
-    return cudaGetLastError();
-}
 
 cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream) {
     const long long frames = (long long)g.d.B * g.d.T;

@@ -23,6 +23,10 @@ int g_nfuncs = 0;
 std::mutex g_mu;
 }  // namespace
 
+namespace { thread_local const char *g_where = ""; }
+void note_failure_site(const char *where) { g_where = where; }
+const char *failure_site() { const char *w = g_where; g_where = ""; return w; }
+
 int current_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -28,6 +28,9 @@ struct RingLayout;
 bool ring_usable(const void *base, int64_t stride_t, int64_t stride_b, int V, const RingLayout &rl);
 
 // ---- host-side caches (host_cache.cu): nothing below costs a driver call after its first use ----
+// a launcher that fails names the step that failed; api.cu appends it to the error message
+void note_failure_site(const char *where);
+const char *failure_site();
 int current_device();
 int sm_count();                                                        // per device
 // opt-in dynamic shared memory + maximum carve-out for `func`; cudaFuncSetAttribute only when more is needed than before
@@ -75,10 +78,21 @@ struct GradParams {
     int64_t gstride_t, gstride_b;
 };
 cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *ws, cudaStream_t stream);
-// zero rows of the padded frames (t >= input_lengths[b]) of a gradient buffer (gram_ctc.py:296); launched by the
-// training-step forward while the lattice recursion is finishing, see api.cu
-cudaError_t launch_zero_padded_rows(const ProblemDesc &d, float *grad, int64_t gstride_t, int64_t gstride_b,
-                                    cudaStream_t stream);
+// LayerNormalization fused into the loss (layernorm_loss.cu): the kernels read the model's last
+// convolution output z (B, V, T) in place instead of the normalised, transposed copy the reference hands to the loss
+constexpr int kLnMaxParts = 160;          // CTAs of the backward kernel (>= SM count): rows of the dgamma/dbeta partial sums
+struct LnLayout {
+    WsLayout w;                           // the regular workspace ...
+    size_t off_mu, off_rstd, off_part;    // ... + per-frame mean and 1/std, per-CTA dgamma/dbeta partial rows
+    size_t total;
+};
+LnLayout make_ln_layout(int kind, int B, int T, int V, int Lmax);
+int ln_supported(int kind, int B, int T, int V, int Lmax, int64_t zs_v, int64_t zs_b, const void *z);
+cudaError_t launch_ln_forward(const ProblemDesc &d, const LnLayout &ll, void *ws, const float *z, int64_t zs_b, int64_t zs_v,
+                              const float *gamma, const float *beta, size_t smem_reserve, cudaStream_t stream);
+cudaError_t launch_ln_backward(const GradParams &g, const LnLayout &ll, const void *ws, const float *z, int64_t zs_b,
+                               int64_t zs_v, const float *gamma, const float *beta, float *dz, int64_t dzs_b, int64_t dzs_v,
+                               float *dgamma, float *dbeta, cudaStream_t stream);
 
 // evaluation path: greedy collapse + gram expansion + edit distance + error rate (greedy_error.cu)
 cudaError_t launch_greedy_error(const int64_t *argmax, const int32_t *input_lengths, int B, int T, const int32_t *labels,

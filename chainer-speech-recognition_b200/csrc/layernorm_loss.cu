@@ -1,0 +1,889 @@
+// layernorm_loss.cu -- LayerNormalization fused into the loss.
+//
+// In the reference every CTC / Gram-CTC model ends in Convolution2D(.., vocab_size, ksize=1) -> LayerNormalization
+// (run/ctc/cnn/model.py:85-88): the convolution output z is (B, V, 1, T), NormalizeLayer normalises every frame over
+// the vocabulary axis (asr/nn/layernorm.py:33-46: mean and std over axes (1,2), no epsilon), gamma/beta scale and
+// shift along axis 1 (asr/nn/nn.py:265), and AcousticModel.__call__ then makes a TRANSPOSED COPY of the whole tensor --
+// swapaxes(1,3), reshape, split_axis into T arrays of (B,V) (asr/model/cnn.py:41-44) -- before the loss reads it.
+// Backward undoes all of it.  Per activation element that is ~48 bytes of HBM traffic around a 12-byte loss.
+//
+// Here the loss kernels read z where it lies, T-contiguous, as 2-D tiles moved by the TMA engine
+// (cp.async.bulk.tensor, SASS UTMALDG): a tile is all V vocabulary rows x 8 consecutive frames of one utterance,
+// split into boxes of 240 rows (7.5 KB; a TMA box dimension is at most 256) that land in a shared-memory ring.  A frame's vocabulary
+// is then spread over the CTA -- thread (warp w of 15, lane) owns rows 240k + 16w + lane/2 (k = 0..K-1) and four of the
+// eight frames -- so per-frame statistics are reductions over threads (shuffles inside a warp, shared memory
+// between warps) and everything per element happens in registers:
+//   forward  (ln_softmax_gather_kernel): one read of z.  Mean / centred second moment of every frame (Chan's
+//            pairwise update, so one reduction round), the softmax statistics of a = gamma*(z-mean)*rstd + beta
+//            (per-thread max and sum, merged as (max, sum) pairs: the second round), the emission probabilities of
+//            the lattice's symbols.  Writes mean, rstd, log2-normaliser and the emission rows; the alpha/beta
+//            recursion (lattice.cu) runs unchanged, next to this kernel.
+//   backward (ln_gradient_kernel): one read of z, one write of dz, in z's own layout.  Sweep 1 re-forms the softmax,
+//            subtracts the merged posteriors (gram_ctc.py:284-297), multiplies by gamma and accumulates the two
+//            per-frame sums LayerNormalization's backward needs (asr/nn/layernorm.py:48-60) while dgamma/dbeta
+//            accumulate per thread over all tiles (a thread's rows never change); sweep 2 re-reads z from the ring
+//            (it is still there) and stores dz = rstd * (dn - mean_v(dn) - n * mean_v(dn*n)).
+// 12 bytes per element again -- for the loss AND the normalisation AND both transposes.
+//
+// Limits of this version: V <= 4080 (a tile must stay resident in shared memory in the backward kernel: 17 boxes),
+// rows of z 16-byte aligned (T_pitch % 4 == 0 -- a TMA requirement), at most 480 emission columns.  Outside them the
+// entry points return B200CTC_UNSUPPORTED and the caller uses the unfused path.
+#include <cuda.h>
+#include <stdio.h>
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "prep.cuh"
+
+namespace b200ctc {
+
+namespace {
+
+constexpr int kLnWarps = 15;                               // compute warps: with the producer warp 512 threads, i.e. 128 registers each
+constexpr int kLnThreads = 32 * (kLnWarps + 1);            // + the producer warp
+constexpr int kLnTT = 8;                                   // frames per tile
+constexpr int kLnBoxRows = 16 * kLnWarps;                  // 240 rows: one step of every compute warp
+constexpr uint32_t kLnBoxBytes = kLnBoxRows * kLnTT * 4;   // 7.5 KB
+constexpr int kLnMetaRing = 64;                            // >= ring slots: a padded tile takes one slot and one record
+constexpr int kLnMaxCols = 32 * kLnWarps;                  // emission columns one tile pass can gather: one per compute thread
+
+struct LnTileMeta { int b, t0, kind, pad; };               // kind 0: work, 1: padded frames only (backward), -1: stop
+
+struct LnSmem {
+    size_t off_ring, off_full, off_empty, off_meta, off_red, off_tot, off_ab, off_abbar, off_post, off_gb, off_bm, total;
+    int R;
+};
+
+// ring of R boxes + everything else a kernel needs; ab_bytes / post_floats / gb_floats / bm_words are 0 in the forward kernel
+LnSmem plan_ln_smem(int K, size_t ab_bytes, size_t post_floats, size_t gb_floats, size_t bm_words, size_t smem_reserve = 0) {
+    LnSmem s;
+    size_t o = 0;
+    s.off_full = o;  o += 8 * 64;
+    s.off_empty = o; o += 8 * 64;
+    s.off_abbar = o; o += 16;
+    s.off_meta = o;  o += sizeof(LnTileMeta) * kLnMetaRing;
+    s.off_red = o;   o += sizeof(float) * 16 * kLnTT * 4;
+    s.off_tot = o;   o += sizeof(float) * kLnTT * 8;
+    s.off_post = o;  o += sizeof(float) * post_floats;
+    s.off_gb = o;    o += sizeof(float) * gb_floats;
+    s.off_bm = o;    o += sizeof(unsigned) * bm_words;
+    o = align_up(o, 128);
+    s.off_ab = o;    o += align_up(ab_bytes, 128);
+    s.off_ring = o;
+    const long long room = (smem_reserve ? 228 * 1024 - 2 * 1024 - (long long)smem_reserve : 227 * 1024) - (long long)o;
+    int R = (int)(room / (long long)kLnBoxBytes);
+    if (R > 64) R = 64;
+    s.R = R;
+    s.total = o + (size_t)(R > 0 ? R : 0) * kLnBoxBytes;
+    (void)K;
+    return s;
+}
+
+__device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *map, int t0, int v0, int b, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(t0), "r"(v0), "r"(b), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kLnWarps) : "memory"); }
+
+// ---- tile order ----
+// Tiles that share 128-byte lines of z (four consecutive 8-frame blocks of one utterance) get consecutive tickets,
+// so that the SMs working on them touch those lines at about the same time; groups of four walk the time axis from
+// both ends (the alpha CTAs of the lattice kernel consume frames in ascending, the beta CTAs in descending order).
+__device__ __forceinline__ bool ln_tile_of_ticket(unsigned f, int B, int nTB, bool two_ended, int &b, int &tb) {
+    const int sub = (int)(f & 3u);
+    const unsigned q = f >> 2;
+    b = (int)(q % (unsigned)B);
+    const int gs = (int)(q / (unsigned)B);
+    const int g = !two_ended ? gs : (gs & 1) ? ((nTB + 3) / 4 - 1 - (gs >> 1)) : (gs >> 1);
+    tb = 4 * g + sub;
+    return tb < nTB;
+}
+
+// ---- reductions of four per-frame values over the 16 lanes that share this lane's half (lane bits 1..4) ----
+// Transposed: after the first two exchanges every lane carries ONE frame (index 2*bit1 + bit2 of its half), so the
+// whole thing takes 5 merges instead of 16.  `merge(a, b)` combines two partial results.
+template <typename T, typename F>
+__device__ __forceinline__ T reduce_frames16(T x0, T x1, T x2, T x3, int lane, F merge, int &frame_in_half) {
+    const bool b1 = (lane >> 1) & 1, b2 = (lane >> 2) & 1;
+    T k0 = b1 ? x2 : x0, k1 = b1 ? x3 : x1;           // kept
+    T s0 = b1 ? x0 : x2, s1 = b1 ? x1 : x3;           // sent to lane ^ 2
+    k0 = merge(k0, T::shfl_xor(s0, 2));
+    k1 = merge(k1, T::shfl_xor(s1, 2));
+    T k = b2 ? k1 : k0, s = b2 ? k0 : k1;
+    k = merge(k, T::shfl_xor(s, 4));
+    k = merge(k, T::shfl_xor(k, 8));
+    k = merge(k, T::shfl_xor(k, 16));
+    frame_in_half = 2 * (int)b1 + (int)b2;
+    return k;
+}
+
+struct Moments {                      // count, mean, centred second moment (Chan et al.)
+    float n, mean, m2;
+    static __device__ __forceinline__ Moments shfl_xor(const Moments &a, int o) {
+        Moments r;
+        r.n = __shfl_xor_sync(0xffffffffu, a.n, o);
+        r.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
+        r.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
+        return r;
+    }
+};
+__device__ __forceinline__ Moments merge_moments(const Moments &a, const Moments &b) {
+    Moments r;
+    r.n = a.n + b.n;
+    const float inv = r.n > 0.f ? __fdividef(1.f, r.n) : 0.f;
+    const float d = b.mean - a.mean;
+    r.mean = fmaf(d, b.n * inv, a.mean);
+    r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n * inv);
+    return r;
+}
+struct MaxSum {                       // running maximum (natural units) and sum of 2^((x - max) * log2 e)
+    float m, s;
+    static __device__ __forceinline__ MaxSum shfl_xor(const MaxSum &a, int o) {
+        MaxSum r;
+        r.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+        r.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+        return r;
+    }
+};
+__device__ __forceinline__ MaxSum merge_maxsum(const MaxSum &a, const MaxSum &b) {
+    MaxSum r;
+    r.m = fmaxf(a.m, b.m);
+    const float fa = a.m == -INFINITY ? 0.f : ex2_approx((a.m - r.m) * LOG2E_HI);
+    const float fb = b.m == -INFINITY ? 0.f : ex2_approx((b.m - r.m) * LOG2E_HI);
+    r.s = a.s * fa + b.s * fb;
+    return r;
+}
+struct Pair2 {                        // two plain sums
+    float a, b;
+    static __device__ __forceinline__ Pair2 shfl_xor(const Pair2 &x, int o) {
+        Pair2 r;
+        r.a = __shfl_xor_sync(0xffffffffu, x.a, o);
+        r.b = __shfl_xor_sync(0xffffffffu, x.b, o);
+        return r;
+    }
+};
+__device__ __forceinline__ Pair2 merge_pair2(const Pair2 &x, const Pair2 &y) { return Pair2{x.a + y.a, x.b + y.b}; }
+
+// log2 normaliser as an unevaluated pair, emission probability as (mantissa, exponent): same arithmetic as the row
+// kernels (softmax_gather.cu), restated here because those helpers are file-local there
+__device__ __forceinline__ void ln_split_lse2(float m, float s, float &la, float &lb) {
+    const float mh = m * LOG2E_HI;
+    float ml = fmaf(m, LOG2E_HI, -mh);
+    ml = fmaf(m, LOG2E_LO, ml);
+    const float lg = log2f(s);
+    const float a = mh + lg;
+    const float bb = a - mh;
+    const float err = (mh - (a - bb)) + (lg - bb);
+    la = a;
+    lb = err + ml;
+}
+__device__ __forceinline__ float2 ln_emission_pair(float x, float la, float lb) {
+    const float ph = x * LOG2E_HI;
+    float pl = fmaf(x, LOG2E_HI, -ph);
+    pl = fmaf(x, LOG2E_LO, pl);
+    const float dd = ph - la;
+    const float bb = dd - ph;
+    const float err = (ph - (dd - bb)) + (-la - bb);
+    const float lo_full = (err + pl) - lb;
+    const float hi = rintf(dd);
+    const float lo = (dd - hi) + lo_full;
+    if (dd < SENT_TEST) return make_float2(0.f, SENT);
+    return make_float2(exp2f(lo), hi);
+}
+
+struct LnParams {
+    ProblemDesc d;                  // d.acts unused; kind/B/T/V/Lmax/blank/labels/bigrams/lengths/progress as usual
+    WsLayout w;
+    unsigned char *ws;
+    const float *z;                 // (B, V, T): element (b, v, t) at z[b*zs_b + v*zs_v + t]
+    int64_t zs_b, zs_v;
+    const float *gamma, *beta;
+    size_t off_mu, off_rstd, off_part;
+    int K;                          // boxes per tile = ceil(V / 256)
+    int nTB;                        // 8-frame blocks = ceil(T / 8)
+    int R;                          // ring slots
+    // backward only
+    const float *grad_loss;
+    int per_utterance;
+    float scale;
+    float *dz;
+    int64_t dzs_b, dzs_v;
+    float *dgamma, *dbeta;
+};
+
+// ---- producer warp: tickets -> tile records -> TMA box loads, as far ahead as the ring allows ----
+// BACKWARD: tile i of the kernel goes to CTA i % gridDim.x (a fixed assignment makes the dgamma/dbeta sums
+// deterministic); forward: tiles are drawn from the global ticket counter (variable-length utterances balance
+// themselves, and the order serves the lattice kernel running next to it).
+template <bool BACKWARD>
+__device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const LnParams &p, unsigned char *smem, const LnSmem &sm) {
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + sm.off_full);
+    uint64_t *empty = reinterpret_cast<uint64_t *>(smem + sm.off_empty);
+    uint64_t *abbar = reinterpret_cast<uint64_t *>(smem + sm.off_abbar);          // [0] full, [1] empty
+    LnTileMeta *metas = reinterpret_cast<LnTileMeta *>(smem + sm.off_meta);
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(p.ws + p.w.off_hdr);
+    const UttInfo *utt = reinterpret_cast<const UttInfo *>(p.ws + p.w.off_utt);
+    const unsigned tiles = (unsigned)p.d.B * (unsigned)(((p.nTB + 3) / 4) * 4);
+    const unsigned R = (unsigned)p.R;
+    const int K = p.K;
+    unsigned box = 0, seq = 0, n_ab = 0;             // boxes / tile records / alpha-beta loads issued by this CTA
+    auto claim = [&](unsigned bx) {                  // wait until the box slot's previous occupant was released
+        if (bx >= R) mbar_wait(&empty[bx % R], ((bx / R) - 1u) & 1u);
+        return (int)(bx % R);
+    };
+    unsigned f = BACKWARD ? blockIdx.x : atomicAdd(&hdr->k1_ticket, 1u);
+    while (f < tiles) {
+        const unsigned fnext = BACKWARD ? f + gridDim.x : atomicAdd(&hdr->k1_ticket, 1u);     // in flight while we issue
+        int b, tb;
+        const bool real = ln_tile_of_ticket(f, p.d.B, p.nTB, !BACKWARD && (p.d.progress & 2) != 0, b, tb);
+        f = fnext;
+        if (!real) continue;
+        const int t0 = tb * kLnTT;
+        int Tb;
+        if (BACKWARD) Tb = utt[b].Tb;
+        else { Tb = p.d.input_lengths ? __ldg(p.d.input_lengths + b) : p.d.T; Tb = max(0, min(Tb, p.d.T)); }
+        const bool padded = t0 >= Tb;
+        if (padded && !BACKWARD) continue;            // forward: frames nobody reads
+        // the tile record travels with the tile's first box (a padded tile takes a box slot that carries no data)
+        const int slot0 = claim(box);
+        LnTileMeta &m = metas[seq % kLnMetaRing];
+        m.b = b; m.t0 = t0; m.kind = padded ? 1 : 0;
+        ++seq;
+        if (padded) {
+            mbar_arrive(&full[slot0]);
+            ++box;
+            continue;
+        }
+        if (BACKWARD) {
+            // alpha and beta rows of the tile's frames: contiguous in the workspace ([b][t][Np])
+            const int nfr = min(kLnTT, p.d.T - t0);
+            const uint32_t bytes = (uint32_t)nfr * (uint32_t)p.w.Np * 8u;
+            if (n_ab > 0) mbar_wait(&abbar[1], (n_ab - 1u) & 1u);
+            ++n_ab;
+            const float2 *av = reinterpret_cast<const float2 *>(p.ws + p.w.off_av) + ((size_t)b * p.d.T + t0) * p.w.Np;
+            const float2 *bv = reinterpret_cast<const float2 *>(p.ws + p.w.off_bv) + ((size_t)b * p.d.T + t0) * p.w.Np;
+            mbar_arrive_expect_tx(&abbar[0], 2 * bytes);
+            bulk_g2s(smem + sm.off_ab, av, bytes, &abbar[0]);
+            bulk_g2s(smem + sm.off_ab + (size_t)kLnTT * p.w.Np * 8, bv, bytes, &abbar[0]);
+        }
+        for (int k = 0; k < K; ++k, ++box) {
+            const int slot = k == 0 ? slot0 : claim(box);
+            mbar_arrive_expect_tx(&full[slot], kLnBoxBytes);
+            tma_load_box(smem + sm.off_ring + (size_t)slot * kLnBoxBytes, tmap, t0, k * kLnBoxRows, b, &full[slot]);
+        }
+    }
+    const int slot0 = claim(box);                    // stop record
+    metas[seq % kLnMetaRing].kind = -1;
+    mbar_arrive(&full[slot0]);
+}
+
+// cross-warp stage of a per-frame reduction: the lanes that carry a warp's result for frame f write it to
+// red[f][w][0..NV), everybody meets, warp f (< 8) merges the 16 partials of frame f and lane 0 of it finalises.
+template <int NV>
+__device__ __forceinline__ void red_store(float *red, int f, int w, const float (&v)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[(f * 16 + w) * 4 + i] = v[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+// 104 registers per thread: 512 threads then leave 12K of the SM's 64K registers to a lattice CTA, which runs next
+// to this kernel exactly as it runs next to the row kernel (api.cu)
+template <int KMAX>
+__global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                                            LnParams p, LnSmem sm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + sm.off_full);
+    uint64_t *empty = reinterpret_cast<uint64_t *>(smem + sm.off_empty);
+    LnTileMeta *metas = reinterpret_cast<LnTileMeta *>(smem + sm.off_meta);
+    float *red = reinterpret_cast<float *>(smem + sm.off_red);
+    float *tot = reinterpret_cast<float *>(smem + sm.off_tot);
+    const uint32_t ring = smem_u32(smem + sm.off_ring);
+    const float *gb = reinterpret_cast<const float *>(smem + sm.off_gb);
+    const ProblemDesc &d = p.d;
+    const unsigned R = (unsigned)p.R;
+    const int K = p.K;
+    const int Vp = K * kLnBoxRows;
+    if (threadIdx.x == 0) {
+        for (unsigned i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kLnWarps); }
+        mbar_init_fence();
+    }
+    for (int i = threadIdx.x; i < Vp; i += blockDim.x) {
+        reinterpret_cast<float *>(smem + sm.off_gb)[i] = i < d.V ? __ldg(p.gamma + i) : 0.f;
+        reinterpret_cast<float *>(smem + sm.off_gb)[Vp + i] = i < d.V ? __ldg(p.beta + i) : 0.f;
+    }
+    __syncthreads();
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (w == kLnWarps) {
+        if (lane == 0) ln_producer<false>(&tmap, p, smem, sm);
+        return;
+    }
+    const int r = lane >> 1, h = lane & 1;
+    int nrows = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) nrows += (k < K && kLnBoxRows * k + 16 * w + r < d.V) ? 1 : 0;
+    const float fn = (float)nrows, inv_n = nrows > 0 ? 1.f / (float)nrows : 0.f;
+    float *mu_out = reinterpret_cast<float *>(p.ws + p.off_mu);
+    float *rstd_out = reinterpret_cast<float *>(p.ws + p.off_rstd);
+    float *lse_out = reinterpret_cast<float *>(p.ws + p.w.off_lse);
+    float2 *lp_out = reinterpret_cast<float2 *>(p.ws + p.w.off_lp);
+    const int tid = threadIdx.x;
+
+    unsigned box = 0, seq = 0;
+    for (;;) {
+        mbar_wait(&full[box % R], (box / R) & 1u);
+        const LnTileMeta m = metas[seq % kLnMetaRing];
+        ++seq;
+        if (m.kind < 0) break;
+        int Tb = d.input_lengths ? __ldg(d.input_lengths + m.b) : d.T;
+        Tb = max(0, min(Tb, d.T));
+        int Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
+        Lb = max(0, min(Lb, d.Lmax));
+        const int ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
+        // ---- the tile into registers: rows 256k + 16w + r, frames 4h .. 4h+3 ----
+        float4 z[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < K) {
+                const unsigned bx = box + (unsigned)k;
+                if (k > 0) mbar_wait(&full[bx % R], (bx / R) & 1u);
+                z[k] = lds128(ring + (bx % R) * kLnBoxBytes + (uint32_t)(w * 512 + lane * 16));
+            }
+        }
+        // ---- the rows of the symbols the lattice can emit: thread c takes column c (gram_ctc.py:24-32, :155) ----
+        int sym = -1;
+        float4 zs0 = make_float4(0.f, 0.f, 0.f, 0.f), zs1 = zs0;
+        float gs = 0.f, bs = 0.f;
+        if (tid < ncol) {
+            if (tid == 0) sym = d.blank;
+            else if (tid <= d.Lmax) sym = (tid - 1 < Lb) ? __ldg(d.labels + (size_t)m.b * d.Lmax + tid - 1) : -1;
+            else sym = __ldg(d.bigrams + (size_t)m.b * d.Lmax + tid - 1 - d.Lmax);
+            if (sym >= 0 && sym < d.V) {
+                const unsigned bx = box + (unsigned)(sym / kLnBoxRows);
+                const uint32_t a = ring + (bx % R) * kLnBoxBytes + (uint32_t)((sym % kLnBoxRows) * 32);
+                zs0 = lds128(a);
+                zs1 = lds128(a + 16);
+                gs = __ldg(p.gamma + sym);
+                bs = __ldg(p.beta + sym);
+            } else {
+                sym = -1;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int k = 0; k < K; ++k) mbar_arrive(&empty[(box + (unsigned)k) % R]);      // the boxes can be refilled
+        }
+        box += (unsigned)K;
+
+        // ---- round 1: mean and centred second moment of every frame (asr/nn/layernorm.py:41-44) ----
+        Moments mo[4];
+        {
+            float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) { sx += z[k].x; sy += z[k].y; sz += z[k].z; sw += z[k].w; }      // rows >= V are zeros
+            mo[0].mean = sx * inv_n; mo[1].mean = sy * inv_n; mo[2].mean = sz * inv_n; mo[3].mean = sw * inv_n;
+            float qx = 0.f, qy = 0.f, qz = 0.f, qw = 0.f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const bool ok = k < K && kLnBoxRows * k + 16 * w + r < d.V;
+                const float dx = z[k].x - mo[0].mean, dy = z[k].y - mo[1].mean, dz = z[k].z - mo[2].mean, dw = z[k].w - mo[3].mean;
+                if (ok) { qx = fmaf(dx, dx, qx); qy = fmaf(dy, dy, qy); qz = fmaf(dz, dz, qz); qw = fmaf(dw, dw, qw); }
+            }
+            mo[0].m2 = qx; mo[1].m2 = qy; mo[2].m2 = qz; mo[3].m2 = qw;
+            mo[0].n = mo[1].n = mo[2].n = mo[3].n = fn;
+        }
+        int fih;
+        const Moments mr = reduce_frames16(mo[0], mo[1], mo[2], mo[3], lane, merge_moments, fih);
+        if (lane < 8) { const float v3[3] = {mr.n, mr.mean, mr.m2}; red_store<3>(red, 4 * h + fih, w, v3); }
+        bar_compute();
+        if (w < kLnTT) {
+            Moments a;
+            const float *src = red + (w * 16 + (lane & 15)) * 4;
+            a.n = src[0]; a.mean = src[1]; a.m2 = src[2];
+            if ((lane & 15) >= kLnWarps) { a.n = 0.f; a.mean = 0.f; a.m2 = 0.f; }
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) a = merge_moments(a, Moments::shfl_xor(a, o));
+            if (lane == 0) {
+                const float var = a.m2 / a.n;                                  // sum(diff^2) / size, no epsilon (:44)
+                const float rstd = 1.f / sqrtf(var);
+                tot[w * 8 + 0] = a.mean;
+                tot[w * 8 + 1] = rstd;
+                const int t = m.t0 + w;
+                if (t < Tb) { mu_out[(size_t)m.b * d.T + t] = a.mean; rstd_out[(size_t)m.b * d.T + t] = rstd; }
+            }
+        }
+        bar_compute();
+        float mu[4], rs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mu[j] = tot[(4 * h + j) * 8 + 0]; rs[j] = tot[(4 * h + j) * 8 + 1]; }
+
+        // ---- round 2: softmax statistics of a = gamma * (z - mean) * rstd + beta (asr/nn/nn.py:265) ----
+        MaxSum ms[4];
+        {
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const bool ok = k < K && kLnBoxRows * k + 16 * w + r < d.V;
+                const float zz[4] = {z[k].x, z[k].y, z[k].z, z[k].w};
+                const float gk = k < K ? gb[kLnBoxRows * k + 16 * w + r] : 0.f, bk = k < K ? gb[Vp + kLnBoxRows * k + 16 * w + r] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = fmaf((zz[j] - mu[j]) * rs[j], gk, bk);
+                    if (ok) mx[j] = fmaxf(mx[j], a);
+                }
+            }
+            float sm_[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const bool ok = k < K && kLnBoxRows * k + 16 * w + r < d.V;
+                const float zz[4] = {z[k].x, z[k].y, z[k].z, z[k].w};
+                const float gk = k < K ? gb[kLnBoxRows * k + 16 * w + r] : 0.f, bk = k < K ? gb[Vp + kLnBoxRows * k + 16 * w + r] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = fmaf((zz[j] - mu[j]) * rs[j], gk, bk);
+                    if (ok) sm_[j] += ex2_approx((a - mx[j]) * LOG2E_HI);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ms[j].m = mx[j]; ms[j].s = sm_[j]; }
+        }
+        const MaxSum sr = reduce_frames16(ms[0], ms[1], ms[2], ms[3], lane, merge_maxsum, fih);
+        if (lane < 8) { const float v2[2] = {sr.m, sr.s}; red_store<2>(red, 4 * h + fih, w, v2); }
+        bar_compute();
+        if (w < kLnTT) {
+            MaxSum a;
+            const float *src = red + (w * 16 + (lane & 15)) * 4;
+            a.m = src[0]; a.s = src[1];
+            if ((lane & 15) >= kLnWarps) { a.m = -INFINITY; a.s = 0.f; }
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) a = merge_maxsum(a, MaxSum::shfl_xor(a, o));
+            if (lane == 0) {
+                float la, lb;
+                ln_split_lse2(a.m, a.s, la, lb);
+                tot[w * 8 + 2] = la;
+                tot[w * 8 + 3] = lb;
+                const int t = m.t0 + w;
+                if (t < Tb) lse_out[(size_t)m.b * d.T + t] = la + lb;
+            }
+        }
+        bar_compute();
+
+        // ---- emission probabilities of the lattice's symbols ----
+        if (tid < ncol) {
+            const float zz[8] = {zs0.x, zs0.y, zs0.z, zs0.w, zs1.x, zs1.y, zs1.z, zs1.w};
+#pragma unroll
+            for (int f = 0; f < kLnTT; ++f) {
+                const int t = m.t0 + f;
+                if (t < Tb) {
+                    float2 v = make_float2(0.f, SENT);
+                    if (sym >= 0) {
+                        const float a = fmaf((zz[f] - tot[f * 8 + 0]) * tot[f * 8 + 1], gs, bs);
+                        v = ln_emission_pair(a, tot[f * 8 + 2], tot[f * 8 + 3]);
+                    }
+                    lp_out[((size_t)m.b * d.T + t) * p.w.W + tid] = v;
+                }
+            }
+        }
+        bar_compute();            // rows stored; also protects red/tot against the next tile
+        if (tid == 0 && (d.progress & 1)) {
+            const int nvalid = min(kLnTT, Tb - m.t0);
+            unsigned *pc = reinterpret_cast<unsigned *>(p.ws + p.w.off_prog) + (size_t)m.b * p.w.nblk + m.t0 / kProgBlock;
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(pc), "r"((unsigned)nvalid) : "memory");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid_constant__ CUtensorMap tmap, LnParams p,
+                                                                     LnSmem sm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + sm.off_full);
+    uint64_t *empty = reinterpret_cast<uint64_t *>(smem + sm.off_empty);
+    uint64_t *abbar = reinterpret_cast<uint64_t *>(smem + sm.off_abbar);
+    LnTileMeta *metas = reinterpret_cast<LnTileMeta *>(smem + sm.off_meta);
+    float *red = reinterpret_cast<float *>(smem + sm.off_red);
+    float *tot = reinterpret_cast<float *>(smem + sm.off_tot);
+    float *post = reinterpret_cast<float *>(smem + sm.off_post);
+    float *gb = reinterpret_cast<float *>(smem + sm.off_gb);
+    unsigned *bm_sm = reinterpret_cast<unsigned *>(smem + sm.off_bm);
+    const uint32_t ring = smem_u32(smem + sm.off_ring);
+    const ProblemDesc &d = p.d;
+    const WsLayout &wl = p.w;
+    const unsigned R = (unsigned)p.R;
+    const int K = p.K;
+    const int Vp = K * kLnBoxRows;
+    const int Upad = (wl.Umax + 3) & ~3;
+    if (threadIdx.x == 0) {
+        for (unsigned i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kLnWarps); }
+        mbar_init(&abbar[0], 1);
+        mbar_init(&abbar[1], 1);
+        mbar_init_fence();
+    }
+    for (int i = threadIdx.x; i < Vp; i += blockDim.x) {
+        gb[i] = i < d.V ? __ldg(p.gamma + i) : 0.f;
+        gb[Vp + i] = i < d.V ? __ldg(p.beta + i) : 0.f;
+    }
+    __syncthreads();
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (w == kLnWarps) {
+        if (lane == 0) ln_producer<true>(&tmap, p, smem, sm);
+        return;
+    }
+    const int r = lane >> 1, h = lane & 1;
+    const int tid = threadIdx.x;
+    const UttInfo *utt = reinterpret_cast<const UttInfo *>(p.ws + wl.off_utt);
+    const float *mu_in = reinterpret_cast<const float *>(p.ws + p.off_mu);
+    const float *rstd_in = reinterpret_cast<const float *>(p.ws + p.off_rstd);
+    const float *lse_in = reinterpret_cast<const float *>(p.ws + wl.off_lse);
+    const int per = d.kind == 0 ? 2 : 3;
+    const float inv_v = 1.f / (float)d.V;
+    float dgam[KMAX], dbet[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) { dgam[k] = 0.f; dbet[k] = 0.f; }
+
+    unsigned box = 0, seq = 0, n_ab = 0;
+    for (;;) {
+        mbar_wait(&full[box % R], (box / R) & 1u);
+        const LnTileMeta m = metas[seq % kLnMetaRing];
+        ++seq;
+        if (m.kind < 0) break;
+        float *dzb = p.dz + (int64_t)m.b * p.dzs_b + m.t0 + 4 * h;
+        const bool store_ok = m.t0 + 4 * h < d.T;
+        if (m.kind == 1) {
+            // every frame of the tile is padding: zeros (gram_ctc.py:296 -> LayerNormalization backward of zero is zero)
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const int v = kLnBoxRows * k + 16 * w + r;
+                if (k < K && v < d.V && store_ok) *reinterpret_cast<float4 *>(dzb + (int64_t)v * p.dzs_v) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[box % R]);
+            ++box;
+            continue;
+        }
+        const UttInfo ui = utt[m.b];
+        // per-frame constants of this thread's four frames; a padded frame gets rstd = 0 and scale = 0, which makes
+        // every quantity below exactly zero for it
+        float rs[4], mur[4], nl[4], scj[4];
+        {
+            const float gy = p.per_utterance ? __ldg(p.grad_loss + m.b) : __ldg(p.grad_loss);
+            const float sc = gy * p.scale;                                    // gram_ctc.py:291-294
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = m.t0 + 4 * h + j;
+                const bool valid = t < ui.Tb;
+                const size_t o = (size_t)m.b * d.T + (valid ? t : 0);
+                const float rr = valid ? __ldg(rstd_in + o) : 0.f;
+                const float mm = valid ? __ldg(mu_in + o) : 0.f;
+                rs[j] = rr; mur[j] = -mm * rr;
+                nl[j] = valid ? -__ldg(lse_in + o) : 0.f;
+                scj[j] = valid ? sc : 0.f;
+            }
+        }
+        // ---- phase (a): merged posteriors of the tile's frames, one warp per frame (gram_ctc.py:180-217, :290) ----
+        mbar_wait(&abbar[0], n_ab & 1u);
+        ++n_ab;
+        {
+            const unsigned *bm_g = reinterpret_cast<const unsigned *>(p.ws + wl.off_bm) + (size_t)m.b * wl.nwords;
+            const int *pc_g = reinterpret_cast<const int *>(p.ws + wl.off_pc) + (size_t)m.b * wl.nwords;
+            for (int i = tid; i < wl.nwords; i += 32 * kLnWarps) { bm_sm[i] = __ldg(bm_g + i); bm_sm[wl.nwords + i] = (unsigned)__ldg(pc_g + i); }
+        }
+        if (w < kLnTT && m.t0 + w < ui.Tb) {
+            float2 *a_sm = reinterpret_cast<float2 *>(smem + sm.off_ab) + (size_t)w * wl.Np;
+            const float2 *b_sm = reinterpret_cast<const float2 *>(smem + sm.off_ab) + (size_t)(kLnTT + w) * wl.Np;
+            float *e_sm = reinterpret_cast<float *>(a_sm);                    // alpha*beta/P, written over the alpha row
+            float blank_part = 0.f;
+            for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
+                const int j = j0 + lane;
+                float e = 0.f;
+                if (j < ui.Nb) e = node_posterior(a_sm[j], b_sm[j + wl.boff], ui.Ph, ui.Pl);
+                __syncwarp();                                                // e_sm aliases the alpha row: reads first
+                if (j < ui.Nb) e_sm[j] = e;
+                if (j < ui.Nb && j % per == 0) blank_part += e;
+            }
+            blank_part = warp_sum(blank_part);
+            __syncwarp();
+            const int *uoff = reinterpret_cast<const int *>(p.ws + wl.off_uoff) + (size_t)m.b * (wl.Nmax + 1);
+            const int *unode = reinterpret_cast<const int *>(p.ws + wl.off_unode) + (size_t)m.b * wl.Nmax;
+            const float gy = p.per_utterance ? __ldg(p.grad_loss + m.b) : __ldg(p.grad_loss);
+            const float sc = gy * p.scale;
+            for (int u = lane; u < ui.Ub; u += 32) {
+                const int n0 = __ldg(uoff + u), n1 = __ldg(uoff + u + 1);
+                float ps = (u == ui.ublank) ? blank_part : 0.f;
+                for (int n = n0; n < n1; ++n) {
+                    const int j = __ldg(unode + n);
+                    if (j < ui.Nb) ps += e_sm[j];
+                }
+                post[w * Upad + u] = ps * sc;
+            }
+        }
+        bar_compute();
+        if (tid == 0) mbar_arrive(&abbar[1]);                                 // the alpha/beta buffer can be refilled
+
+        // ---- sweep 1: g = softmax * sc - posterior;  dn = g * gamma;  per-frame sums of dn and dn * n ----
+        float4 dn[KMAX];
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            dn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < K) {
+                const unsigned bx = box + (unsigned)k;
+                if (k > 0) mbar_wait(&full[bx % R], (bx / R) & 1u);
+                const float4 zq = lds128(ring + (bx % R) * kLnBoxBytes + (uint32_t)(w * 512 + lane * 16));
+                const int v = kLnBoxRows * k + 16 * w + r;
+                const float g_ = gb[v], b_ = gb[Vp + v];
+                const unsigned word = v < d.V ? bm_sm[v >> 5] : 0u;
+                const bool issym = (word >> (v & 31)) & 1u;
+                const int u = issym ? (int)bm_sm[wl.nwords + (v >> 5)] + __popc(word & ((1u << (v & 31)) - 1u)) : 0;
+                const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
+                float dd[4];
+                float accb = 0.f, accg = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float n = fmaf(zz[j], rs[j], mur[j]);
+                    const float a = fmaf(n, g_, b_);
+                    float g = ex2_approx(fmaf(a, LOG2E_HI, nl[j])) * scj[j];
+                    if (issym && scj[j] != 0.f) g -= post[(4 * h + j) * Upad + u];
+                    if (v >= d.V || scj[j] == 0.f) g = 0.f;
+                    const float dnv = g * g_;
+                    s1[j] += dnv;
+                    s2[j] = fmaf(dnv, n, s2[j]);
+                    accb += g;
+                    accg = fmaf(g, n, accg);
+                    dd[j] = dnv;
+                }
+                dbet[k] += accb;                                             // bias backward: sum over (b, t)
+                dgam[k] += accg;                                             // scale backward: sum of g * normalised z
+                dn[k] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+            }
+        }
+        // ---- the two per-frame sums of LayerNormalization's backward (asr/nn/layernorm.py:48-60) ----
+        int fih;
+        const Pair2 pr = reduce_frames16(Pair2{s1[0], s2[0]}, Pair2{s1[1], s2[1]}, Pair2{s1[2], s2[2]}, Pair2{s1[3], s2[3]}, lane,
+                                         merge_pair2, fih);
+        if (lane < 8) { const float v2[2] = {pr.a, pr.b}; red_store<2>(red, 4 * h + fih, w, v2); }
+        bar_compute();
+        if (w < kLnTT) {
+            const float *src = red + (w * 16 + (lane & 15)) * 4;
+            float a = src[0], b = src[1];
+            if ((lane & 15) >= kLnWarps) { a = 0.f; b = 0.f; }
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if (lane == 0) { tot[w * 8 + 0] = a * inv_v; tot[w * 8 + 1] = b * inv_v; }
+        }
+        bar_compute();
+        float c1[4], c2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c1[j] = tot[(4 * h + j) * 8 + 0]; c2[j] = tot[(4 * h + j) * 8 + 1]; }
+
+        // ---- sweep 2: dz = rstd * (dn - mean_v(dn) - n * mean_v(dn * n)), stored in z's own layout ----
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                const unsigned bx = box + (unsigned)k;
+                const float4 zq = lds128(ring + (bx % R) * kLnBoxBytes + (uint32_t)(w * 512 + lane * 16));
+                const int v = kLnBoxRows * k + 16 * w + r;
+                const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
+                const float dd[4] = {dn[k].x, dn[k].y, dn[k].z, dn[k].w};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float n = fmaf(zz[j], rs[j], mur[j]);
+                    o[j] = rs[j] * (dd[j] - c1[j] - n * c2[j]);
+                }
+                if (v < d.V && store_ok) *reinterpret_cast<float4 *>(dzb + (int64_t)v * p.dzs_v) = make_float4(o[0], o[1], o[2], o[3]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[bx % R]);
+            }
+        }
+        box += (unsigned)K;
+        bar_compute();            // red / tot / post / bitmap are reused by the next tile
+    }
+    // ---- this CTA's share of dgamma / dbeta: the two halves of a row pair up, then one partial row per CTA ----
+    float *part = reinterpret_cast<float *>(p.ws + p.off_part) + (size_t)blockIdx.x * 2 * Vp;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const float g = dgam[k] + __shfl_xor_sync(0xffffffffu, dgam[k], 1);
+        const float b = dbet[k] + __shfl_xor_sync(0xffffffffu, dbet[k], 1);
+        const int v = kLnBoxRows * k + 16 * w + r;
+        if (k < K && h == 0) { part[v] = g; part[Vp + v] = b; }
+    }
+}
+
+// dgamma[v] = sum over CTAs of their partial rows, in CTA order (deterministic)
+__global__ void ln_reduce_params_kernel(const float *part, int nparts, int Vp, int V, float *dgamma, float *dbeta) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float g = 0.f, b = 0.f;
+    for (int c = 0; c < nparts; ++c) {
+        g += part[(size_t)c * 2 * Vp + v];
+        b += part[(size_t)c * 2 * Vp + Vp + v];
+    }
+    if (dgamma) dgamma[v] = g;
+    if (dbeta) dbeta[v] = b;
+}
+
+// ---- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// z viewed as a 3-D tensor (t fastest, then v, then b); a box is 8 frames x 256 rows of one utterance.  Rows and frames
+// outside the tensor read as zeros.
+bool make_z_map(CUtensorMap *map, const float *z, int B, int T, int V, int64_t zs_b, int64_t zs_v) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    // The encoder is a DRIVER entry point and wants the device's primary context current on the calling thread.  The
+    // runtime binds it lazily, on a thread's first runtime call that needs it -- and backward runs on an autograd worker
+    // thread that may not have made one yet (its buffers come out of the caller's caching allocator): bind it once.
+    static thread_local bool bound = false;
+    if (!bound) { cudaFree(nullptr); bound = true; }
+    const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)V, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)zs_v * 4, (cuuint64_t)zs_b * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kLnTT, (cuuint32_t)kLnBoxRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(z), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename Kern>
+cudaError_t launch_ln(Kern kern, int grid, const CUtensorMap &map, const LnParams &p, const LnSmem &sm, cudaStream_t stream) {
+    (void)cudaGetLastError();
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), sm.total);
+    if (e != cudaSuccess) { note_failure_site("shared-memory opt-in"); return e; }
+    kern<<<grid, kLnThreads, sm.total, stream>>>(map, p, sm);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) note_failure_site("tile kernel launch");
+    return e;
+}
+
+}  // namespace
+
+LnLayout make_ln_layout(int kind, int B, int T, int V, int Lmax) {
+    LnLayout l;
+    l.w = make_layout(kind, B, T, V, Lmax);
+    size_t o = l.w.total;
+    const size_t BT = (size_t)B * (size_t)T;
+    l.off_mu = o;   o = align_up(o + sizeof(float) * BT, 256);
+    l.off_rstd = o; o = align_up(o + sizeof(float) * BT, 256);
+    const int K = (V + kLnBoxRows - 1) / kLnBoxRows;
+    l.off_part = o; o = align_up(o + sizeof(float) * 2 * (size_t)K * kLnBoxRows * kLnMaxParts, 256);
+    l.total = o;
+    return l;
+}
+
+int ln_supported(int kind, int B, int T, int V, int Lmax, int64_t zs_v, int64_t zs_b, const void *z) {
+    (void)B; (void)T;
+    if (kind != 0 && kind != 1) return 0;                           // the joint objective is not fused yet
+    if (V > 17 * kLnBoxRows) return 0;
+    if (1 + (kind == 0 ? Lmax : 2 * Lmax) > kLnMaxCols) return 0;
+    if ((zs_v & 3) != 0 || (zs_b & 3) != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return 0;
+    return encode_tiled_fn() != nullptr;
+}
+
+static int ln_kmax(int K) { return K <= 5 ? 5 : (K <= 9 ? 9 : (K <= 15 ? 15 : 17)); }
+
+cudaError_t launch_ln_forward(const ProblemDesc &d, const LnLayout &ll, void *ws, const float *z, int64_t zs_b, int64_t zs_v,
+                              const float *gamma, const float *beta, size_t smem_reserve, cudaStream_t stream) {
+    if ((long long)d.B * d.T == 0) return cudaSuccess;
+    LnParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = d; p.w = ll.w; p.ws = static_cast<unsigned char *>(ws);
+    p.z = z; p.zs_b = zs_b; p.zs_v = zs_v; p.gamma = gamma; p.beta = beta;
+    p.off_mu = ll.off_mu; p.off_rstd = ll.off_rstd; p.off_part = ll.off_part;
+    p.K = (d.V + kLnBoxRows - 1) / kLnBoxRows;
+    p.nTB = (d.T + kLnTT - 1) / kLnTT;
+    LnSmem sm = plan_ln_smem(p.K, 0, 0, (size_t)2 * p.K * kLnBoxRows, 0, smem_reserve);
+    if (sm.R < p.K + 2) sm = plan_ln_smem(p.K, 0, 0, (size_t)2 * p.K * kLnBoxRows, 0, 0);     // no room to share the SM
+    if (sm.R < p.K + 2) return cudaErrorInvalidConfiguration;
+    if (sm.R > 2 * p.K + 4) {                     // more than two tiles' worth buys nothing; leave the rest to the L1
+        sm.total -= (size_t)(sm.R - (2 * p.K + 4)) * kLnBoxBytes;
+        sm.R = 2 * p.K + 4;
+    }
+    p.R = sm.R;
+    CUtensorMap map;
+    if (!make_z_map(&map, z, d.B, d.T, d.V, zs_b, zs_v)) return cudaErrorInvalidValue;
+    long long tiles = (long long)d.B * p.nTB;
+    int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    if (grid < 1) grid = 1;
+    switch (ln_kmax(p.K)) {
+        case 5: return launch_ln(ln_softmax_gather_kernel<5>, grid, map, p, sm, stream);
+        case 9: return launch_ln(ln_softmax_gather_kernel<9>, grid, map, p, sm, stream);
+        case 15: return launch_ln(ln_softmax_gather_kernel<15>, grid, map, p, sm, stream);
+        default: return launch_ln(ln_softmax_gather_kernel<17>, grid, map, p, sm, stream);
+    }
+}
+
+cudaError_t launch_ln_backward(const GradParams &g, const LnLayout &ll, const void *ws, const float *z, int64_t zs_b, int64_t zs_v,
+                               const float *gamma, const float *beta, float *dz, int64_t dzs_b, int64_t dzs_v, float *dgamma,
+                               float *dbeta, cudaStream_t stream) {
+    const ProblemDesc &d = g.d;
+    if ((long long)d.B * d.T == 0) return cudaSuccess;
+    LnParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = d; p.w = ll.w; p.ws = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
+    p.z = z; p.zs_b = zs_b; p.zs_v = zs_v; p.gamma = gamma; p.beta = beta;
+    p.off_mu = ll.off_mu; p.off_rstd = ll.off_rstd; p.off_part = ll.off_part;
+    p.K = (d.V + kLnBoxRows - 1) / kLnBoxRows;
+    p.nTB = (d.T + kLnTT - 1) / kLnTT;
+    p.grad_loss = g.grad_loss; p.per_utterance = g.per_utterance; p.scale = g.scale;
+    p.dz = dz; p.dzs_b = dzs_b; p.dzs_v = dzs_v; p.dgamma = dgamma; p.dbeta = dbeta;
+    const int Vp = p.K * kLnBoxRows;
+    const LnSmem sm = plan_ln_smem(p.K, (size_t)2 * kLnTT * ll.w.Np * 8, (size_t)kLnTT * ((ll.w.Umax + 3) & ~3), (size_t)2 * Vp,
+                                   (size_t)2 * ll.w.nwords);
+    if (sm.R < p.K + 2) { note_failure_site("shared-memory plan"); return cudaErrorInvalidConfiguration; }
+    p.R = sm.R;
+    CUtensorMap map;
+    if (!make_z_map(&map, z, d.B, d.T, d.V, zs_b, zs_v)) { note_failure_site("tensor map of z"); return cudaErrorInvalidValue; }
+    long long tiles = (long long)d.B * p.nTB;
+    int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    if (grid > kLnMaxParts) grid = kLnMaxParts;
+    if (grid < 1) grid = 1;
+    cudaError_t e;
+    switch (ln_kmax(p.K)) {
+        case 5: e = launch_ln(ln_gradient_kernel<5>, grid, map, p, sm, stream); break;
+        case 9: e = launch_ln(ln_gradient_kernel<9>, grid, map, p, sm, stream); break;
+        case 15: e = launch_ln(ln_gradient_kernel<15>, grid, map, p, sm, stream); break;
+        default: e = launch_ln(ln_gradient_kernel<17>, grid, map, p, sm, stream); break;
+    }
+    if (e != cudaSuccess) return e;
+    if (dgamma || dbeta) {
+        const float *part = reinterpret_cast<const float *>(p.ws + p.off_part);
+        ln_reduce_params_kernel<<<(d.V + 127) / 128, 128, 0, stream>>>(part, grid, Vp, d.V, dgamma, dbeta);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) note_failure_site("dgamma/dbeta reduction launch");
+    }
+    return e;
+}
+
+}  // namespace b200ctc

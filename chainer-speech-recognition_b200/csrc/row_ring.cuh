@@ -128,6 +128,13 @@ __device__ __forceinline__ int ring_claim(const Ring &r, unsigned q) {
     return s;
 }
 
+// Producer side, non-blocking: is the slot of row sequence number q free (its previous occupant released)?
+__device__ __forceinline__ bool ring_slot_free(const Ring &r, unsigned q) {
+    const int s = (int)(q % (unsigned)r.slots);
+    const unsigned n = q / (unsigned)r.slots;
+    return n == 0 || mbar_test_wait(&r.empty[s], (n - 1) & 1u);
+}
+
 // Consumer side: wait until row sequence number q has landed in its slot; returns the slot.
 // An mbarrier parity wait can only tell "this phase" from "the one before", while rows complete out of order
 // (a batch is issued by several lanes at once, each row is several bulk copies): a fast consumer may get here

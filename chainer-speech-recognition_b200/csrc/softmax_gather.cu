@@ -19,7 +19,13 @@ namespace b200ctc {
 __device__ long long *g_tl_k1 = nullptr;      // timeline hook, see common.cuh
 void softmax_set_timeline(long long *p) { cudaMemcpyToSymbol(g_tl_k1, &p, sizeof(p)); }
 #define B200CTC_TL_K1(end) timeline_mark(g_tl_k1, 0, end)
+// role breakdown (tools/k1_roles.py): per CTA and warp, cycles spent [0] waiting for a ticket / a row, [1] waiting for a
+// free slot (producer) / processing (consumer), [2] rows handled, [3] total cycles
+__device__ long long *g_k1_roles = nullptr;
+void softmax_set_roles(long long *p) { cudaMemcpyToSymbol(g_k1_roles, &p, sizeof(p)); }
+#define K1_CLK() (g_k1_roles ? clock64() : 0ll)
 #else
+#define K1_CLK() 0ll
 #define B200CTC_TL_K1(end) ((void)0)
 #endif
 
@@ -257,7 +263,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) softmax_gather_kernel(Probl
 // consumer warp that was 28 us of a 105 us kernel.  So the consumers only note finished rows in a small
 // shared-memory FIFO (CTA-scope ordering, cheap) and one extra warp drains all FIFOs with ONE GPU-scope fence per
 // sweep, then bumps the progress counters (the __syncthreads / thread 0 fences / atomic pattern of a grid barrier).
-constexpr int kK1Consumers = 10;
+#ifndef B200CTC_K1_CONSUMERS
+#define B200CTC_K1_CONSUMERS 10
+#endif
+constexpr int kK1Consumers = B200CTC_K1_CONSUMERS;
 constexpr int kK1Threads = 32 * (1 + kK1Consumers + 1);   // producer + consumers + signal warp
 constexpr int kGatherRegs = 4;                         // emitted ids per lane on the early-release path (<= 128 columns)
 constexpr int kFifoDepth = 4;
@@ -364,9 +373,13 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     if (warp == 0) {
         // ===== producer (lane i owns frame i of the current batch) =====
         unsigned q = 0, pend;
+        long long r_wait0 = 0, r_wait1 = 0, r_rows = 0;
+        const long long r_begin = K1_CLK();
         ring_first_ticket(&hdr->k1_ticket, pend, lane, ring.batch);
         for (;;) {
+            const long long c0 = K1_CLK();
             const unsigned base = ring_take_batch(&hdr->k1_ticket, pend, lane, ring.batch, frames);
+            r_wait0 += K1_CLK() - c0;
             if (base >= frames) break;
             const unsigned f = base + (unsigned)lane;
             int b = 0, t = 0;
@@ -379,22 +392,39 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
                 need = valid || ARGMAX;
             }
             const unsigned mask = __ballot_sync(0xffffffffu, need);
-            if (need) {
-                const unsigned myq = q + (unsigned)__popc(mask & ((1u << lane) - 1u));
-                const int s = ring_claim(ring, myq);
-                // the 16-byte aligned span that covers the row (rows themselves only need 4-byte alignment)
-                const float *src = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
-                const int off = row_misalignment(src);
-                const uint32_t span = row_span_bytes(off, d.V);
-                ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = valid ? 0 : 1; ring.meta[s].off = off;
-                ring_publish(ring, s, myq);
-                mbar_arrive_expect_tx(&ring.full[s], span);
-                bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
+            const unsigned myq = q + (unsigned)__popc(mask & ((1u << lane) - 1u));
+            // every lane issues its row as soon as ITS slot is free, in whatever order the consumers hand slots back
+            bool pending = need;
+            const long long c1 = K1_CLK();
+            r_rows += __popc(mask);
+            while (__any_sync(0xffffffffu, pending)) {
+                bool issued = false;
+                if (pending && ring_slot_free(ring, myq)) {
+                    const int s = (int)(myq % (unsigned)ring.slots);
+                    // the 16-byte aligned span that covers the row (rows themselves only need 4-byte alignment)
+                    const float *src = d.acts + (int64_t)t * d.stride_t + (int64_t)b * d.stride_b;
+                    const int off = row_misalignment(src);
+                    const uint32_t span = row_span_bytes(off, d.V);
+                    ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = valid ? 0 : 1; ring.meta[s].off = off;
+                    ring_publish(ring, s, myq);
+                    mbar_arrive_expect_tx(&ring.full[s], span);
+                    bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
+                    pending = false;
+                    issued = true;
+                }
+                if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
             }
+            r_wait1 += K1_CLK() - c1;
             q += (unsigned)__popc(mask);
         }
         ring_stop(ring, q, lane);
         B200CTC_TL_K1(true);
+#ifdef B200CTC_EXPERIMENT
+        if (g_k1_roles && lane == 0) {
+            long long *o = g_k1_roles + ((size_t)blockIdx.x * 16 + 0) * 4;
+            o[0] = r_wait0; o[1] = r_wait1; o[2] = r_rows; o[3] = clock64() - r_begin;
+        }
+#endif
         return;
     }
 
@@ -403,8 +433,13 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     float2 *lp_out = reinterpret_cast<float2 *>(ws + w.off_lp);
     if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
     unsigned pushed = 0;
+    long long c_wait = 0, c_proc = 0, c_rows = 0;
+    const long long c_begin = K1_CLK();
     for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
+        const long long c0 = K1_CLK();
         const int s = ring_acquire(ring, q);
+        const long long c1 = K1_CLK();
+        c_wait += c1 - c0;
         const RowMeta m = ring.meta[s];
         if (m.kind < 0) {                       // stop record: hand the slot back (the ring may be shorter than
             __syncwarp();                       // the number of consumers) and leave
@@ -523,8 +558,16 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
         }
         __syncwarp();
         if (lane == 0 && !released) mbar_arrive(&ring.empty[s]);
+        c_proc += K1_CLK() - c1;
+        ++c_rows;
     }
     if (signalling && lane == 0) fifo_push(fifo, warp - 1, pushed, -1, 0);
+#ifdef B200CTC_EXPERIMENT
+    if (g_k1_roles && lane == 0) {
+        long long *o = g_k1_roles + ((size_t)blockIdx.x * 16 + warp) * 4;
+        o[0] = c_wait; o[1] = c_proc; o[2] = c_rows; o[3] = clock64() - c_begin;
+    }
+#endif
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) argmax_kernel(const float *acts, int64_t stride_t,

@@ -44,7 +44,7 @@ def bigram_id(a, b, V, salt=0):
     h = (h * 2654435761) & 0xffffffff
     if (h >> 8) % 10 >= 6:
         return -1
-    return N_UNIGRAM + (h % (V - N_UNIGRAM))
+    return N_UNIGRAM + (h % max(1, V - N_UNIGRAM))
 
 
 def make_gram_labels(rs, B, L, V, lab_len, repeat_prob=0.1, n_unigram=N_UNIGRAM):

@@ -114,21 +114,37 @@ int b200ctc_backward(int kind,
                      const void *workspace, size_t workspace_bytes, void *stream);
 
 /*
- * Forward of a TRAINING step: b200ctc_forward plus one piece of the backward pass that needs nothing from the
- * lattice.  `grad_out` is the buffer the following b200ctc_backward is going to fill; this call writes the zero rows
- * of its padded frames (t >= input_lengths[b], gram_ctc.py:296) while the alpha/beta recursion is finishing and HBM is
- * otherwise idle, and leaves a note in the workspace.  b200ctc_backward, when handed the same buffer and strides
- * with that workspace, skips those rows (once: the note is cleared by the backward pass that uses it; any other
- * buffer is filled completely as usual).  With grad_out == NULL or input_lengths == NULL it is b200ctc_forward.
+ * LayerNormalization fused into the loss.  Every CTC / Gram-CTC model of the reference ends in
+ * Convolution2D(.., vocab_size, ksize=1) -> LayerNormalization (run/ctc/cnn/model.py:85-88, asr/nn/nn.py:240-265,
+ * asr/nn/layernorm.py:29-61), after which AcousticModel.__call__ makes a transposed copy of the whole tensor for the
+ * loss (swapaxes/reshape/split_axis, asr/model/cnn.py:41-44).  These entry points take the convolution output itself:
+ *   z        float32 (B, V, 1, T) as the model produces it: element (b, v, t) at z[b*zstride_b + v*zstride_v + t]
+ *            (time stride 1); rows must be 16-byte aligned (base pointer, zstride_v % 4 == 0, zstride_b % 4 == 0)
+ *   gamma, beta  float32 (V): LayerNormalization's scale and shift along the vocabulary axis
+ * and compute  loss(gamma * (z - mean_v z) / std_v z + beta)  per frame, std = sqrt(mean_v (z - mean)^2), no epsilon
+ * (asr/nn/layernorm.py:41-46).  Backward returns the gradient where the model needs it:
+ *   dz       float32, same layout rules as z; every element is written (zeros for t >= input_lengths[b])
+ *   dgamma, dbeta  float32 (V) or NULL: sums over all frames of the batch, in a fixed order (deterministic)
+ * with LayerNormalization's backward (asr/nn/layernorm.py:48-60) and both transposes folded in: z is read once in
+ * forward, once in backward, dz is written once.  loss outputs, grad_loss / per_utterance / scale as in
+ * b200ctc_forward / b200ctc_backward.  Returns B200CTC_UNSUPPORTED (use the unfused entry points) for the joint
+ * objective, V > 4080, more than 480 emission columns (1 + Lmax for CTC, 1 + 2*Lmax for Gram-CTC) or unaligned rows.
  */
-int b200ctc_forward_train(int kind,
-                          const float *acts, int64_t stride_t, int64_t stride_b,
-                          const int32_t *labels, const int32_t *bigrams,
-                          const int32_t *input_lengths, const int32_t *label_lengths,
-                          int blank, int B, int T, int V, int Lmax,
-                          float *loss_per_utt, float *loss_reduced, float loss_scale, int64_t *argmax_out,
-                          float *grad_out, int64_t gstride_t, int64_t gstride_b,
-                          void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+int b200ctc_ln_workspace_bytes(int kind, int B, int T, int V, int Lmax, size_t *bytes_out);
+int b200ctc_ln_forward(int kind,
+                       const float *z, int64_t zstride_b, int64_t zstride_v, const float *gamma, const float *beta,
+                       const int32_t *labels, const int32_t *bigrams,
+                       const int32_t *input_lengths, const int32_t *label_lengths,
+                       int blank, int B, int T, int V, int Lmax,
+                       float *loss_per_utt, float *loss_reduced, float loss_scale,
+                       void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+int b200ctc_ln_backward(int kind,
+                        const float *z, int64_t zstride_b, int64_t zstride_v, const float *gamma, const float *beta,
+                        const int32_t *labels, const int32_t *bigrams,
+                        int blank, int B, int T, int V, int Lmax,
+                        const float *grad_loss, int per_utterance, float scale,
+                        float *dz, int64_t dzstride_b, int64_t dzstride_v, float *dgamma, float *dbeta,
+                        const void *workspace, size_t workspace_bytes, void *stream);
 
 /* Greedy path alone (run/ctc/cnn/train.py:232 and its 9 sibling call sites): out (B,T) int64. */
 int b200ctc_greedy_argmax(const float *acts, int64_t stride_t, int64_t stride_b,

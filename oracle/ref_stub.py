@@ -186,3 +186,76 @@ def load_processing_module():
         spec.loader.exec_module(mod)
         _processing_module = mod
     return _processing_module
+
+
+_layernorm_module = None
+
+
+def _backward_one(xp, shape, dtype, g):
+    """``chainer.functions.array.broadcast._backward_one`` (third-party: Chainer, version unpinned "Chainer 2+",
+    README.md:14; imported by asr/nn/layernorm.py:6).  Its published behaviour -- the backward of ``broadcast_to``:
+    sum the gradient over the leading axes the broadcast added and over every axis whose input extent was 1,
+    keeping those axes -- restated here because Chainer is not installable offline."""
+    g = xp.asarray(g)
+    ndim = len(shape)
+    if g.ndim != ndim:
+        g = g.sum(axis=tuple(range(g.ndim - ndim)))
+    axis = tuple(i for i, sx in enumerate(shape) if sx == 1)
+    if axis:
+        g = g.sum(keepdims=True, axis=axis)
+    return g.astype(dtype, copy=False)
+
+
+def load_layernorm_module():
+    """The reference's asr/nn/layernorm.py, UNMODIFIED (NumPy path).  Needs ``chainer.function.Function`` (with
+    ``retain_inputs``), ``chainer.cuda.get_array_module`` and ``_backward_one`` (above)."""
+    global _layernorm_module
+    if _layernorm_module is None:
+        if not os.path.isfile(os.path.join(REFERENCE_ROOT, "asr", "nn", "layernorm.py")):
+            raise RuntimeError("reference not available at %s" % REFERENCE_ROOT)
+        _install_chainer_stub()
+        chainer = sys.modules["chainer"]
+        if not hasattr(chainer.function.Function, "retain_inputs"):
+            chainer.function.Function.retain_inputs = lambda self, idx: None          # layernorm.py:34
+        chainer.function.cuda = chainer.cuda                                           # "from chainer import function, cuda"
+        functions = types.ModuleType("chainer.functions")
+        array = types.ModuleType("chainer.functions.array")
+        broadcast = types.ModuleType("chainer.functions.array.broadcast")
+        broadcast._backward_one = _backward_one
+        array.broadcast = broadcast
+        functions.array = array
+        chainer.functions = functions
+        sys.modules.setdefault("chainer.functions", functions)
+        sys.modules.setdefault("chainer.functions.array", array)
+        sys.modules.setdefault("chainer.functions.array.broadcast", broadcast)
+        spec = importlib.util.spec_from_file_location("_ref_layernorm", os.path.join(REFERENCE_ROOT, "asr", "nn", "layernorm.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _layernorm_module = mod
+    return _layernorm_module
+
+
+def run_layernorm_ctc(z_bv1t, gamma, beta, unigram, bigram, input_length, label_length, blank=0, reduce="no", gy=None):
+    """The reference's model tail + loss, forward and backward, every piece the reference's own code:
+    NormalizeLayer (asr/nn/layernorm.py) -> scale/bias by gamma/beta (asr/nn/nn.py:265; Chainer's scale/bias are
+    broadcast multiplies/adds along axis 1) -> swapaxes/reshape/split (asr/model/cnn.py:41-44) -> GramCTC
+    (asr/loss/gram_ctc.py).  z_bv1t: (B, V, 1, T) float32.  Returns loss, dz (B,V,1,T), dgamma, dbeta, activations."""
+    ln = load_layernorm_module()
+    z = np.ascontiguousarray(z_bv1t, np.float32)
+    gamma = np.asarray(gamma, np.float32)
+    beta = np.asarray(beta, np.float32)
+    B, V, H, T = z.shape
+    f = ln.NormalizeLayer()
+    n = f.forward((z,))[0]                                             # (B, V, 1, T)
+    y = n * gamma[None, :, None, None] + beta[None, :, None, None]     # nn.py:265
+    out = np.swapaxes(y, 1, 3).reshape(B, -1)                          # cnn.py:42-43
+    xs = np.split(out, T, axis=1)                                      # cnn.py:44: T arrays (B, V)
+    x_tbv = np.stack(xs).astype(np.float32)
+    loss, grad_tbv, _ = run_gram_ctc(x_tbv, unigram, bigram, input_length, label_length, blank=blank, reduce=reduce, gy=gy)
+    g_out = np.concatenate([grad_tbv[t] for t in range(T)], axis=1)    # backward of split_axis
+    g_y = np.swapaxes(g_out.reshape(B, T, H, V), 1, 3)                  # backward of reshape / swapaxes: (B, V, 1, T)
+    dbeta = g_y.sum(axis=(0, 2, 3))                                    # bias backward
+    dgamma = (g_y * n).sum(axis=(0, 2, 3))                             # scale backward
+    dn = np.ascontiguousarray(g_y * gamma[None, :, None, None], np.float32)
+    dz = f.backward((z,), (dn,))[0]
+    return loss, np.asarray(dz, np.float32), dgamma.astype(np.float32), dbeta.astype(np.float32), x_tbv

@@ -124,7 +124,7 @@ def test_sweep_at_batch_64(pkg, T, V):
 def test_vocabulary_sizes_off_the_16_byte_grid(pkg, V, kind):
     s = synth()
     B, T, L = 6, 420, 30
-    prob = s.ctc_problem(B, T, V, L, seed=47) if kind == "ctc" else s.gram_problem(B, T, V, L, seed=47, n_unigram=min(119, V // 2))
+    prob = s.ctc_problem(B, T, V, L, seed=47) if kind == "ctc" else s.gram_problem(B, T, V, L, seed=47, n_unigram=min(100, V // 2))
     loss, grad, am = run_cuda(pkg, prob, kind, want_argmax=True)
     loss_ref, grad_ref, am_ref = run_oracle(prob, kind, want_argmax=True)
     assert_parity(loss, grad, loss_ref, grad_ref, "%s V=%d" % (kind, V))
