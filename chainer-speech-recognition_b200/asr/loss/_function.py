@@ -42,6 +42,34 @@ def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_ws_bytes = {}
+
+
+def _workspace_bytes(kind, B, T, V, Lmax):
+    """b200ctc_workspace_bytes, remembered per shape (a training loop asks for the same few shapes over and over)."""
+    key = (kind, B, T, V, Lmax)
+    n = _ws_bytes.get(key)
+    if n is None:
+        n = _ws_bytes[key] = _lib.workspace_bytes(kind, B, T, V, Lmax)
+    return n
+
+
+class _on_device(object):
+    """``with torch.cuda.device(dev)`` only when dev is not already the current device (the context manager costs
+    several microseconds per use, and a step has two)."""
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 class _CaiBlock(object):
     """A (T,B,V) float32 block of device memory described for torch.as_tensor; keeps the frame owners alive."""
 
@@ -88,6 +116,8 @@ def stack_frames(xs):
 def _as_int32(a, device, name):
     if a is None:
         return None
+    if isinstance(a, torch.Tensor) and a.dtype == torch.int32 and a.device == device and a.is_contiguous():
+        return a                                               # the usual case: nothing to convert
     a = as_device_tensor(a, name)
     if isinstance(a, torch.Tensor):
         if a.dtype.is_floating_point or a.dtype == torch.bool:
@@ -110,14 +140,14 @@ class LatticeLossFunction(torch.autograd.Function):
         T, B, V = acts.shape
         Lmax = labels.shape[1]
         dev = acts.device
-        loss_b = torch.empty(B, dtype=torch.float32, device=dev)
-        loss_red = torch.empty((), dtype=torch.float32, device=dev)
+        losses = torch.empty(B + 1, dtype=torch.float32, device=dev)          # [per-utterance losses | reduced loss]
+        loss_b, loss_red = losses[:B], losses[B]
         loss_scale = 1.0 / float(batch_global) if reduce == "mean" else 1.0     # gram_ctc.py:280-281
         argmax = torch.empty((B, T), dtype=torch.int64, device=dev) if want_argmax else None
         ptr = lambda t: t.data_ptr() if t is not None else None
-        nbytes = _lib.workspace_bytes(kind, B, T, V, Lmax)
+        nbytes = _workspace_bytes(kind, B, T, V, Lmax)
         workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.b200ctc_forward(
                 kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), ptr(bigrams),
                 ptr(input_length), ptr(label_length), blank, B, T, V, Lmax, loss_b.data_ptr(), loss_red.data_ptr(),
@@ -146,14 +176,15 @@ class LatticeLossFunction(torch.autograd.Function):
         acts, labels, bigrams, workspace = ctx.saved_tensors
         B, T, V, Lmax = ctx.dims
         dev = acts.device
-        gy = gy.to(device=dev, dtype=torch.float32).contiguous()
+        if not (gy.dtype == torch.float32 and gy.device == dev and gy.is_contiguous()):
+            gy = gy.to(device=dev, dtype=torch.float32).contiguous()
         per_utt = 0 if ctx.reduce == "mean" else 1
         scale = 1.0 / float(ctx.batch_global) if ctx.reduce == "mean" else 1.0     # :291-294
         big_ptr = bigrams.data_ptr() if ctx.has_bigrams else None
         grad = torch.empty_like(acts)
         if grad.stride(2) != 1:
             grad = torch.empty(acts.shape, dtype=acts.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.b200ctc_backward(
                 ctx.kind, acts.data_ptr(), acts.stride(0), acts.stride(1), labels.data_ptr(), big_ptr,
                 ctx.blank, B, T, V, Lmax, gy.data_ptr(), per_utt, scale, grad.data_ptr(), grad.stride(0),

@@ -5,15 +5,18 @@ asr/loss/gram_ctc.py:247,285); a user of that path hands over host activations a
 gradients.  Here the arithmetic still runs on the GPU: the batch is cut into utterance groups and the
 three stages of a group -- activations host->device, loss forward + gradient, gradient device->host --
 run on three CUDA streams, so the PCIe transfers in both directions overlap each other and the kernels.
-Host->device, only valid frames cross PCIe (padded frames are never read by the kernels).  The gradient comes back
-whole: letting the host zero the padded rows itself instead (they are exactly 0, gram_ctc.py:296) was measured
-slower -- a CPU memset of pinned memory runs at a fraction of the PCIe rate.
+Only valid frames cross PCIe, in both directions: padded frames are never read by the kernels, and their gradient rows
+are exactly zero (gram_ctc.py:296), so the host writes those itself -- on a small thread pool (a single-threaded memset
+of pinned memory is slower than the DMA it would replace; a few threads are not) while the copies are in flight.
 Utterances are independent, so grouping changes no result bit-for-bit per utterance.
 
 Layout: host activations are (B,T,V) ("batch first", the decoder layout of asr/model/cnn.py:45-47), which makes
 a group a contiguous slab of host memory; pass pinned tensors (``torch.Tensor.pin_memory()``) for the
 copies to be asynchronous.
 """
+import concurrent.futures
+import os
+
 import numpy as np
 import torch
 
@@ -21,6 +24,19 @@ from ... import _lib
 from ._function import _as_int32
 
 _streams = {}
+_pool = None
+
+
+def _zero_pool():
+    """Threads that zero the padded gradient rows on the host (NumPy slice assignment releases the GIL)."""
+    global _pool
+    if _pool is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except Exception:
+            n = os.cpu_count() or 2
+        _pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(8, n // 2)), thread_name_prefix="b200ctc-zero")
+    return _pool
 
 
 def _get_streams(dev):
@@ -94,6 +110,18 @@ def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length,
     groups = max(1, min(int(groups), B))
     bounds = [B * g // groups for g in range(groups + 1)]
     parts = []
+    zero_jobs = []
+    if il_host is not None:
+        # padded rows of the host gradient: zeroed by the pool while the DMA engines move the valid rows
+        g_np = grad_out.numpy()
+
+        def zero_rows(b, n):
+            g_np[b, n:] = 0.0
+        pool = _zero_pool()
+        for b in range(B):
+            n = int(min(max(il_host[b], 0), T))
+            if n < T:
+                zero_jobs.append(pool.submit(zero_rows, b, n))
     for g in range(groups):
         b0, b1 = bounds[g], bounds[g + 1]
         if b1 == b0:
@@ -118,7 +146,13 @@ def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length,
             e_run = torch.cuda.Event(); e_run.record(s_run)
         with torch.cuda.stream(s_out):
             s_out.wait_event(e_run)
-            grad_out[b0:b1].copy_(g_dev[b0:b1], non_blocking=True)
+            if il_host is None:
+                grad_out[b0:b1].copy_(g_dev[b0:b1], non_blocking=True)
+            else:
+                for b in range(b0, b1):
+                    n = int(min(max(il_host[b], 0), T))
+                    if n > 0:
+                        grad_out[b, :n].copy_(g_dev[b, :n], non_blocking=True)
     with torch.cuda.stream(s_out):
         s_out.wait_stream(s_run)
         if reduce == "mean":
@@ -129,6 +163,8 @@ def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length,
     for t_ in (x_dev, g_dev, gy_one, labels):
         t_.record_stream(s_run); t_.record_stream(s_out)
     s_out.synchronize()
+    for j in zero_jobs:
+        j.result()
     cur.wait_stream(s_out)
     return (float(total_host) if reduce == "mean" else total_host.numpy()), grad_out
 

@@ -210,6 +210,7 @@ void lattice_set_debug(long long *p);
 void lattice_set_timeline(long long *p);
 void softmax_set_timeline(long long *p);
 void softmax_set_roles(long long *p);
+void ln_set_debug(long long *p);
 void gradient_set_timeline(long long *p);
 }
 #endif
@@ -220,6 +221,7 @@ extern "C" {
 /* profiling hooks of the experiment build (tools/step_timeline.py, tools/lattice_timeline.py); not part of the ABI */
 void b200ctc_debug_lattice(long long *p) { b200ctc::lattice_set_debug(p); }
 void b200ctc_debug_k1_roles(long long *p) { b200ctc::softmax_set_roles(p); }
+void b200ctc_debug_ln(long long *p) { b200ctc::ln_set_debug(p); }
 void b200ctc_debug_timeline(long long *p) {
     b200ctc::softmax_set_timeline(p); b200ctc::lattice_set_timeline(p); b200ctc::gradient_set_timeline(p);
 }

@@ -30,6 +30,7 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kUnroll = 4;
+constexpr int kUttCache = 160;        // utterance records the ring kernel keeps in shared memory (40 bytes each)
 
 __device__ __forceinline__ void zero_row(float *__restrict__ g, int V, int lane) {
     const int mis = (int)((reinterpret_cast<uintptr_t>(g) >> 2) & 3);
@@ -241,7 +242,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     B200CTC_TL_K3(false);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
     float *post_all = zero_row + ((d.V + 4 + 3) & ~3);
+    // the utterance records, once per CTA: a consumer's row then starts without a round trip to L2
+    UttInfo *utt_sm = reinterpret_cast<UttInfo *>(post_all + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
+    const bool utt_cached = d.B <= kUttCache;
     for (int i = threadIdx.x; i < d.V + 4; i += blockDim.x) zero_row[i] = 0.f;
+    if (utt_cached) {
+        const int nwords = d.B * (int)(sizeof(UttInfo) / 4);
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x)
+            reinterpret_cast<int *>(utt_sm)[i] = reinterpret_cast<const int *>(utt)[i];
+    }
     fence_proxy_async_smem();
     __syncthreads();
 
@@ -249,6 +258,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         // ===== producer (lane i owns frame i of the current batch) =====
         const float2 *av_all = reinterpret_cast<const float2 *>(ws + w.off_av);
         const float2 *bv_all = reinterpret_cast<const float2 *>(ws + w.off_bv);
+        const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
         unsigned q = 0, pend;
         ring_first_ticket(&hdr->k3_ticket, pend, lane, ring.batch);
         for (;;) {
@@ -257,6 +267,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             const unsigned f = base + (unsigned)lane;
             int b = 0, t = 0;
             bool need = false;
+            float row_lse = 0.f, row_sc = 0.f;
             if (lane < ring.batch && f < frames) {
                 if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
                 else { t = (int)(f / d.B); b = (int)(f % d.B); }
@@ -265,6 +276,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                     store_row_image(dst, zero_row + row_misalignment(dst), d.V);
                 } else {
                     need = true;
+                    row_lse = __ldg(lse_all + (size_t)b * d.T + t);
+                    row_sc = (gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss)) * gp.scale;     // :291-294
                 }
             }
             const unsigned mask = __ballot_sync(0xffffffffu, need);
@@ -279,6 +292,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                     const int off = row_misalignment(src);
                     const uint32_t span = row_span_bytes(off, d.V);
                     ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0; ring.meta[s].off = off;
+                    ring.meta[s].lse = row_lse; ring.meta[s].sc = row_sc;
                     ring_publish(ring, s, myq);
                     mbar_arrive_expect_tx(&ring.full[s], span + 2 * ab_bytes + 2 * ab2_bytes);
                     bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
@@ -310,7 +324,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     }
 
     // ===== consumers =====
-    const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
     const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
     const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
     const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
@@ -335,11 +348,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         const float2 *a2_sm = b_sm + w.Np;                                   // joint: plain-CTC alpha row, beta row
         const float2 *b2_sm = a2_sm + w.Np2;
         float *e2_sm = reinterpret_cast<float *>(const_cast<float2 *>(a2_sm));
-        const UttInfo ui = utt[b];
-        const float lse2 = __ldg(lse_all + (size_t)b * d.T + t);
-        const float gy = gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss);
-        const float sc = gy * gp.scale;                                      // :291-294
-        const float c = -lse2;
+        const UttInfo ui = utt_cached ? utt_sm[b] : utt[b];
+        const float sc = m.sc;                                               // :291-294 (fetched by the producer)
+        const float c = -m.lse;
 
         float blank_part = 0.f;
         for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
@@ -423,7 +434,8 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
     if (frames == 0) return cudaSuccess;
     unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
     const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
-    const size_t extra = sizeof(float) * ((size_t)((g.d.V + 4 + 3) & ~3) + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
+    const size_t extra = sizeof(float) * ((size_t)((g.d.V + 4 + 3) & ~3) + (size_t)kRingConsumers * ((w.Umax + 3) & ~3)) +
+                         (g.d.B <= kUttCache ? sizeof(UttInfo) * (size_t)g.d.B : 0);
     const RingLayout rl = make_ring(ring_row_bytes(g.d.V) + sizeof(float) * (4 * (size_t)w.Np + (w.joint ? 4 * (size_t)w.Np2 : 0)), extra);
     if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
         ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl) && !knobs().no_tma_k3) {

@@ -48,6 +48,18 @@ constexpr uint32_t kLnBoxBytes = kLnBoxRows * kLnTT * 4;   // 7.5 KB
 constexpr int kLnMetaRing = 64;                            // >= ring slots: a padded tile takes one slot and one record
 constexpr int kLnMaxCols = 32 * kLnWarps;                  // emission columns one tile pass can gather: one per compute thread
 
+#ifdef B200CTC_EXPERIMENT
+// phase timers (tools/ln_phases.py): per CTA and warp, cycles per phase of the tile loop
+__device__ long long *g_ln_dbg = nullptr;
+#define LN_T_DECL long long *const ln_dbg = g_ln_dbg; long long ln_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ln_last = ln_dbg ? clock64() : 0
+#define LN_T(i) do { if (ln_dbg) { const long long now_ = clock64(); ln_acc[i] += now_ - ln_last; ln_last = now_; } } while (0)
+#define LN_T_FLUSH(w) do { if (ln_dbg && lane == 0) { for (int i_ = 0; i_ < 8; ++i_) ln_dbg[((size_t)blockIdx.x * 16 + (w)) * 8 + i_] = ln_acc[i_]; } } while (0)
+#else
+#define LN_T_DECL
+#define LN_T(i) ((void)0)
+#define LN_T_FLUSH(w) ((void)0)
+#endif
+
 struct LnTileMeta { int b, t0, kind, pad; };               // kind 0: work, 1: padded frames only (backward), -1: stop
 
 struct LnSmem {
@@ -294,33 +306,45 @@ __device__ __forceinline__ void red_store(float *red, int f, int w, const float 
     for (int i = 0; i < NV; ++i) red[(f * 16 + w) * 4 + i] = v[i];
 }
 
+// A box slot and its barrier phase, advanced without a division.
+struct SlotIter {
+    unsigned slot, phase;
+    __device__ __forceinline__ void next(unsigned R) { if (++slot == R) { slot = 0; phase ^= 1u; } }
+};
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }            // try_wait suspends the thread in hardware while it waits
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 // 104 registers per thread: 512 threads then leave 12K of the SM's 64K registers to a lattice CTA, which runs next
-// to this kernel exactly as it runs next to the row kernel (api.cu)
+// to this kernel exactly as it runs next to the row kernel (api.cu).
+// Rows that do not exist (v >= V: the tail of the last box, read as zeros, and register slots k >= K) are made
+// neutral by DATA, not by predicates: their gamma is 0 and their beta -inf in the shared-memory table, so their
+// activation is -inf -- never a maximum, probability 0 -- and the one place where a zero row is not neutral, the centred
+// second moment, is corrected in closed form.
 template <int KMAX>
-__global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                                            LnParams p, LnSmem sm) {
+__global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant__ CUtensorMap tmap, LnParams p, LnSmem sm) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + sm.off_full);
     uint64_t *empty = reinterpret_cast<uint64_t *>(smem + sm.off_empty);
     LnTileMeta *metas = reinterpret_cast<LnTileMeta *>(smem + sm.off_meta);
     float *red = reinterpret_cast<float *>(smem + sm.off_red);
     float *tot = reinterpret_cast<float *>(smem + sm.off_tot);
+    float *gb = reinterpret_cast<float *>(smem + sm.off_gb);
     const uint32_t ring = smem_u32(smem + sm.off_ring);
-    const float *gb = reinterpret_cast<const float *>(smem + sm.off_gb);
     const ProblemDesc &d = p.d;
     const unsigned R = (unsigned)p.R;
     const int K = p.K;
-    const int Vp = K * kLnBoxRows;
+    constexpr int Vt = KMAX * kLnBoxRows;                 // rows of the gamma/beta table
     if (threadIdx.x == 0) {
         for (unsigned i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kLnWarps); }
         mbar_init_fence();
     }
-    for (int i = threadIdx.x; i < Vp; i += blockDim.x) {
-        reinterpret_cast<float *>(smem + sm.off_gb)[i] = i < d.V ? __ldg(p.gamma + i) : 0.f;
-        reinterpret_cast<float *>(smem + sm.off_gb)[Vp + i] = i < d.V ? __ldg(p.beta + i) : 0.f;
+    for (int i = threadIdx.x; i < Vt; i += blockDim.x) {
+        gb[i] = i < d.V ? __ldg(p.gamma + i) : 0.f;
+        gb[Vt + i] = i < d.V ? __ldg(p.beta + i) : -INFINITY;
     }
     __syncthreads();
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -330,19 +354,24 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
         return;
     }
     const int r = lane >> 1, h = lane & 1;
+    const int vrow = 16 * w + r;                          // this thread's row inside every box
     int nrows = 0;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) nrows += (k < K && kLnBoxRows * k + 16 * w + r < d.V) ? 1 : 0;
-    const float fn = (float)nrows, inv_n = nrows > 0 ? 1.f / (float)nrows : 0.f;
+    for (int k = 0; k < KMAX; ++k) nrows += (k < K && kLnBoxRows * k + vrow < d.V) ? 1 : 0;
+    const float fn = (float)nrows, inv_n = nrows > 0 ? 1.f / (float)nrows : 0.f, fmissing = (float)(KMAX - nrows);
+    const uint32_t lane_off = (uint32_t)(w * 512 + lane * 16);
     float *mu_out = reinterpret_cast<float *>(p.ws + p.off_mu);
     float *rstd_out = reinterpret_cast<float *>(p.ws + p.off_rstd);
     float *lse_out = reinterpret_cast<float *>(p.ws + p.w.off_lse);
     float2 *lp_out = reinterpret_cast<float2 *>(p.ws + p.w.off_lp);
     const int tid = threadIdx.x;
 
-    unsigned box = 0, seq = 0;
+    SlotIter it = {0u, 0u};
+    unsigned seq = 0;
+    LN_T_DECL;
     for (;;) {
-        mbar_wait(&full[box % R], (box / R) & 1u);
+        mbar_spin(&full[it.slot], it.phase);
+        LN_T(0);
         const LnTileMeta m = metas[seq % kLnMetaRing];
         ++seq;
         if (m.kind < 0) break;
@@ -351,63 +380,72 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
         int Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
         Lb = max(0, min(Lb, d.Lmax));
         const int ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
-        // ---- the tile into registers: rows 256k + 16w + r, frames 4h .. 4h+3 ----
+        // ---- the tile into registers: rows 240k + 16w + r, frames 4h .. 4h+3 ----
         float4 z[KMAX];
+        const SlotIter first = it;
+        {
+            SlotIter s = it;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < K) {
-                const unsigned bx = box + (unsigned)k;
-                if (k > 0) mbar_wait(&full[bx % R], (bx / R) & 1u);
-                z[k] = lds128(ring + (bx % R) * kLnBoxBytes + (uint32_t)(w * 512 + lane * 16));
+            for (int k = 0; k < KMAX; ++k) {
+                z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < K) {
+                    if (k > 0) mbar_spin(&full[s.slot], s.phase);
+                    z[k] = lds128(ring + s.slot * kLnBoxBytes + lane_off);
+                    s.next(R);
+                }
             }
+            it = s;
         }
         // ---- the rows of the symbols the lattice can emit: thread c takes column c (gram_ctc.py:24-32, :155) ----
         int sym = -1;
         float4 zs0 = make_float4(0.f, 0.f, 0.f, 0.f), zs1 = zs0;
-        float gs = 0.f, bs = 0.f;
         if (tid < ncol) {
             if (tid == 0) sym = d.blank;
             else if (tid <= d.Lmax) sym = (tid - 1 < Lb) ? __ldg(d.labels + (size_t)m.b * d.Lmax + tid - 1) : -1;
             else sym = __ldg(d.bigrams + (size_t)m.b * d.Lmax + tid - 1 - d.Lmax);
             if (sym >= 0 && sym < d.V) {
-                const unsigned bx = box + (unsigned)(sym / kLnBoxRows);
-                const uint32_t a = ring + (bx % R) * kLnBoxBytes + (uint32_t)((sym % kLnBoxRows) * 32);
+                unsigned sl = first.slot + (unsigned)(sym / kLnBoxRows);
+                if (sl >= R) sl -= R;
+                const uint32_t a = ring + sl * kLnBoxBytes + (uint32_t)((sym % kLnBoxRows) * 32);
                 zs0 = lds128(a);
                 zs1 = lds128(a + 16);
-                gs = __ldg(p.gamma + sym);
-                bs = __ldg(p.beta + sym);
             } else {
                 sym = -1;
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            for (int k = 0; k < K; ++k) mbar_arrive(&empty[(box + (unsigned)k) % R]);      // the boxes can be refilled
+        if (lane == 0) {                                   // the boxes can be refilled
+            SlotIter s = first;
+            for (int k = 0; k < K; ++k) { mbar_arrive(&empty[s.slot]); s.next(R); }
         }
-        box += (unsigned)K;
+        LN_T(1);
 
         // ---- round 1: mean and centred second moment of every frame (asr/nn/layernorm.py:41-44) ----
         Moments mo[4];
         {
             float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) { sx += z[k].x; sy += z[k].y; sz += z[k].z; sw += z[k].w; }      // rows >= V are zeros
-            mo[0].mean = sx * inv_n; mo[1].mean = sy * inv_n; mo[2].mean = sz * inv_n; mo[3].mean = sw * inv_n;
+            for (int k = 0; k < KMAX; ++k) { sx += z[k].x; sy += z[k].y; sz += z[k].z; sw += z[k].w; }      // missing rows are zeros
+            const float mx_ = sx * inv_n, my_ = sy * inv_n, mz_ = sz * inv_n, mw_ = sw * inv_n;
             float qx = 0.f, qy = 0.f, qz = 0.f, qw = 0.f;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-                const bool ok = k < K && kLnBoxRows * k + 16 * w + r < d.V;
-                const float dx = z[k].x - mo[0].mean, dy = z[k].y - mo[1].mean, dz = z[k].z - mo[2].mean, dw = z[k].w - mo[3].mean;
-                if (ok) { qx = fmaf(dx, dx, qx); qy = fmaf(dy, dy, qy); qz = fmaf(dz, dz, qz); qw = fmaf(dw, dw, qw); }
+                const float dx = z[k].x - mx_, dy = z[k].y - my_, dz = z[k].z - mz_, dw = z[k].w - mw_;
+                qx = fmaf(dx, dx, qx); qy = fmaf(dy, dy, qy); qz = fmaf(dz, dz, qz); qw = fmaf(dw, dw, qw);
             }
-            mo[0].m2 = qx; mo[1].m2 = qy; mo[2].m2 = qz; mo[3].m2 = qw;
+            // a missing row read as 0 and contributed mean^2: take that back
+            mo[0].mean = mx_; mo[0].m2 = fmaf(-fmissing * mx_, mx_, qx);
+            mo[1].mean = my_; mo[1].m2 = fmaf(-fmissing * my_, my_, qy);
+            mo[2].mean = mz_; mo[2].m2 = fmaf(-fmissing * mz_, mz_, qz);
+            mo[3].mean = mw_; mo[3].m2 = fmaf(-fmissing * mw_, mw_, qw);
             mo[0].n = mo[1].n = mo[2].n = mo[3].n = fn;
         }
         int fih;
         const Moments mr = reduce_frames16(mo[0], mo[1], mo[2], mo[3], lane, merge_moments, fih);
         if (lane < 8) { const float v3[3] = {mr.n, mr.mean, mr.m2}; red_store<3>(red, 4 * h + fih, w, v3); }
+        LN_T(2);
         bar_compute();
+        LN_T(3);
         if (w < kLnTT) {
             Moments a;
             const float *src = red + (w * 16 + (lane & 15)) * 4;
@@ -416,7 +454,7 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) a = merge_moments(a, Moments::shfl_xor(a, o));
             if (lane == 0) {
-                const float var = a.m2 / a.n;                                  // sum(diff^2) / size, no epsilon (:44)
+                const float var = fmaxf(a.m2, 0.f) / a.n;                      // sum(diff^2) / size, no epsilon (:44)
                 const float rstd = 1.f / sqrtf(var);
                 tot[w * 8 + 0] = a.mean;
                 tot[w * 8 + 1] = rstd;
@@ -425,42 +463,38 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
             }
         }
         bar_compute();
-        float mu[4], rs[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { mu[j] = tot[(4 * h + j) * 8 + 0]; rs[j] = tot[(4 * h + j) * 8 + 1]; }
+        LN_T(4);
 
-        // ---- round 2: softmax statistics of a = gamma * (z - mean) * rstd + beta (asr/nn/nn.py:265) ----
+        // ---- round 2: a = gamma * (z - mean) * rstd + beta (asr/nn/nn.py:265), in place; softmax statistics ----
         MaxSum ms[4];
         {
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float rs[4], mur[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { rs[j] = tot[(4 * h + j) * 8 + 1]; mur[j] = -tot[(4 * h + j) * 8 + 0] * rs[j]; }
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-                const bool ok = k < K && kLnBoxRows * k + 16 * w + r < d.V;
-                const float zz[4] = {z[k].x, z[k].y, z[k].z, z[k].w};
-                const float gk = k < K ? gb[kLnBoxRows * k + 16 * w + r] : 0.f, bk = k < K ? gb[Vp + kLnBoxRows * k + 16 * w + r] : 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float a = fmaf((zz[j] - mu[j]) * rs[j], gk, bk);
-                    if (ok) mx[j] = fmaxf(mx[j], a);
-                }
+                const float gk = gb[kLnBoxRows * k + vrow], bk = gb[Vt + kLnBoxRows * k + vrow];      // (0, -inf) for a missing row
+                z[k].x = fmaf(fmaf(z[k].x, rs[0], mur[0]), gk, bk); m0 = fmaxf(m0, z[k].x);
+                z[k].y = fmaf(fmaf(z[k].y, rs[1], mur[1]), gk, bk); m1 = fmaxf(m1, z[k].y);
+                z[k].z = fmaf(fmaf(z[k].z, rs[2], mur[2]), gk, bk); m2 = fmaxf(m2, z[k].z);
+                z[k].w = fmaf(fmaf(z[k].w, rs[3], mur[3]), gk, bk); m3 = fmaxf(m3, z[k].w);
             }
-            float sm_[4] = {0.f, 0.f, 0.f, 0.f};
+            const float c0 = m0 == -INFINITY ? 0.f : -m0 * LOG2E_HI, c1 = m1 == -INFINITY ? 0.f : -m1 * LOG2E_HI;
+            const float c2 = m2 == -INFINITY ? 0.f : -m2 * LOG2E_HI, c3 = m3 == -INFINITY ? 0.f : -m3 * LOG2E_HI;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-                const bool ok = k < K && kLnBoxRows * k + 16 * w + r < d.V;
-                const float zz[4] = {z[k].x, z[k].y, z[k].z, z[k].w};
-                const float gk = k < K ? gb[kLnBoxRows * k + 16 * w + r] : 0.f, bk = k < K ? gb[Vp + kLnBoxRows * k + 16 * w + r] : 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float a = fmaf((zz[j] - mu[j]) * rs[j], gk, bk);
-                    if (ok) sm_[j] += ex2_approx((a - mx[j]) * LOG2E_HI);
-                }
+                s0 += ex2_approx(fmaf(z[k].x, LOG2E_HI, c0));
+                s1 += ex2_approx(fmaf(z[k].y, LOG2E_HI, c1));
+                s2 += ex2_approx(fmaf(z[k].z, LOG2E_HI, c2));
+                s3 += ex2_approx(fmaf(z[k].w, LOG2E_HI, c3));
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { ms[j].m = mx[j]; ms[j].s = sm_[j]; }
+            ms[0].m = m0; ms[0].s = s0; ms[1].m = m1; ms[1].s = s1; ms[2].m = m2; ms[2].s = s2; ms[3].m = m3; ms[3].s = s3;
         }
         const MaxSum sr = reduce_frames16(ms[0], ms[1], ms[2], ms[3], lane, merge_maxsum, fih);
         if (lane < 8) { const float v2[2] = {sr.m, sr.s}; red_store<2>(red, 4 * h + fih, w, v2); }
+        LN_T(5);
         bar_compute();
         if (w < kLnTT) {
             MaxSum a;
@@ -479,10 +513,12 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
             }
         }
         bar_compute();
+        LN_T(6);
 
         // ---- emission probabilities of the lattice's symbols ----
         if (tid < ncol) {
             const float zz[8] = {zs0.x, zs0.y, zs0.z, zs0.w, zs1.x, zs1.y, zs1.z, zs1.w};
+            const float gs = sym >= 0 ? gb[sym] : 0.f, bs = sym >= 0 ? gb[Vt + sym] : 0.f;
 #pragma unroll
             for (int f = 0; f < kLnTT; ++f) {
                 const int t = m.t0 + f;
@@ -502,12 +538,17 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
             unsigned *pc = reinterpret_cast<unsigned *>(p.ws + p.w.off_prog) + (size_t)m.b * p.w.nblk + m.t0 / kProgBlock;
             asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(pc), "r"((unsigned)nvalid) : "memory");
         }
+        LN_T(7);
     }
+    LN_T_FLUSH(w);
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
+// Rows that do not exist get gamma = beta = 0 in the shared-memory table: their dn is 0 (nothing enters the per-frame
+// sums) and what they add to this thread's dgamma/dbeta slots is never stored.  Frames that do not exist (padding) get
+// rstd = 0 and scale = 0, which makes every quantity of theirs exactly zero.  No predicates in the sweeps.
 template <int KMAX>
 __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid_constant__ CUtensorMap tmap, LnParams p,
                                                                      LnSmem sm) {
@@ -526,7 +567,7 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
     const WsLayout &wl = p.w;
     const unsigned R = (unsigned)p.R;
     const int K = p.K;
-    const int Vp = K * kLnBoxRows;
+    constexpr int Vt = KMAX * kLnBoxRows;
     const int Upad = (wl.Umax + 3) & ~3;
     if (threadIdx.x == 0) {
         for (unsigned i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kLnWarps); }
@@ -534,10 +575,11 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
         mbar_init(&abbar[1], 1);
         mbar_init_fence();
     }
-    for (int i = threadIdx.x; i < Vp; i += blockDim.x) {
+    for (int i = threadIdx.x; i < Vt; i += blockDim.x) {
         gb[i] = i < d.V ? __ldg(p.gamma + i) : 0.f;
-        gb[Vp + i] = i < d.V ? __ldg(p.beta + i) : 0.f;
+        gb[Vt + i] = i < d.V ? __ldg(p.beta + i) : 0.f;
     }
+    for (int i = threadIdx.x; i < 2 * (Vt / 32 + 1); i += blockDim.x) bm_sm[i] = 0u;
     __syncthreads();
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -546,133 +588,143 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
         return;
     }
     const int r = lane >> 1, h = lane & 1;
+    const int vrow = 16 * w + r;
     const int tid = threadIdx.x;
+    const uint32_t lane_off = (uint32_t)(w * 512 + lane * 16);
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(p.ws + wl.off_utt);
     const float *mu_in = reinterpret_cast<const float *>(p.ws + p.off_mu);
     const float *rstd_in = reinterpret_cast<const float *>(p.ws + p.off_rstd);
     const float *lse_in = reinterpret_cast<const float *>(p.ws + wl.off_lse);
     const int per = d.kind == 0 ? 2 : 3;
     const float inv_v = 1.f / (float)d.V;
+    const int nwt = Vt / 32 + 1;                          // words of the bitmap / prefix tables in shared memory
     float dgam[KMAX], dbet[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) { dgam[k] = 0.f; dbet[k] = 0.f; }
 
-    unsigned box = 0, seq = 0, n_ab = 0;
+    SlotIter it = {0u, 0u};
+    unsigned seq = 0, n_ab = 0;
+    LN_T_DECL;
     for (;;) {
-        mbar_wait(&full[box % R], (box / R) & 1u);
+        mbar_spin(&full[it.slot], it.phase);
+        LN_T(0);
         const LnTileMeta m = metas[seq % kLnMetaRing];
         ++seq;
         if (m.kind < 0) break;
-        float *dzb = p.dz + (int64_t)m.b * p.dzs_b + m.t0 + 4 * h;
+        float *dzb = p.dz + (int64_t)m.b * p.dzs_b + m.t0 + 4 * h + (int64_t)vrow * p.dzs_v;
+        const int64_t box_step = (int64_t)kLnBoxRows * p.dzs_v;
         const bool store_ok = m.t0 + 4 * h < d.T;
         if (m.kind == 1) {
             // every frame of the tile is padding: zeros (gram_ctc.py:296 -> LayerNormalization backward of zero is zero)
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                const int v = kLnBoxRows * k + 16 * w + r;
-                if (k < K && v < d.V && store_ok) *reinterpret_cast<float4 *>(dzb + (int64_t)v * p.dzs_v) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K && kLnBoxRows * k + vrow < d.V && store_ok)
+                    *reinterpret_cast<float4 *>(dzb + k * box_step) = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[box % R]);
-            ++box;
+            if (lane == 0) mbar_arrive(&empty[it.slot]);
+            it.next(R);
+            LN_T(1);
             continue;
         }
         const UttInfo ui = utt[m.b];
-        // per-frame constants of this thread's four frames; a padded frame gets rstd = 0 and scale = 0, which makes
-        // every quantity below exactly zero for it
+        const float sc = (p.per_utterance ? __ldg(p.grad_loss + m.b) : __ldg(p.grad_loss)) * p.scale;      // gram_ctc.py:291-294
+        // per-frame constants of this thread's four frames
         float rs[4], mur[4], nl[4], scj[4];
-        {
-            const float gy = p.per_utterance ? __ldg(p.grad_loss + m.b) : __ldg(p.grad_loss);
-            const float sc = gy * p.scale;                                    // gram_ctc.py:291-294
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int t = m.t0 + 4 * h + j;
-                const bool valid = t < ui.Tb;
-                const size_t o = (size_t)m.b * d.T + (valid ? t : 0);
-                const float rr = valid ? __ldg(rstd_in + o) : 0.f;
-                const float mm = valid ? __ldg(mu_in + o) : 0.f;
-                rs[j] = rr; mur[j] = -mm * rr;
-                nl[j] = valid ? -__ldg(lse_in + o) : 0.f;
-                scj[j] = valid ? sc : 0.f;
-            }
+        for (int j = 0; j < 4; ++j) {
+            const int t = m.t0 + 4 * h + j;
+            const bool valid = t < ui.Tb;
+            const size_t o = (size_t)m.b * d.T + (valid ? t : 0);
+            const float rr = valid ? __ldg(rstd_in + o) : 0.f;
+            const float mm = valid ? __ldg(mu_in + o) : 0.f;
+            rs[j] = rr; mur[j] = -mm * rr;
+            nl[j] = valid ? -__ldg(lse_in + o) : 0.f;
+            scj[j] = valid ? sc : 0.f;
         }
         // ---- phase (a): merged posteriors of the tile's frames, one warp per frame (gram_ctc.py:180-217, :290) ----
-        mbar_wait(&abbar[0], n_ab & 1u);
+        mbar_spin(&abbar[0], n_ab & 1u);
         ++n_ab;
+        LN_T(2);
         {
             const unsigned *bm_g = reinterpret_cast<const unsigned *>(p.ws + wl.off_bm) + (size_t)m.b * wl.nwords;
             const int *pc_g = reinterpret_cast<const int *>(p.ws + wl.off_pc) + (size_t)m.b * wl.nwords;
-            for (int i = tid; i < wl.nwords; i += 32 * kLnWarps) { bm_sm[i] = __ldg(bm_g + i); bm_sm[wl.nwords + i] = (unsigned)__ldg(pc_g + i); }
+            for (int i = tid; i < wl.nwords; i += 32 * kLnWarps) { bm_sm[i] = __ldg(bm_g + i); bm_sm[nwt + i] = (unsigned)__ldg(pc_g + i); }
         }
-        if (w < kLnTT && m.t0 + w < ui.Tb) {
-            float2 *a_sm = reinterpret_cast<float2 *>(smem + sm.off_ab) + (size_t)w * wl.Np;
-            const float2 *b_sm = reinterpret_cast<const float2 *>(smem + sm.off_ab) + (size_t)(kLnTT + w) * wl.Np;
-            float *e_sm = reinterpret_cast<float *>(a_sm);                    // alpha*beta/P, written over the alpha row
-            float blank_part = 0.f;
-            for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
-                const int j = j0 + lane;
-                float e = 0.f;
-                if (j < ui.Nb) e = node_posterior(a_sm[j], b_sm[j + wl.boff], ui.Ph, ui.Pl);
-                __syncwarp();                                                // e_sm aliases the alpha row: reads first
-                if (j < ui.Nb) e_sm[j] = e;
-                if (j < ui.Nb && j % per == 0) blank_part += e;
-            }
-            blank_part = warp_sum(blank_part);
-            __syncwarp();
-            const int *uoff = reinterpret_cast<const int *>(p.ws + wl.off_uoff) + (size_t)m.b * (wl.Nmax + 1);
-            const int *unode = reinterpret_cast<const int *>(p.ws + wl.off_unode) + (size_t)m.b * wl.Nmax;
-            const float gy = p.per_utterance ? __ldg(p.grad_loss + m.b) : __ldg(p.grad_loss);
-            const float sc = gy * p.scale;
-            for (int u = lane; u < ui.Ub; u += 32) {
-                const int n0 = __ldg(uoff + u), n1 = __ldg(uoff + u + 1);
-                float ps = (u == ui.ublank) ? blank_part : 0.f;
-                for (int n = n0; n < n1; ++n) {
-                    const int j = __ldg(unode + n);
-                    if (j < ui.Nb) ps += e_sm[j];
+        if (w < kLnTT) {
+            float *prow = post + w * Upad;
+            if (m.t0 + w < ui.Tb) {
+                float2 *a_sm = reinterpret_cast<float2 *>(smem + sm.off_ab) + (size_t)w * wl.Np;
+                const float2 *b_sm = reinterpret_cast<const float2 *>(smem + sm.off_ab) + (size_t)(kLnTT + w) * wl.Np;
+                float *e_sm = reinterpret_cast<float *>(a_sm);                    // alpha*beta/P, written over the alpha row
+                float blank_part = 0.f;
+                for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
+                    const int j = j0 + lane;
+                    float e = 0.f;
+                    if (j < ui.Nb) e = node_posterior(a_sm[j], b_sm[j + wl.boff], ui.Ph, ui.Pl);
+                    __syncwarp();                                                // e_sm aliases the alpha row: reads first
+                    if (j < ui.Nb) e_sm[j] = e;
+                    if (j < ui.Nb && j % per == 0) blank_part += e;
                 }
-                post[w * Upad + u] = ps * sc;
+                blank_part = warp_sum(blank_part);
+                __syncwarp();
+                const int *uoff = reinterpret_cast<const int *>(p.ws + wl.off_uoff) + (size_t)m.b * (wl.Nmax + 1);
+                const int *unode = reinterpret_cast<const int *>(p.ws + wl.off_unode) + (size_t)m.b * wl.Nmax;
+                for (int u = lane; u < ui.Ub; u += 32) {
+                    const int n0 = __ldg(uoff + u), n1 = __ldg(uoff + u + 1);
+                    float ps = (u == ui.ublank) ? blank_part : 0.f;
+                    for (int n = n0; n < n1; ++n) {
+                        const int j = __ldg(unode + n);
+                        if (j < ui.Nb) ps += e_sm[j];
+                    }
+                    prow[u] = ps * sc;
+                }
+            } else {
+                for (int u = lane; u < ui.Ub; u += 32) prow[u] = 0.f;            // a padded frame has no posterior
             }
         }
         bar_compute();
         if (tid == 0) mbar_arrive(&abbar[1]);                                 // the alpha/beta buffer can be refilled
+        LN_T(3);
 
         // ---- sweep 1: g = softmax * sc - posterior;  dn = g * gamma;  per-frame sums of dn and dn * n ----
         float4 dn[KMAX];
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        const SlotIter first = it;
+        const float *prow0 = post + (4 * h) * Upad;
+        {
+            SlotIter s = it;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            dn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < K) {
-                const unsigned bx = box + (unsigned)k;
-                if (k > 0) mbar_wait(&full[bx % R], (bx / R) & 1u);
-                const float4 zq = lds128(ring + (bx % R) * kLnBoxBytes + (uint32_t)(w * 512 + lane * 16));
-                const int v = kLnBoxRows * k + 16 * w + r;
-                const float g_ = gb[v], b_ = gb[Vp + v];
-                const unsigned word = v < d.V ? bm_sm[v >> 5] : 0u;
-                const bool issym = (word >> (v & 31)) & 1u;
-                const int u = issym ? (int)bm_sm[wl.nwords + (v >> 5)] + __popc(word & ((1u << (v & 31)) - 1u)) : 0;
-                const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
-                float dd[4];
-                float accb = 0.f, accg = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float n = fmaf(zz[j], rs[j], mur[j]);
-                    const float a = fmaf(n, g_, b_);
-                    float g = ex2_approx(fmaf(a, LOG2E_HI, nl[j])) * scj[j];
-                    if (issym && scj[j] != 0.f) g -= post[(4 * h + j) * Upad + u];
-                    if (v >= d.V || scj[j] == 0.f) g = 0.f;
-                    const float dnv = g * g_;
-                    s1[j] += dnv;
-                    s2[j] = fmaf(dnv, n, s2[j]);
-                    accb += g;
-                    accg = fmaf(g, n, accg);
-                    dd[j] = dnv;
+            for (int k = 0; k < KMAX; ++k) {
+                dn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < K) {
+                    if (k > 0) mbar_spin(&full[s.slot], s.phase);
+                    const float4 zq = lds128(ring + s.slot * kLnBoxBytes + lane_off);
+                    s.next(R);
+                    const int v = kLnBoxRows * k + vrow;
+                    const float g_ = gb[v], b_ = gb[Vt + v];
+                    const unsigned word = bm_sm[v >> 5];
+                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+                    if ((word >> (v & 31)) & 1u) {                             // ~2% of the rows: ids the lattice emits
+                        const int u = (int)bm_sm[nwt + (v >> 5)] + __popc(word & ((1u << (v & 31)) - 1u));
+                        p0 = prow0[u]; p1 = prow0[Upad + u]; p2 = prow0[2 * Upad + u]; p3 = prow0[3 * Upad + u];
+                    }
+                    const float n0 = fmaf(zq.x, rs[0], mur[0]), n1 = fmaf(zq.y, rs[1], mur[1]);
+                    const float n2 = fmaf(zq.z, rs[2], mur[2]), n3 = fmaf(zq.w, rs[3], mur[3]);
+                    const float g0 = fmaf(ex2_approx(fmaf(fmaf(n0, g_, b_), LOG2E_HI, nl[0])), scj[0], -p0);
+                    const float g1 = fmaf(ex2_approx(fmaf(fmaf(n1, g_, b_), LOG2E_HI, nl[1])), scj[1], -p1);
+                    const float g2 = fmaf(ex2_approx(fmaf(fmaf(n2, g_, b_), LOG2E_HI, nl[2])), scj[2], -p2);
+                    const float g3 = fmaf(ex2_approx(fmaf(fmaf(n3, g_, b_), LOG2E_HI, nl[3])), scj[3], -p3);
+                    const float d0 = g0 * g_, d1 = g1 * g_, d2 = g2 * g_, d3 = g3 * g_;
+                    s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
+                    s2[0] = fmaf(d0, n0, s2[0]); s2[1] = fmaf(d1, n1, s2[1]); s2[2] = fmaf(d2, n2, s2[2]); s2[3] = fmaf(d3, n3, s2[3]);
+                    dbet[k] += (g0 + g1) + (g2 + g3);                          // bias backward: sum over (b, t)
+                    dgam[k] = fmaf(g0, n0, fmaf(g1, n1, fmaf(g2, n2, fmaf(g3, n3, dgam[k]))));      // scale backward
+                    dn[k] = make_float4(d0, d1, d2, d3);
                 }
-                dbet[k] += accb;                                             // bias backward: sum over (b, t)
-                dgam[k] += accg;                                             // scale backward: sum of g * normalised z
-                dn[k] = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
+            it = s;
         }
+        LN_T(4);
         // ---- the two per-frame sums of LayerNormalization's backward (asr/nn/layernorm.py:48-60) ----
         int fih;
         const Pair2 pr = reduce_frames16(Pair2{s1[0], s2[0]}, Pair2{s1[1], s2[1]}, Pair2{s1[2], s2[2]}, Pair2{s1[3], s2[3]}, lane,
@@ -688,40 +740,43 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
             if (lane == 0) { tot[w * 8 + 0] = a * inv_v; tot[w * 8 + 1] = b * inv_v; }
         }
         bar_compute();
-        float c1[4], c2[4];
+        LN_T(5);
+        float c1r[4], c2r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { c1[j] = tot[(4 * h + j) * 8 + 0]; c2[j] = tot[(4 * h + j) * 8 + 1]; }
+        for (int j = 0; j < 4; ++j) { c1r[j] = -tot[(4 * h + j) * 8 + 0] * rs[j]; c2r[j] = -tot[(4 * h + j) * 8 + 1] * rs[j]; }
 
         // ---- sweep 2: dz = rstd * (dn - mean_v(dn) - n * mean_v(dn * n)), stored in z's own layout ----
+        {
+            SlotIter s = first;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            if (k < K) {
-                const unsigned bx = box + (unsigned)k;
-                const float4 zq = lds128(ring + (bx % R) * kLnBoxBytes + (uint32_t)(w * 512 + lane * 16));
-                const int v = kLnBoxRows * k + 16 * w + r;
-                const float zz[4] = {zq.x, zq.y, zq.z, zq.w};
-                const float dd[4] = {dn[k].x, dn[k].y, dn[k].z, dn[k].w};
-                float o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float n = fmaf(zz[j], rs[j], mur[j]);
-                    o[j] = rs[j] * (dd[j] - c1[j] - n * c2[j]);
+            for (int k = 0; k < KMAX; ++k) {
+                if (k < K) {
+                    const float4 zq = lds128(ring + s.slot * kLnBoxBytes + lane_off);
+                    float4 o;
+                    o.x = fmaf(fmaf(zq.x, rs[0], mur[0]), c2r[0], fmaf(dn[k].x, rs[0], c1r[0]));
+                    o.y = fmaf(fmaf(zq.y, rs[1], mur[1]), c2r[1], fmaf(dn[k].y, rs[1], c1r[1]));
+                    o.z = fmaf(fmaf(zq.z, rs[2], mur[2]), c2r[2], fmaf(dn[k].z, rs[2], c1r[2]));
+                    o.w = fmaf(fmaf(zq.w, rs[3], mur[3]), c2r[3], fmaf(dn[k].w, rs[3], c1r[3]));
+                    if (kLnBoxRows * k + vrow < d.V && store_ok) *reinterpret_cast<float4 *>(dzb + k * box_step) = o;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s.slot]);
+                    s.next(R);
                 }
-                if (v < d.V && store_ok) *reinterpret_cast<float4 *>(dzb + (int64_t)v * p.dzs_v) = make_float4(o[0], o[1], o[2], o[3]);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[bx % R]);
             }
         }
-        box += (unsigned)K;
+        LN_T(6);
         bar_compute();            // red / tot / post / bitmap are reused by the next tile
+        LN_T(7);
     }
+    LN_T_FLUSH(w);
     // ---- this CTA's share of dgamma / dbeta: the two halves of a row pair up, then one partial row per CTA ----
+    const int Vp = K * kLnBoxRows;
     float *part = reinterpret_cast<float *>(p.ws + p.off_part) + (size_t)blockIdx.x * 2 * Vp;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         const float g = dgam[k] + __shfl_xor_sync(0xffffffffu, dgam[k], 1);
         const float b = dbet[k] + __shfl_xor_sync(0xffffffffu, dbet[k], 1);
-        const int v = kLnBoxRows * k + 16 * w + r;
+        const int v = kLnBoxRows * k + vrow;
         if (k < K && h == 0) { part[v] = g; part[Vp + v] = b; }
     }
 }
@@ -738,6 +793,8 @@ __global__ void ln_reduce_params_kernel(const float *part, int nparts, int Vp, i
     if (dgamma) dgamma[v] = g;
     if (dbeta) dbeta[v] = b;
 }
+
+static int ln_kmax(int K) { return K <= 5 ? 5 : (K <= 9 ? 9 : (K <= 15 ? 15 : 17)); }
 
 // ---- host side ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -789,6 +846,10 @@ cudaError_t launch_ln(Kern kern, int grid, const CUtensorMap &map, const LnParam
 
 }  // namespace
 
+#ifdef B200CTC_EXPERIMENT
+void ln_set_debug(long long *p) { cudaMemcpyToSymbol(g_ln_dbg, &p, sizeof(p)); }
+#endif
+
 LnLayout make_ln_layout(int kind, int B, int T, int V, int Lmax) {
     LnLayout l;
     l.w = make_layout(kind, B, T, V, Lmax);
@@ -811,7 +872,7 @@ int ln_supported(int kind, int B, int T, int V, int Lmax, int64_t zs_v, int64_t 
     return encode_tiled_fn() != nullptr;
 }
 
-static int ln_kmax(int K) { return K <= 5 ? 5 : (K <= 9 ? 9 : (K <= 15 ? 15 : 17)); }
+
 
 cudaError_t launch_ln_forward(const ProblemDesc &d, const LnLayout &ll, void *ws, const float *z, int64_t zs_b, int64_t zs_v,
                               const float *gamma, const float *beta, size_t smem_reserve, cudaStream_t stream) {
@@ -823,8 +884,9 @@ cudaError_t launch_ln_forward(const ProblemDesc &d, const LnLayout &ll, void *ws
     p.off_mu = ll.off_mu; p.off_rstd = ll.off_rstd; p.off_part = ll.off_part;
     p.K = (d.V + kLnBoxRows - 1) / kLnBoxRows;
     p.nTB = (d.T + kLnTT - 1) / kLnTT;
-    LnSmem sm = plan_ln_smem(p.K, 0, 0, (size_t)2 * p.K * kLnBoxRows, 0, smem_reserve);
-    if (sm.R < p.K + 2) sm = plan_ln_smem(p.K, 0, 0, (size_t)2 * p.K * kLnBoxRows, 0, 0);     // no room to share the SM
+    const size_t gbf = (size_t)2 * ln_kmax(p.K) * kLnBoxRows;
+    LnSmem sm = plan_ln_smem(p.K, 0, 0, gbf, 0, smem_reserve);
+    if (sm.R < p.K + 2) sm = plan_ln_smem(p.K, 0, 0, gbf, 0, 0);     // no room to share the SM
     if (sm.R < p.K + 2) return cudaErrorInvalidConfiguration;
     if (sm.R > 2 * p.K + 4) {                     // more than two tiles' worth buys nothing; leave the rest to the L1
         sm.total -= (size_t)(sm.R - (2 * p.K + 4)) * kLnBoxBytes;
@@ -859,8 +921,9 @@ cudaError_t launch_ln_backward(const GradParams &g, const LnLayout &ll, const vo
     p.grad_loss = g.grad_loss; p.per_utterance = g.per_utterance; p.scale = g.scale;
     p.dz = dz; p.dzs_b = dzs_b; p.dzs_v = dzs_v; p.dgamma = dgamma; p.dbeta = dbeta;
     const int Vp = p.K * kLnBoxRows;
-    const LnSmem sm = plan_ln_smem(p.K, (size_t)2 * kLnTT * ll.w.Np * 8, (size_t)kLnTT * ((ll.w.Umax + 3) & ~3), (size_t)2 * Vp,
-                                   (size_t)2 * ll.w.nwords);
+    const int Vt = ln_kmax(p.K) * kLnBoxRows;
+    const LnSmem sm = plan_ln_smem(p.K, (size_t)2 * kLnTT * ll.w.Np * 8, (size_t)kLnTT * ((ll.w.Umax + 3) & ~3), (size_t)2 * Vt,
+                                   (size_t)2 * (Vt / 32 + 1));
     if (sm.R < p.K + 2) { note_failure_site("shared-memory plan"); return cudaErrorInvalidConfiguration; }
     p.R = sm.R;
     CUtensorMap map;

@@ -36,6 +36,12 @@ struct RowMeta {
     int kind;      // 0: full work, 1: argmax only (padded frame), -1: stop
     unsigned seq;  // row sequence number currently occupying the slot (published before the barrier is armed)
     int off;       // the row's element 0 sits `off` floats into the slot (0..3: misalignment of the row in global memory)
+    // per-row constants the producer fetches on the consumers' behalf (a dependent global load at the start of a
+    // consumer's row is ~800 cycles during which the slot is held for nothing):
+    int Lb;        // softmax/gather kernel: clamped label length of the utterance
+    float lse;     // gradient kernel: log2 normaliser of the frame
+    float sc;      // gradient kernel: upstream gradient * scale of the utterance
+    int pad_;
 };
 
 // bytes a slot needs for a row of V floats wherever it starts

@@ -320,10 +320,12 @@ __device__ __forceinline__ void signal_warp(SignalFifo *f, int nc, int lane, uns
 // four independent accumulators -- no loop-carried maximum, no rescaling branch.  The references are aligned at the
 // end with exact powers of two.  A reference that is not the maximum only moves the intermediate sums along the
 // float32 exponent range (no precision is lost); what it cannot absorb is an element more than ~2^100 above a
-// lane's reference -- the sum then overflows to +inf (or a NaN / all -inf row shows up) and the caller redoes the
-// row with the running-maximum scan below.  Returns false in that case.
-__device__ __forceinline__ bool fast_row_lse(const float4 *__restrict__ row4, int n4, int lane, float &la, float &lb) {
-    float ref = -INFINITY, nr = 0.f;
+// lane's reference -- the sum then overflows to +inf (or a NaN / all -inf row shows up), fast_row_scan reports it
+// (warp-uniform) and the caller redoes the row with the running-maximum scan below.  Split in two so that the ring
+// slot can be handed back between the scan (which needs the row) and the warp reductions (which do not).
+__device__ __forceinline__ bool fast_row_scan(const float4 *__restrict__ row4, int n4, int lane, float &ref, float &sl) {
+    float nr = 0.f;
+    ref = -INFINITY;
     if (lane < n4) {
         const float4 v = row4[lane];
         const float cm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));       // NaNs are dropped here and caught by the sum
@@ -338,16 +340,20 @@ __device__ __forceinline__ bool fast_row_lse(const float4 *__restrict__ row4, in
         s2 += ex2_approx(fmaf(v.z, LOG2E_HI, nr));
         s3 += ex2_approx(fmaf(v.w, LOG2E_HI, nr));
     }
-    const float sl = (s0 + s1) + (s2 + s3);
+    sl = (s0 + s1) + (s2 + s3);
+    // every lane's partial sum must be an ordinary number (NaN fails both comparisons) with room for 32 of them to
+    // be added, its reference an exactly representable integer; and the row must have some probability mass
+    const bool lane_ok = sl >= 0.f && sl < 1e30f && (ref == -INFINITY || fabsf(ref) < 4194304.f);
+    return __all_sync(0xffffffffu, lane_ok) && __any_sync(0xffffffffu, sl > 0.f);
+}
+__device__ __forceinline__ void fast_row_finish(float ref, float sl, float &la, float &lb) {
     const float R = warp_max(ref);
     const float S = warp_sum(sl * ex2_approx(ref - R));                  // ref - R: integer <= 0 (or -inf for an empty lane)
-    if (!(S > 0.f && S < INFINITY && fabsf(R) < 4194304.f)) return false;    // warp-uniform
     const float lg = log2f(S);
     const float a = R + lg;                                              // TwoSum(R, lg)
     const float bb = a - R;
     la = a;
     lb = (R - (a - bb)) + (lg - bb);
-    return true;
 }
 
 template <bool ARGMAX>
@@ -382,12 +388,14 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             r_wait0 += K1_CLK() - c0;
             if (base >= frames) break;
             const unsigned f = base + (unsigned)lane;
-            int b = 0, t = 0;
+            int b = 0, t = 0, Lb = 0;
             bool valid = false, need = false;
             if (lane < ring.batch && f < frames) {
                 frame_of_ticket(f, d.B, d.T, (d.progress & 2) != 0, b, t);
                 int Tb = d.input_lengths ? __ldg(d.input_lengths + b) : d.T;
+                Lb = d.label_lengths ? __ldg(d.label_lengths + b) : d.Lmax;
                 Tb = max(0, min(Tb, d.T));
+                Lb = max(0, min(Lb, d.Lmax));
                 valid = t < Tb;
                 need = valid || ARGMAX;
             }
@@ -406,6 +414,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
                     const int off = row_misalignment(src);
                     const uint32_t span = row_span_bytes(off, d.V);
                     ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = valid ? 0 : 1; ring.meta[s].off = off;
+                    ring.meta[s].Lb = Lb;
                     ring_publish(ring, s, myq);
                     mbar_arrive_expect_tx(&ring.full[s], span);
                     bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
@@ -470,8 +479,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
         int syms[kGatherRegs];
         bool early = false;
         if (m.kind == 0) {
-            Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
-            Lb = max(0, min(Lb, d.Lmax));
+            Lb = m.Lb;
             ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
             early = ncol <= 32 * kGatherRegs;
             if (early) {
@@ -480,9 +488,10 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             }
         }
         float la = 0.f, lb = 0.f;
-        bool have_lse = false;
-        if (!ARGMAX && m.kind == 0) have_lse = fast_row_lse(row4, n4, lane, la, lb);
-        if (!have_lse) {
+        float ref = 0.f, sl = 0.f;
+        bool fast = false;
+        if (!ARGMAX && m.kind == 0) fast = fast_row_scan(row4, n4, lane, ref, sl);
+        if (!fast) {
             // one pass with a per-lane running (max, sum of 2^((x - max) * log2 e)) and the greedy index; a padded
             // frame (argmax only) skips the exponentials
             RowStat st;
@@ -524,7 +533,6 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             }
         }
         if (m.kind == 0) {
-            if (lane == 0) lse_out[(size_t)m.b * d.T + m.t] = la + lb;
             float2 *lprow = lp_out + ((size_t)m.b * d.T + m.t) * w.W;
             if (early) {
                 // The usual case.  Only the activations at the emitted ids are still needed from the row: fetch them,
@@ -540,12 +548,16 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ring.empty[s]);
                 released = true;
+                if (fast) fast_row_finish(ref, sl, la, lb);
+                if (lane == 0) lse_out[(size_t)m.b * d.T + m.t] = la + lb;
 #pragma unroll
                 for (int k = 0; k < kGatherRegs; ++k) {
                     const int cidx = lane + 32 * k;
                     if (cidx < ncol) lprow[cidx] = ok[k] ? emission_pair(xv[k], la, lb) : make_float2(0.f, SENT);
                 }
             } else {
+                if (fast) fast_row_finish(ref, sl, la, lb);
+                if (lane == 0) lse_out[(size_t)m.b * d.T + m.t] = la + lb;
                 for (int cidx = lane; cidx < ncol; cidx += 32) {
                     const int sym = symbol_of(cidx);
                     float2 v = make_float2(0.f, SENT);
