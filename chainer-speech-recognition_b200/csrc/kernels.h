@@ -83,7 +83,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
 constexpr int kLnMaxParts = 160;          // CTAs of the backward kernel (>= SM count): rows of the dgamma/dbeta partial sums
 struct LnLayout {
     WsLayout w;                           // the regular workspace ...
-    size_t off_mu, off_rstd, off_part;    // ... + per-frame mean and 1/std, per-CTA dgamma/dbeta partial rows
+    size_t off_mu, off_rstd, off_lse, off_part;   // ... + per-frame mean, 1/std, log2 normaliser; per-CTA dgamma/dbeta partial rows
     size_t total;
 };
 LnLayout make_ln_layout(int kind, int B, int T, int V, int Lmax);

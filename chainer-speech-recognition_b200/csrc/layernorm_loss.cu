@@ -60,27 +60,49 @@ __device__ long long *g_ln_dbg = nullptr;
 #define LN_T_FLUSH(w) ((void)0)
 #endif
 
-struct LnTileMeta { int b, t0, kind, pad; };               // kind 0: work, 1: padded frames only (backward), -1: stop
+// Everything a tile's consumers need to know about it, fetched by the producer lane (a dependent global load at the
+// start of a tile would stall all fifteen compute warps for its round trip)
+struct LnTileMeta {
+    int b, t0, kind;                 // kind 0: work, -1: stop
+    int Tb, Lb;                      // clamped input / label length of the utterance
+    int Nb, Ub, ublank;              // backward: lattice nodes, distinct symbols, position of the blank among them
+    float Ph, Pl, sc;                // backward: P as in UttInfo, upstream gradient * scale
+    int pad;
+};
+
+constexpr int kLnFifo = 8;
+constexpr int kLnBlankChunks = 64;                         // 32-node chunks of the largest lattice (Nmax <= 2048)
+struct LnSignalFifo {                // forward: finished tiles on their way to the progress counters
+    int4 entry[kLnFifo];             // (b, 16-frame block, valid frames, 0); b < 0: done
+    unsigned head, tail;
+};
 
 struct LnSmem {
-    size_t off_ring, off_full, off_empty, off_meta, off_red, off_tot, off_ab, off_abbar, off_post, off_gb, off_bm, total;
+    size_t off_ring, off_full, off_empty, off_meta, off_red, off_tot, off_fc, off_fifo, off_ab, off_abbar, off_post, off_ebuf,
+        off_csr, off_gb, off_bm, off_zero, total;
     int R;
 };
 
-// ring of R boxes + everything else a kernel needs; ab_bytes / post_floats / gb_floats / bm_words are 0 in the forward kernel
-LnSmem plan_ln_smem(int K, size_t ab_bytes, size_t post_floats, size_t gb_floats, size_t bm_words, size_t smem_reserve = 0) {
+// ring of R boxes + everything else a kernel needs (the backward-only parts are 0 in the forward kernel)
+LnSmem plan_ln_smem(int K, size_t ab_bytes, size_t post_floats, size_t ebuf_floats, size_t csr_ints, size_t gb_floats,
+                    size_t bm_words, size_t zero_bytes, size_t smem_reserve = 0) {
     LnSmem s;
     size_t o = 0;
     s.off_full = o;  o += 8 * 64;
     s.off_empty = o; o += 8 * 64;
-    s.off_abbar = o; o += 16;
+    s.off_abbar = o; o += 32;                               // alpha/beta full, empty; output full; spare
     s.off_meta = o;  o += sizeof(LnTileMeta) * kLnMetaRing;
     s.off_red = o;   o += sizeof(float) * 16 * kLnTT * 4;
     s.off_tot = o;   o += sizeof(float) * kLnTT * 8;
+    s.off_fc = o;    o += sizeof(float) * 3 * kLnTT;        // per-frame mean, 1/std, log2 normaliser (16-byte aligned)
+    s.off_fifo = o;  o += sizeof(LnSignalFifo);
     s.off_post = o;  o += sizeof(float) * post_floats;
+    s.off_ebuf = o;  o += sizeof(float) * ebuf_floats;
+    s.off_csr = o;   o += sizeof(int) * csr_ints;
     s.off_gb = o;    o += sizeof(float) * gb_floats;
     s.off_bm = o;    o += sizeof(unsigned) * bm_words;
     o = align_up(o, 128);
+    s.off_zero = o;  o += align_up(zero_bytes, 128);
     s.off_ab = o;    o += align_up(ab_bytes, 128);
     s.off_ring = o;
     const long long room = (smem_reserve ? 228 * 1024 - 2 * 1024 - (long long)smem_reserve : 227 * 1024) - (long long)o;
@@ -99,10 +121,31 @@ __device__ __forceinline__ void tma_load_box(void *dst, const CUtensorMap *map, 
         "l"(map), "r"(t0), "r"(v0), "r"(b), "r"(smem_u32(bar))
         : "memory");
 }
+// shared -> global tile store (bulk-group completion); elements outside the tensor are not written
+__device__ __forceinline__ void tma_store_box(const CUtensorMap *map, const void *src, int t0, int v0, int b) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(t0), "r"(v0),
+                 "r"(b), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
+}
+#ifdef B200CTC_EXPERIMENT
+#define LN_WATCHDOG(site, it_) do { if (++(it_) > (1ll << 25)) { printf("LN HANG site %d block %d thread %d\n", site, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define LN_WATCHDOG(site, it_) ((void)0)
+#endif
+// For the lanes of the producer warp, which share ONE warp while running different loops: a suspending wait in one
+// lane would put the others to sleep with it, so these lanes only probe (test_wait returns at once) and nap.
+__device__ __forceinline__ void mbar_poll(uint64_t *bar, uint32_t parity, int site = 0) {
+    long long it_ = 0;
+    (void)it_; (void)site;
+    while (!mbar_test_wait(bar, parity)) { __nanosleep(40); LN_WATCHDOG(site, it_); }
 }
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kLnWarps) : "memory"); }
 
@@ -219,8 +262,9 @@ struct LnParams {
     const float *z;                 // (B, V, T): element (b, v, t) at z[b*zs_b + v*zs_v + t]
     int64_t zs_b, zs_v;
     const float *gamma, *beta;
-    size_t off_mu, off_rstd, off_part;
-    int K;                          // boxes per tile = ceil(V / 256)
+    size_t off_mu, off_rstd, off_lse, off_part;
+    int Tq;                         // row pitch of the per-frame arrays: T rounded up to a multiple of 4 (16-byte rows)
+    int K;                          // boxes per tile = ceil(V / 240)
     int nTB;                        // 8-frame blocks = ceil(T / 8)
     int R;                          // ring slots
     // backward only
@@ -232,12 +276,15 @@ struct LnParams {
     float *dgamma, *dbeta;
 };
 
-// ---- producer warp: tickets -> tile records -> TMA box loads, as far ahead as the ring allows ----
+// ---- producer lane: tickets -> tile records -> TMA box loads, as far ahead as the ring allows ----
 // BACKWARD: tile i of the kernel goes to CTA i % gridDim.x (a fixed assignment makes the dgamma/dbeta sums
 // deterministic); forward: tiles are drawn from the global ticket counter (variable-length utterances balance
 // themselves, and the order serves the lattice kernel running next to it).
+// Tiles whose frames are all padding never reach the compute warps: the forward pass skips them, the backward pass
+// stores their zeros (gram_ctc.py:296; LayerNormalization's backward of zero is zero) straight from a box of zeros.
 template <bool BACKWARD>
-__device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const LnParams &p, unsigned char *smem, const LnSmem &sm) {
+__device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const CUtensorMap *tmap_out, const LnParams &p,
+                                            unsigned char *smem, const LnSmem &sm) {
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + sm.off_full);
     uint64_t *empty = reinterpret_cast<uint64_t *>(smem + sm.off_empty);
     uint64_t *abbar = reinterpret_cast<uint64_t *>(smem + sm.off_abbar);          // [0] full, [1] empty
@@ -249,7 +296,7 @@ __device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const LnPar
     const int K = p.K;
     unsigned box = 0, seq = 0, n_ab = 0;             // boxes / tile records / alpha-beta loads issued by this CTA
     auto claim = [&](unsigned bx) {                  // wait until the box slot's previous occupant was released
-        if (bx >= R) mbar_wait(&empty[bx % R], ((bx / R) - 1u) & 1u);
+        if (bx >= R) mbar_poll(&empty[bx % R], ((bx / R) - 1u) & 1u, BACKWARD ? 11 : 1);
         return (int)(bx % R);
     };
     unsigned f = BACKWARD ? blockIdx.x : atomicAdd(&hdr->k1_ticket, 1u);
@@ -260,32 +307,48 @@ __device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const LnPar
         f = fnext;
         if (!real) continue;
         const int t0 = tb * kLnTT;
-        int Tb;
-        if (BACKWARD) Tb = utt[b].Tb;
-        else { Tb = p.d.input_lengths ? __ldg(p.d.input_lengths + b) : p.d.T; Tb = max(0, min(Tb, p.d.T)); }
-        const bool padded = t0 >= Tb;
-        if (padded && !BACKWARD) continue;            // forward: frames nobody reads
-        // the tile record travels with the tile's first box (a padded tile takes a box slot that carries no data)
-        const int slot0 = claim(box);
-        LnTileMeta &m = metas[seq % kLnMetaRing];
-        m.b = b; m.t0 = t0; m.kind = padded ? 1 : 0;
-        ++seq;
-        if (padded) {
-            mbar_arrive(&full[slot0]);
-            ++box;
+        LnTileMeta mm;
+        mm.b = b; mm.t0 = t0; mm.kind = 0; mm.pad = 0;
+        mm.Nb = 0; mm.Ub = 0; mm.ublank = 0; mm.Ph = 0.f; mm.Pl = 0.f; mm.sc = 0.f;
+        if (BACKWARD) {
+            const UttInfo ui = utt[b];
+            mm.Tb = ui.Tb; mm.Lb = ui.Lb; mm.Nb = ui.Nb; mm.Ub = ui.Ub; mm.ublank = ui.ublank; mm.Ph = ui.Ph; mm.Pl = ui.Pl;
+            mm.sc = (p.per_utterance ? __ldg(p.grad_loss + b) : __ldg(p.grad_loss)) * p.scale;      // gram_ctc.py:291-294
+        } else {
+            int Tb = p.d.input_lengths ? __ldg(p.d.input_lengths + b) : p.d.T;
+            int Lb = p.d.label_lengths ? __ldg(p.d.label_lengths + b) : p.d.Lmax;
+            mm.Tb = max(0, min(Tb, p.d.T));
+            mm.Lb = max(0, min(Lb, p.d.Lmax));
+        }
+        if (t0 >= mm.Tb) {                            // nothing but padding
+            if (BACKWARD) {
+                for (int k = 0; k < K; ++k) tma_store_box(tmap_out, smem + sm.off_zero, t0, k * kLnBoxRows, b);
+                bulk_commit();
+            }
             continue;
         }
+        // the tile record travels with the tile's first box
+        const int slot0 = claim(box);
+        metas[seq % kLnMetaRing] = mm;
+        ++seq;
         if (BACKWARD) {
-            // alpha and beta rows of the tile's frames: contiguous in the workspace ([b][t][Np])
+            // alpha and beta rows of the tile's frames (contiguous in the workspace: [b][t][Np]) and the per-frame
+            // mean, 1/std and log2 normaliser the forward pass left
             const int nfr = min(kLnTT, p.d.T - t0);
             const uint32_t bytes = (uint32_t)nfr * (uint32_t)p.w.Np * 8u;
-            if (n_ab > 0) mbar_wait(&abbar[1], (n_ab - 1u) & 1u);
+            const uint32_t fbytes = (uint32_t)min(kLnTT, p.Tq - t0) * 4u;          // 16 or 32 bytes
+            if (n_ab > 0) mbar_poll(&abbar[1], (n_ab - 1u) & 1u, 12);
             ++n_ab;
+            const size_t fo = (size_t)b * p.Tq + t0;                                // 16-byte aligned rows of the per-frame arrays
             const float2 *av = reinterpret_cast<const float2 *>(p.ws + p.w.off_av) + ((size_t)b * p.d.T + t0) * p.w.Np;
             const float2 *bv = reinterpret_cast<const float2 *>(p.ws + p.w.off_bv) + ((size_t)b * p.d.T + t0) * p.w.Np;
-            mbar_arrive_expect_tx(&abbar[0], 2 * bytes);
+            float *fc = reinterpret_cast<float *>(smem + sm.off_fc);
+            mbar_arrive_expect_tx(&abbar[0], 2 * bytes + 3 * fbytes);
             bulk_g2s(smem + sm.off_ab, av, bytes, &abbar[0]);
             bulk_g2s(smem + sm.off_ab + (size_t)kLnTT * p.w.Np * 8, bv, bytes, &abbar[0]);
+            bulk_g2s(fc, reinterpret_cast<const float *>(p.ws + p.off_mu) + fo, fbytes, &abbar[0]);
+            bulk_g2s(fc + kLnTT, reinterpret_cast<const float *>(p.ws + p.off_rstd) + fo, fbytes, &abbar[0]);
+            bulk_g2s(fc + 2 * kLnTT, reinterpret_cast<const float *>(p.ws + p.off_lse) + fo, fbytes, &abbar[0]);
         }
         for (int k = 0; k < K; ++k, ++box) {
             const int slot = k == 0 ? slot0 : claim(box);
@@ -296,6 +359,72 @@ __device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const LnPar
     const int slot0 = claim(box);                    // stop record
     metas[seq % kLnMetaRing].kind = -1;
     mbar_arrive(&full[slot0]);
+    if (BACKWARD) bulk_wait_all<0>();                // the zero box must outlive the stores that read it
+}
+
+// ---- forward, lane 1 of the producer warp: finished tiles -> progress counters of the lattice kernel ----
+// The "rows written" signal is a release at GPU scope and costs ~1.5 us (common.cuh): it must not sit on a compute warp.
+__device__ __forceinline__ void ln_signaller(const LnParams &p, unsigned char *smem, const LnSmem &sm) {
+    LnSignalFifo *ff = reinterpret_cast<LnSignalFifo *>(smem + sm.off_fifo);
+    unsigned taken = 0;
+    for (;;) {
+        long long it_ = 0;
+        (void)it_;
+        while (*reinterpret_cast<volatile unsigned *>(&ff->head) == taken) { __nanosleep(100); LN_WATCHDOG(2, it_); }
+        __threadfence_block();
+        const volatile int *e = reinterpret_cast<volatile int *>(&ff->entry[taken % kLnFifo]);
+        const int b = e[0], blk = e[1], n = e[2];
+        *reinterpret_cast<volatile unsigned *>(&ff->tail) = ++taken;
+        if (b < 0) break;
+        unsigned *pc = reinterpret_cast<unsigned *>(p.ws + p.w.off_prog) + (size_t)b * p.w.nblk + blk;
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(pc), "r"((unsigned)n) : "memory");
+    }
+}
+__device__ __forceinline__ void ln_signal_push(LnSignalFifo *ff, unsigned &pushed, int b, int blk, int n) {
+    long long it_ = 0;
+    (void)it_;
+    while (pushed - *reinterpret_cast<volatile unsigned *>(&ff->tail) >= (unsigned)kLnFifo) { __nanosleep(64); LN_WATCHDOG(3, it_); }
+    ff->entry[pushed % kLnFifo] = make_int4(b, blk, n, 0);
+    __threadfence_block();                           // the tile's stores (ordered by the CTA barrier) and the entry, then the head
+    *reinterpret_cast<volatile unsigned *>(&ff->head) = ++pushed;
+}
+
+// ---- backward, lane 1 of the producer warp: finished tiles (dz images in their boxes) -> TMA tile stores ----
+__device__ __forceinline__ void ln_storer(const CUtensorMap *tmap_out, const LnParams &p, unsigned char *smem, const LnSmem &sm) {
+    uint64_t *empty = reinterpret_cast<uint64_t *>(smem + sm.off_empty);
+    uint64_t *outbar = reinterpret_cast<uint64_t *>(smem + sm.off_abbar) + 2;
+    const LnTileMeta *metas = reinterpret_cast<const LnTileMeta *>(smem + sm.off_meta);
+    const unsigned R = (unsigned)p.R;
+    // How many tiles there will be is announced through a plain word, NOT as one more arrival on the barrier: the
+    // compute warps meet the stop record nanoseconds after their last tile, and two completions in a row would move the
+    // barrier's parity bit back to where this lane is still waiting for it.  (Two TILE arrivals can never run ahead of
+    // this lane: a tile's boxes only become free when this lane has stored the tile before it.)
+    const volatile unsigned *total = &reinterpret_cast<const LnSignalFifo *>(smem + sm.off_fifo)->head;      // tiles + 1, 0 = not known yet
+    unsigned slot = 0;
+    for (unsigned n = 0;; ++n) {
+        bool stop = false;
+        long long it_ = 0;
+        (void)it_;
+        while (!mbar_test_wait(outbar, n & 1u)) {
+            if (*total == n + 1u) { stop = true; break; }
+            __nanosleep(40);
+            LN_WATCHDOG(13, it_);
+        }
+        if (stop) break;
+        const LnTileMeta m = metas[n % kLnMetaRing];
+        unsigned s = slot;
+        for (int k = 0; k < p.K; ++k) {
+            tma_store_box(tmap_out, smem + sm.off_ring + (size_t)s * kLnBoxBytes, m.t0, k * kLnBoxRows, m.b);
+            if (++s == R) s = 0;
+        }
+        bulk_commit();
+        bulk_wait_read<0>();                         // the engine has read the boxes: hand them back to the loader
+        for (int k = 0; k < p.K; ++k) {
+            mbar_arrive(&empty[slot]);
+            if (++slot == R) slot = 0;
+        }
+    }
+    bulk_wait_all<0>();
 }
 
 // cross-warp stage of a per-frame reduction: the lanes that carry a warp's result for frame f write it to
@@ -311,9 +440,16 @@ struct SlotIter {
     unsigned slot, phase;
     __device__ __forceinline__ void next(unsigned R) { if (++slot == R) { slot = 0; phase ^= 1u; } }
 };
-__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }            // try_wait suspends the thread in hardware while it waits
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity, int site = 0) {
+    long long it_ = 0;
+    (void)it_; (void)site;
+#ifdef B200CTC_EXPERIMENT
+    while (!mbar_test_wait(bar, parity)) { LN_WATCHDOG(site, it_); }     // watchdog build: probe, count, report
+#else
+    while (!mbar_try_wait(bar, parity)) { }                              // try_wait suspends the thread in hardware while it waits
+#endif
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // forward
@@ -341,6 +477,8 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
     if (threadIdx.x == 0) {
         for (unsigned i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kLnWarps); }
         mbar_init_fence();
+        reinterpret_cast<LnSignalFifo *>(smem + sm.off_fifo)->head = 0u;
+        reinterpret_cast<LnSignalFifo *>(smem + sm.off_fifo)->tail = 0u;
     }
     for (int i = threadIdx.x; i < Vt; i += blockDim.x) {
         gb[i] = i < d.V ? __ldg(p.gamma + i) : 0.f;
@@ -349,8 +487,10 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
     __syncthreads();
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    LnSignalFifo *fifo = reinterpret_cast<LnSignalFifo *>(smem + sm.off_fifo);
     if (w == kLnWarps) {
-        if (lane == 0) ln_producer<false>(&tmap, p, smem, sm);
+        if (lane == 0) ln_producer<false>(&tmap, nullptr, p, smem, sm);
+        else if (lane == 1 && (d.progress & 1)) ln_signaller(p, smem, sm);
         return;
     }
     const int r = lane >> 1, h = lane & 1;
@@ -362,24 +502,29 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
     const uint32_t lane_off = (uint32_t)(w * 512 + lane * 16);
     float *mu_out = reinterpret_cast<float *>(p.ws + p.off_mu);
     float *rstd_out = reinterpret_cast<float *>(p.ws + p.off_rstd);
-    float *lse_out = reinterpret_cast<float *>(p.ws + p.w.off_lse);
+    float *lse_out = reinterpret_cast<float *>(p.ws + p.off_lse);
     float2 *lp_out = reinterpret_cast<float2 *>(p.ws + p.w.off_lp);
     const int tid = threadIdx.x;
 
     SlotIter it = {0u, 0u};
-    unsigned seq = 0;
+    unsigned seq = 0, pushed = 0;
     LN_T_DECL;
     for (;;) {
-        mbar_spin(&full[it.slot], it.phase);
+        mbar_spin(&full[it.slot], it.phase, 4);
         LN_T(0);
         const LnTileMeta m = metas[seq % kLnMetaRing];
         ++seq;
         if (m.kind < 0) break;
-        int Tb = d.input_lengths ? __ldg(d.input_lengths + m.b) : d.T;
-        Tb = max(0, min(Tb, d.T));
-        int Lb = d.label_lengths ? __ldg(d.label_lengths + m.b) : d.Lmax;
-        Lb = max(0, min(Lb, d.Lmax));
+        const int Tb = m.Tb, Lb = m.Lb;
         const int ncol = 1 + (d.kind == 1 ? d.Lmax + Lb : Lb);
+        // the id of this thread's emission column, requested now (its round trip hides behind the tile load and the
+        // moments): thread c takes column c -- 0 = blank, 1..Lmax = labels, Lmax+1.. = bigrams (gram_ctc.py:24-32, :155)
+        int sym = -1;
+        if (tid < ncol) {
+            if (tid == 0) sym = d.blank;
+            else if (tid <= d.Lmax) sym = (tid - 1 < Lb) ? __ldg(d.labels + (size_t)m.b * d.Lmax + tid - 1) : -1;
+            else sym = __ldg(d.bigrams + (size_t)m.b * d.Lmax + tid - 1 - d.Lmax);
+        }
         // ---- the tile into registers: rows 240k + 16w + r, frames 4h .. 4h+3 ----
         float4 z[KMAX];
         const SlotIter first = it;
@@ -389,34 +534,12 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
             for (int k = 0; k < KMAX; ++k) {
                 z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k < K) {
-                    if (k > 0) mbar_spin(&full[s.slot], s.phase);
+                    if (k > 0) mbar_spin(&full[s.slot], s.phase, 5);
                     z[k] = lds128(ring + s.slot * kLnBoxBytes + lane_off);
                     s.next(R);
                 }
             }
             it = s;
-        }
-        // ---- the rows of the symbols the lattice can emit: thread c takes column c (gram_ctc.py:24-32, :155) ----
-        int sym = -1;
-        float4 zs0 = make_float4(0.f, 0.f, 0.f, 0.f), zs1 = zs0;
-        if (tid < ncol) {
-            if (tid == 0) sym = d.blank;
-            else if (tid <= d.Lmax) sym = (tid - 1 < Lb) ? __ldg(d.labels + (size_t)m.b * d.Lmax + tid - 1) : -1;
-            else sym = __ldg(d.bigrams + (size_t)m.b * d.Lmax + tid - 1 - d.Lmax);
-            if (sym >= 0 && sym < d.V) {
-                unsigned sl = first.slot + (unsigned)(sym / kLnBoxRows);
-                if (sl >= R) sl -= R;
-                const uint32_t a = ring + sl * kLnBoxBytes + (uint32_t)((sym % kLnBoxRows) * 32);
-                zs0 = lds128(a);
-                zs1 = lds128(a + 16);
-            } else {
-                sym = -1;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {                                   // the boxes can be refilled
-            SlotIter s = first;
-            for (int k = 0; k < K; ++k) { mbar_arrive(&empty[s.slot]); s.next(R); }
         }
         LN_T(1);
 
@@ -443,6 +566,22 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
         int fih;
         const Moments mr = reduce_frames16(mo[0], mo[1], mo[2], mo[3], lane, merge_moments, fih);
         if (lane < 8) { const float v3[3] = {mr.n, mr.mean, mr.m2}; red_store<3>(red, 4 * h + fih, w, v3); }
+        // ---- the rows of the emitted symbols, then the boxes can be refilled ----
+        float4 zs0 = make_float4(0.f, 0.f, 0.f, 0.f), zs1 = zs0;
+        if (sym >= 0 && sym < d.V) {
+            unsigned sl = first.slot + (unsigned)(sym / kLnBoxRows);
+            if (sl >= R) sl -= R;
+            const uint32_t a = ring + sl * kLnBoxBytes + (uint32_t)((sym % kLnBoxRows) * 32);
+            zs0 = lds128(a);
+            zs1 = lds128(a + 16);
+        } else {
+            sym = -1;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            SlotIter s = first;
+            for (int k = 0; k < K; ++k) { mbar_arrive(&empty[s.slot]); s.next(R); }
+        }
         LN_T(2);
         bar_compute();
         LN_T(3);
@@ -459,7 +598,7 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
                 tot[w * 8 + 0] = a.mean;
                 tot[w * 8 + 1] = rstd;
                 const int t = m.t0 + w;
-                if (t < Tb) { mu_out[(size_t)m.b * d.T + t] = a.mean; rstd_out[(size_t)m.b * d.T + t] = rstd; }
+                if (t < Tb) { mu_out[(size_t)m.b * p.Tq + t] = a.mean; rstd_out[(size_t)m.b * p.Tq + t] = rstd; }
             }
         }
         bar_compute();
@@ -509,7 +648,7 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
                 tot[w * 8 + 2] = la;
                 tot[w * 8 + 3] = lb;
                 const int t = m.t0 + w;
-                if (t < Tb) lse_out[(size_t)m.b * d.T + t] = la + lb;
+                if (t < Tb) lse_out[(size_t)m.b * p.Tq + t] = la + lb;
             }
         }
         bar_compute();
@@ -533,13 +672,10 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
             }
         }
         bar_compute();            // rows stored; also protects red/tot against the next tile
-        if (tid == 0 && (d.progress & 1)) {
-            const int nvalid = min(kLnTT, Tb - m.t0);
-            unsigned *pc = reinterpret_cast<unsigned *>(p.ws + p.w.off_prog) + (size_t)m.b * p.w.nblk + m.t0 / kProgBlock;
-            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(pc), "r"((unsigned)nvalid) : "memory");
-        }
+        if (tid == 0 && (d.progress & 1)) ln_signal_push(fifo, pushed, m.b, m.t0 / kProgBlock, min(kLnTT, Tb - m.t0));
         LN_T(7);
     }
+    if (tid == 0 && (d.progress & 1)) ln_signal_push(fifo, pushed, -1, 0, 0);
     LN_T_FLUSH(w);
 }
 
@@ -549,8 +685,12 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
 // Rows that do not exist get gamma = beta = 0 in the shared-memory table: their dn is 0 (nothing enters the per-frame
 // sums) and what they add to this thread's dgamma/dbeta slots is never stored.  Frames that do not exist (padding) get
 // rstd = 0 and scale = 0, which makes every quantity of theirs exactly zero.  No predicates in the sweeps.
+// dz leaves as it came in: sweep 2 writes each box's image over the z it was computed from, and lane 1 of the producer
+// warp hands the boxes to the TMA engine as tile stores (an SM storing 32-byte pieces itself spends 16 L1 wavefronts
+// per instruction: the LSU, not HBM, bounded the first version of this kernel).
 template <int KMAX>
-__global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid_constant__ CUtensorMap tmap, LnParams p,
+__global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                     const __grid_constant__ CUtensorMap tmap_dz, LnParams p,
                                                                      LnSmem sm) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + sm.off_full);
@@ -559,7 +699,10 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
     LnTileMeta *metas = reinterpret_cast<LnTileMeta *>(smem + sm.off_meta);
     float *red = reinterpret_cast<float *>(smem + sm.off_red);
     float *tot = reinterpret_cast<float *>(smem + sm.off_tot);
+    const float *fc = reinterpret_cast<const float *>(smem + sm.off_fc);
     float *post = reinterpret_cast<float *>(smem + sm.off_post);
+    float *ebuf = reinterpret_cast<float *>(smem + sm.off_ebuf);
+    int *csr = reinterpret_cast<int *>(smem + sm.off_csr);
     float *gb = reinterpret_cast<float *>(smem + sm.off_gb);
     unsigned *bm_sm = reinterpret_cast<unsigned *>(smem + sm.off_bm);
     const uint32_t ring = smem_u32(smem + sm.off_ring);
@@ -569,32 +712,35 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
     const int K = p.K;
     constexpr int Vt = KMAX * kLnBoxRows;
     const int Upad = (wl.Umax + 3) & ~3;
+    const int Nst = wl.Np;                                // row pitch of ebuf
+    float *bpart = ebuf + (size_t)kLnTT * wl.Np;          // [frame][32-node chunk] partial sums over the blank nodes
     if (threadIdx.x == 0) {
-        for (unsigned i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kLnWarps); }
+        for (unsigned i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&abbar[0], 1);
         mbar_init(&abbar[1], 1);
+        mbar_init(&abbar[2], 1);
         mbar_init_fence();
+        reinterpret_cast<LnSignalFifo *>(smem + sm.off_fifo)->head = 0u;
     }
     for (int i = threadIdx.x; i < Vt; i += blockDim.x) {
         gb[i] = i < d.V ? __ldg(p.gamma + i) : 0.f;
         gb[Vt + i] = i < d.V ? __ldg(p.beta + i) : 0.f;
     }
     for (int i = threadIdx.x; i < 2 * (Vt / 32 + 1); i += blockDim.x) bm_sm[i] = 0u;
+    for (int i = threadIdx.x; i < (int)(kLnBoxBytes / 4); i += blockDim.x) reinterpret_cast<float *>(smem + sm.off_zero)[i] = 0.f;
+    fence_proxy_async_smem();                             // the zero box is read by the TMA engine
     __syncthreads();
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     if (w == kLnWarps) {
-        if (lane == 0) ln_producer<true>(&tmap, p, smem, sm);
+        if (lane == 0) ln_producer<true>(&tmap, &tmap_dz, p, smem, sm);
+        else if (lane == 1) ln_storer(&tmap_dz, p, smem, sm);
         return;
     }
     const int r = lane >> 1, h = lane & 1;
     const int vrow = 16 * w + r;
     const int tid = threadIdx.x;
     const uint32_t lane_off = (uint32_t)(w * 512 + lane * 16);
-    const UttInfo *utt = reinterpret_cast<const UttInfo *>(p.ws + wl.off_utt);
-    const float *mu_in = reinterpret_cast<const float *>(p.ws + p.off_mu);
-    const float *rstd_in = reinterpret_cast<const float *>(p.ws + p.off_rstd);
-    const float *lse_in = reinterpret_cast<const float *>(p.ws + wl.off_lse);
     const int per = d.kind == 0 ? 2 : 3;
     const float inv_v = 1.f / (float)d.V;
     const int nwt = Vt / 32 + 1;                          // words of the bitmap / prefix tables in shared memory
@@ -606,84 +752,81 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
     unsigned seq = 0, n_ab = 0;
     LN_T_DECL;
     for (;;) {
-        mbar_spin(&full[it.slot], it.phase);
+        mbar_spin(&full[it.slot], it.phase, 14);
         LN_T(0);
         const LnTileMeta m = metas[seq % kLnMetaRing];
         ++seq;
-        if (m.kind < 0) break;
-        float *dzb = p.dz + (int64_t)m.b * p.dzs_b + m.t0 + 4 * h + (int64_t)vrow * p.dzs_v;
-        const int64_t box_step = (int64_t)kLnBoxRows * p.dzs_v;
-        const bool store_ok = m.t0 + 4 * h < d.T;
-        if (m.kind == 1) {
-            // every frame of the tile is padding: zeros (gram_ctc.py:296 -> LayerNormalization backward of zero is zero)
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k)
-                if (k < K && kLnBoxRows * k + vrow < d.V && store_ok)
-                    *reinterpret_cast<float4 *>(dzb + k * box_step) = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[it.slot]);
-            it.next(R);
-            LN_T(1);
-            continue;
+        if (m.kind < 0) {
+            // tell the store lane how many tiles there were (see ln_storer for why this is not a barrier arrival)
+            if (tid == 0) *reinterpret_cast<volatile unsigned *>(&reinterpret_cast<LnSignalFifo *>(smem + sm.off_fifo)->head) = seq;
+            break;
         }
-        const UttInfo ui = utt[m.b];
-        const float sc = (p.per_utterance ? __ldg(p.grad_loss + m.b) : __ldg(p.grad_loss)) * p.scale;      // gram_ctc.py:291-294
-        // per-frame constants of this thread's four frames
+        // ---- phase (a): merged posteriors of the tile's frames (gram_ctc.py:180-217, :290), all warps ----
+        // requested first, used last: this utterance's symbol tables (prep.cuh)
+        {
+            const int *uoff = reinterpret_cast<const int *>(p.ws + wl.off_uoff) + (size_t)m.b * (wl.Nmax + 1);
+            const int *unode = reinterpret_cast<const int *>(p.ws + wl.off_unode) + (size_t)m.b * wl.Nmax;
+            const unsigned *bm_g = reinterpret_cast<const unsigned *>(p.ws + wl.off_bm) + (size_t)m.b * wl.nwords;
+            const int *pc_g = reinterpret_cast<const int *>(p.ws + wl.off_pc) + (size_t)m.b * wl.nwords;
+            for (int i = tid; i <= m.Ub; i += 32 * kLnWarps) csr[i] = __ldg(uoff + i);
+            for (int i = tid; i < m.Nb; i += 32 * kLnWarps) csr[wl.Nmax + 1 + i] = __ldg(unode + i);
+            for (int i = tid; i < wl.nwords; i += 32 * kLnWarps) { bm_sm[i] = __ldg(bm_g + i); bm_sm[nwt + i] = (unsigned)__ldg(pc_g + i); }
+        }
+        mbar_spin(&abbar[0], n_ab & 1u, 15);
+        ++n_ab;
+        LN_T(2);
+        // per-frame constants of this thread's four frames (staged by the producer)
         float rs[4], mur[4], nl[4], scj[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int t = m.t0 + 4 * h + j;
-            const bool valid = t < ui.Tb;
-            const size_t o = (size_t)m.b * d.T + (valid ? t : 0);
-            const float rr = valid ? __ldg(rstd_in + o) : 0.f;
-            const float mm = valid ? __ldg(mu_in + o) : 0.f;
-            rs[j] = rr; mur[j] = -mm * rr;
-            nl[j] = valid ? -__ldg(lse_in + o) : 0.f;
-            scj[j] = valid ? sc : 0.f;
+            const bool valid = m.t0 + 4 * h + j < m.Tb;
+            const float rr = valid ? fc[kLnTT + 4 * h + j] : 0.f;
+            rs[j] = rr; mur[j] = valid ? -fc[4 * h + j] * rr : 0.f;
+            nl[j] = valid ? -fc[2 * kLnTT + 4 * h + j] : 0.f;
+            scj[j] = valid ? m.sc : 0.f;
         }
-        // ---- phase (a): merged posteriors of the tile's frames, one warp per frame (gram_ctc.py:180-217, :290) ----
-        mbar_spin(&abbar[0], n_ab & 1u);
-        ++n_ab;
-        LN_T(2);
         {
-            const unsigned *bm_g = reinterpret_cast<const unsigned *>(p.ws + wl.off_bm) + (size_t)m.b * wl.nwords;
-            const int *pc_g = reinterpret_cast<const int *>(p.ws + wl.off_pc) + (size_t)m.b * wl.nwords;
-            for (int i = tid; i < wl.nwords; i += 32 * kLnWarps) { bm_sm[i] = __ldg(bm_g + i); bm_sm[nwt + i] = (unsigned)__ldg(pc_g + i); }
-        }
-        if (w < kLnTT) {
-            float *prow = post + w * Upad;
-            if (m.t0 + w < ui.Tb) {
-                float2 *a_sm = reinterpret_cast<float2 *>(smem + sm.off_ab) + (size_t)w * wl.Np;
-                const float2 *b_sm = reinterpret_cast<const float2 *>(smem + sm.off_ab) + (size_t)(kLnTT + w) * wl.Np;
-                float *e_sm = reinterpret_cast<float *>(a_sm);                    // alpha*beta/P, written over the alpha row
-                float blank_part = 0.f;
-                for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
-                    const int j = j0 + lane;
-                    float e = 0.f;
-                    if (j < ui.Nb) e = node_posterior(a_sm[j], b_sm[j + wl.boff], ui.Ph, ui.Pl);
-                    __syncwarp();                                                // e_sm aliases the alpha row: reads first
-                    if (j < ui.Nb) e_sm[j] = e;
-                    if (j < ui.Nb && j % per == 0) blank_part += e;
+            // alpha * beta / P of every node of every valid frame
+            const float2 *a_sm = reinterpret_cast<const float2 *>(smem + sm.off_ab);
+            const float2 *b_sm = a_sm + (size_t)kLnTT * wl.Np;
+            const int nfv = min(kLnTT, m.Tb - m.t0);
+            const int Nbp = (m.Nb + 31) & ~31;
+            // a warp's 32 items are 32 consecutive nodes of ONE frame (Nbp and the stride are multiples of 32): the blank
+            // nodes among them are summed by shuffle and left as one partial per 32-node chunk, summed in order below
+            for (int i = tid; i < nfv * Nbp; i += 32 * kLnWarps) {
+                const int f = i / Nbp, j = i - f * Nbp;
+                float e = 0.f;
+                if (j < m.Nb) {
+                    e = node_posterior(a_sm[f * wl.Np + j], b_sm[f * wl.Np + j + wl.boff], m.Ph, m.Pl);
+                    ebuf[f * Nst + j] = e;
                 }
-                blank_part = warp_sum(blank_part);
-                __syncwarp();
-                const int *uoff = reinterpret_cast<const int *>(p.ws + wl.off_uoff) + (size_t)m.b * (wl.Nmax + 1);
-                const int *unode = reinterpret_cast<const int *>(p.ws + wl.off_unode) + (size_t)m.b * wl.Nmax;
-                for (int u = lane; u < ui.Ub; u += 32) {
-                    const int n0 = __ldg(uoff + u), n1 = __ldg(uoff + u + 1);
-                    float ps = (u == ui.ublank) ? blank_part : 0.f;
-                    for (int n = n0; n < n1; ++n) {
-                        const int j = __ldg(unode + n);
-                        if (j < ui.Nb) ps += e_sm[j];
-                    }
-                    prow[u] = ps * sc;
-                }
-            } else {
-                for (int u = lane; u < ui.Ub; u += 32) prow[u] = 0.f;            // a padded frame has no posterior
+                const float bp = warp_sum((j < m.Nb && j % per == 0) ? e : 0.f);
+                if (lane == 0) bpart[f * kLnBlankChunks + (j >> 5)] = bp;
             }
         }
         bar_compute();
-        if (tid == 0) mbar_arrive(&abbar[1]);                                 // the alpha/beta buffer can be refilled
+        if (tid == 0) mbar_arrive(&abbar[1]);                                 // alpha/beta and the frame constants can be refilled
+        {
+            // merged per emitted id, in node order (deterministic); the blank collects every per-th node
+            const int nfv = min(kLnTT, m.Tb - m.t0);
+            for (int i = tid; i < kLnTT * m.Ub; i += 32 * kLnWarps) {
+                const int f = i / m.Ub, u = i - f * m.Ub;
+                float ps = 0.f;
+                if (f < nfv) {
+                    const float *e = ebuf + f * Nst;
+                    if (u == m.ublank)
+                        for (int c = 0; c < (m.Nb + 31) / 32; ++c) ps += bpart[f * kLnBlankChunks + c];
+                    const int n0 = csr[u], n1 = csr[u + 1];
+                    for (int n = n0; n < n1; ++n) {
+                        const int j = csr[wl.Nmax + 1 + n];
+                        if (j < m.Nb) ps += e[j];
+                    }
+                    ps *= m.sc;
+                }
+                post[f * Upad + u] = ps;
+            }
+        }
+        bar_compute();
         LN_T(3);
 
         // ---- sweep 1: g = softmax * sc - posterior;  dn = g * gamma;  per-frame sums of dn and dn * n ----
@@ -697,7 +840,7 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
             for (int k = 0; k < KMAX; ++k) {
                 dn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k < K) {
-                    if (k > 0) mbar_spin(&full[s.slot], s.phase);
+                    if (k > 0) mbar_spin(&full[s.slot], s.phase, 16);
                     const float4 zq = lds128(ring + s.slot * kLnBoxBytes + lane_off);
                     s.next(R);
                     const int v = kLnBoxRows * k + vrow;
@@ -745,27 +888,28 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_gradient_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 4; ++j) { c1r[j] = -tot[(4 * h + j) * 8 + 0] * rs[j]; c2r[j] = -tot[(4 * h + j) * 8 + 1] * rs[j]; }
 
-        // ---- sweep 2: dz = rstd * (dn - mean_v(dn) - n * mean_v(dn * n)), stored in z's own layout ----
+        // ---- sweep 2: dz = rstd * (dn - mean_v(dn) - n * mean_v(dn * n)), written over the z it came from ----
         {
             SlotIter s = first;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
                 if (k < K) {
-                    const float4 zq = lds128(ring + s.slot * kLnBoxBytes + lane_off);
+                    const uint32_t addr = ring + s.slot * kLnBoxBytes + lane_off;
+                    const float4 zq = lds128(addr);
                     float4 o;
                     o.x = fmaf(fmaf(zq.x, rs[0], mur[0]), c2r[0], fmaf(dn[k].x, rs[0], c1r[0]));
                     o.y = fmaf(fmaf(zq.y, rs[1], mur[1]), c2r[1], fmaf(dn[k].y, rs[1], c1r[1]));
                     o.z = fmaf(fmaf(zq.z, rs[2], mur[2]), c2r[2], fmaf(dn[k].z, rs[2], c1r[2]));
                     o.w = fmaf(fmaf(zq.w, rs[3], mur[3]), c2r[3], fmaf(dn[k].w, rs[3], c1r[3]));
-                    if (kLnBoxRows * k + vrow < d.V && store_ok) *reinterpret_cast<float4 *>(dzb + k * box_step) = o;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[s.slot]);
+                    sts128(addr, o);
                     s.next(R);
                 }
             }
         }
+        fence_proxy_async_smem();     // the images are read by the TMA engine
         LN_T(6);
-        bar_compute();            // red / tot / post / bitmap are reused by the next tile
+        bar_compute();                // images complete; red / tot / post / tables are reused by the next tile
+        if (tid == 0) mbar_arrive(&abbar[2]);      // store lane: this tile's boxes are ready
         LN_T(7);
     }
     LN_T_FLUSH(w);
@@ -833,12 +977,12 @@ bool make_z_map(CUtensorMap *map, const float *z, int B, int T, int V, int64_t z
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename Kern>
-cudaError_t launch_ln(Kern kern, int grid, const CUtensorMap &map, const LnParams &p, const LnSmem &sm, cudaStream_t stream) {
+template <typename Kern, typename... Maps>
+cudaError_t launch_ln(Kern kern, int grid, const LnParams &p, const LnSmem &sm, cudaStream_t stream, const Maps &...maps) {
     (void)cudaGetLastError();
     cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), sm.total);
     if (e != cudaSuccess) { note_failure_site("shared-memory opt-in"); return e; }
-    kern<<<grid, kLnThreads, sm.total, stream>>>(map, p, sm);
+    kern<<<grid, kLnThreads, sm.total, stream>>>(maps..., p, sm);
     e = cudaGetLastError();
     if (e != cudaSuccess) note_failure_site("tile kernel launch");
     return e;
@@ -854,9 +998,10 @@ LnLayout make_ln_layout(int kind, int B, int T, int V, int Lmax) {
     LnLayout l;
     l.w = make_layout(kind, B, T, V, Lmax);
     size_t o = l.w.total;
-    const size_t BT = (size_t)B * (size_t)T;
+    const size_t BT = (size_t)B * (size_t)((T + 3) & ~3);          // rows of these arrays are 16-byte aligned (bulk-copied)
     l.off_mu = o;   o = align_up(o + sizeof(float) * BT, 256);
     l.off_rstd = o; o = align_up(o + sizeof(float) * BT, 256);
+    l.off_lse = o;  o = align_up(o + sizeof(float) * BT, 256);
     const int K = (V + kLnBoxRows - 1) / kLnBoxRows;
     l.off_part = o; o = align_up(o + sizeof(float) * 2 * (size_t)K * kLnBoxRows * kLnMaxParts, 256);
     l.total = o;
@@ -881,12 +1026,13 @@ cudaError_t launch_ln_forward(const ProblemDesc &d, const LnLayout &ll, void *ws
     memset(&p, 0, sizeof(p));
     p.d = d; p.w = ll.w; p.ws = static_cast<unsigned char *>(ws);
     p.z = z; p.zs_b = zs_b; p.zs_v = zs_v; p.gamma = gamma; p.beta = beta;
-    p.off_mu = ll.off_mu; p.off_rstd = ll.off_rstd; p.off_part = ll.off_part;
+    p.off_mu = ll.off_mu; p.off_rstd = ll.off_rstd; p.off_lse = ll.off_lse; p.off_part = ll.off_part;
+    p.Tq = (d.T + 3) & ~3;
     p.K = (d.V + kLnBoxRows - 1) / kLnBoxRows;
     p.nTB = (d.T + kLnTT - 1) / kLnTT;
     const size_t gbf = (size_t)2 * ln_kmax(p.K) * kLnBoxRows;
-    LnSmem sm = plan_ln_smem(p.K, 0, 0, gbf, 0, smem_reserve);
-    if (sm.R < p.K + 2) sm = plan_ln_smem(p.K, 0, 0, gbf, 0, 0);     // no room to share the SM
+    LnSmem sm = plan_ln_smem(p.K, 0, 0, 0, 0, gbf, 0, 0, smem_reserve);
+    if (sm.R < p.K + 2) sm = plan_ln_smem(p.K, 0, 0, 0, 0, gbf, 0, 0, 0);     // no room to share the SM
     if (sm.R < p.K + 2) return cudaErrorInvalidConfiguration;
     if (sm.R > 2 * p.K + 4) {                     // more than two tiles' worth buys nothing; leave the rest to the L1
         sm.total -= (size_t)(sm.R - (2 * p.K + 4)) * kLnBoxBytes;
@@ -899,10 +1045,10 @@ cudaError_t launch_ln_forward(const ProblemDesc &d, const LnLayout &ll, void *ws
     int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     if (grid < 1) grid = 1;
     switch (ln_kmax(p.K)) {
-        case 5: return launch_ln(ln_softmax_gather_kernel<5>, grid, map, p, sm, stream);
-        case 9: return launch_ln(ln_softmax_gather_kernel<9>, grid, map, p, sm, stream);
-        case 15: return launch_ln(ln_softmax_gather_kernel<15>, grid, map, p, sm, stream);
-        default: return launch_ln(ln_softmax_gather_kernel<17>, grid, map, p, sm, stream);
+        case 5: return launch_ln(ln_softmax_gather_kernel<5>, grid, p, sm, stream, map);
+        case 9: return launch_ln(ln_softmax_gather_kernel<9>, grid, p, sm, stream, map);
+        case 15: return launch_ln(ln_softmax_gather_kernel<15>, grid, p, sm, stream, map);
+        default: return launch_ln(ln_softmax_gather_kernel<17>, grid, p, sm, stream, map);
     }
 }
 
@@ -915,29 +1061,33 @@ cudaError_t launch_ln_backward(const GradParams &g, const LnLayout &ll, const vo
     memset(&p, 0, sizeof(p));
     p.d = d; p.w = ll.w; p.ws = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
     p.z = z; p.zs_b = zs_b; p.zs_v = zs_v; p.gamma = gamma; p.beta = beta;
-    p.off_mu = ll.off_mu; p.off_rstd = ll.off_rstd; p.off_part = ll.off_part;
+    p.off_mu = ll.off_mu; p.off_rstd = ll.off_rstd; p.off_lse = ll.off_lse; p.off_part = ll.off_part;
+    p.Tq = (d.T + 3) & ~3;
     p.K = (d.V + kLnBoxRows - 1) / kLnBoxRows;
     p.nTB = (d.T + kLnTT - 1) / kLnTT;
     p.grad_loss = g.grad_loss; p.per_utterance = g.per_utterance; p.scale = g.scale;
     p.dz = dz; p.dzs_b = dzs_b; p.dzs_v = dzs_v; p.dgamma = dgamma; p.dbeta = dbeta;
     const int Vp = p.K * kLnBoxRows;
     const int Vt = ln_kmax(p.K) * kLnBoxRows;
-    const LnSmem sm = plan_ln_smem(p.K, (size_t)2 * kLnTT * ll.w.Np * 8, (size_t)kLnTT * ((ll.w.Umax + 3) & ~3), (size_t)2 * Vt,
-                                   (size_t)2 * (Vt / 32 + 1));
+    const LnSmem sm = plan_ln_smem(p.K, (size_t)2 * kLnTT * ll.w.Np * 8, (size_t)kLnTT * ((ll.w.Umax + 3) & ~3),
+                                   (size_t)kLnTT * ll.w.Np + (size_t)kLnTT * kLnBlankChunks, (size_t)2 * ll.w.Nmax + 2, (size_t)2 * Vt,
+                                   (size_t)2 * (Vt / 32 + 1),
+                                   kLnBoxBytes);
     if (sm.R < p.K + 2) { note_failure_site("shared-memory plan"); return cudaErrorInvalidConfiguration; }
     p.R = sm.R;
-    CUtensorMap map;
+    CUtensorMap map, map_dz;
     if (!make_z_map(&map, z, d.B, d.T, d.V, zs_b, zs_v)) { note_failure_site("tensor map of z"); return cudaErrorInvalidValue; }
+    if (!make_z_map(&map_dz, dz, d.B, d.T, d.V, dzs_b, dzs_v)) { note_failure_site("tensor map of dz"); return cudaErrorInvalidValue; }
     long long tiles = (long long)d.B * p.nTB;
     int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     if (grid > kLnMaxParts) grid = kLnMaxParts;
     if (grid < 1) grid = 1;
     cudaError_t e;
     switch (ln_kmax(p.K)) {
-        case 5: e = launch_ln(ln_gradient_kernel<5>, grid, map, p, sm, stream); break;
-        case 9: e = launch_ln(ln_gradient_kernel<9>, grid, map, p, sm, stream); break;
-        case 15: e = launch_ln(ln_gradient_kernel<15>, grid, map, p, sm, stream); break;
-        default: e = launch_ln(ln_gradient_kernel<17>, grid, map, p, sm, stream); break;
+        case 5: e = launch_ln(ln_gradient_kernel<5>, grid, p, sm, stream, map, map_dz); break;
+        case 9: e = launch_ln(ln_gradient_kernel<9>, grid, p, sm, stream, map, map_dz); break;
+        case 15: e = launch_ln(ln_gradient_kernel<15>, grid, p, sm, stream, map, map_dz); break;
+        default: e = launch_ln(ln_gradient_kernel<17>, grid, p, sm, stream, map, map_dz); break;
     }
     if (e != cudaSuccess) return e;
     if (dgamma || dbeta) {

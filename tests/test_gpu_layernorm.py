@@ -160,6 +160,9 @@ def test_fused_layernorm_layouts(pkg):
     for other in (b, c):
         for x, y in zip(a, other):
             assert np.array_equal(x, y)
+    # a frame count that is not a multiple of 4 works with a padded row pitch
+    prob, z, gamma, beta = make_case("gram", 3, 42, 130, 6, seed=66)
+    check(run_cuda_ln(pkg, "gram", z, gamma, beta, prob, pitch=44), run_oracle_ln("gram", z, gamma, beta, prob), 3, 42, "T=42 pitch=44")
 
 
 def test_fused_layernorm_equals_unfused_composition(pkg):
