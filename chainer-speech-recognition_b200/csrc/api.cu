@@ -191,6 +191,9 @@ int forward_impl(const LnInput *ln, int kind, const float *acts, int64_t stride_
         if ((rc = check_cuda(cudaEventRecord(side->join, side->stream), "join event"))) return rc;
         if ((rc = check_cuda(cudaStreamWaitEvent(stream, side->join, 0), "join wait"))) return rc;
     } else {
+#ifdef B200CTC_EXPERIMENT
+        if (knobs().dbg_progress >= 0) d.progress = knobs().dbg_progress & 64;      // streaming-rate experiment (softmax_gather.cu)
+#endif
         if (ln) {
             if ((rc = check_cuda(launch_ln_forward(d, ll, ws, ln->z, ln->zs_b, ln->zs_v, ln->gamma, ln->beta, 0, stream),
                                  "layernorm softmax/gather kernel"))) return rc;

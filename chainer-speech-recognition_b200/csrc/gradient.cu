@@ -258,26 +258,20 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         // ===== producer (lane i owns frame i of the current batch) =====
         const float2 *av_all = reinterpret_cast<const float2 *>(ws + w.off_av);
         const float2 *bv_all = reinterpret_cast<const float2 *>(ws + w.off_bv);
-        const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
-        unsigned q = 0, pend;
-        ring_first_ticket(&hdr->k3_ticket, pend, lane, ring.batch);
-        for (;;) {
-            const unsigned base = ring_take_batch(&hdr->k3_ticket, pend, lane, ring.batch, frames);
-            if (base >= frames) break;
+        unsigned q = 0;
+        auto issue_batch = [&](unsigned base) -> bool {
+            if (base >= frames) return false;
             const unsigned f = base + (unsigned)lane;
             int b = 0, t = 0;
             bool need = false;
-            float row_lse = 0.f, row_sc = 0.f;
             if (lane < ring.batch && f < frames) {
                 if (b_major) { b = (int)(f / d.T); t = (int)(f % d.T); }
                 else { t = (int)(f / d.B); b = (int)(f % d.B); }
-                if (t >= utt[b].Tb) {                                                // :296 -- zeros, straight from smem
+                if (t >= (utt_cached ? utt_sm[b].Tb : utt[b].Tb)) {                  // :296 -- zeros, straight from smem
                     float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
                     store_row_image(dst, zero_row + row_misalignment(dst), d.V);
                 } else {
                     need = true;
-                    row_lse = __ldg(lse_all + (size_t)b * d.T + t);
-                    row_sc = (gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss)) * gp.scale;     // :291-294
                 }
             }
             const unsigned mask = __ballot_sync(0xffffffffu, need);
@@ -292,7 +286,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                     const int off = row_misalignment(src);
                     const uint32_t span = row_span_bytes(off, d.V);
                     ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0; ring.meta[s].off = off;
-                    ring.meta[s].lse = row_lse; ring.meta[s].sc = row_sc;
                     ring_publish(ring, s, myq);
                     mbar_arrive_expect_tx(&ring.full[s], span + 2 * ab_bytes + 2 * ab2_bytes);
                     bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
@@ -310,6 +303,18 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                 if (!__any_sync(0xffffffffu, issued)) __nanosleep(40);
             }
             q += (unsigned)__popc(mask);
+            return true;
+        };
+        // two tickets in flight: the one a batch needs was requested two batches ago (see softmax_gather.cu)
+        unsigned pa = 0, pb = 0;
+        if (lane == 0) { pa = atomicAdd(&hdr->k3_ticket, (unsigned)ring.batch); pb = atomicAdd(&hdr->k3_ticket, (unsigned)ring.batch); }
+        for (;;) {
+            unsigned base = __shfl_sync(0xffffffffu, pa, 0);
+            if (lane == 0 && base < frames) pa = atomicAdd(&hdr->k3_ticket, (unsigned)ring.batch);
+            if (!issue_batch(base)) break;
+            base = __shfl_sync(0xffffffffu, pb, 0);
+            if (lane == 0 && base < frames) pb = atomicAdd(&hdr->k3_ticket, (unsigned)ring.batch);
+            if (!issue_batch(base)) break;
         }
         ring_stop(ring, q, lane);
         bulk_wait_all<0>();
@@ -324,13 +329,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     }
 
     // ===== consumers =====
+    const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
     const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
     const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
     const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
     float *post_sm = post_all + (size_t)(warp - 1) * ((w.Umax + 3) & ~3);
     const int per = d.kind == 0 ? 2 : 3;
     if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
-    for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
+    for (;;) {
+        const unsigned q = ring_next_row(ring, lane);
         const int s = ring_acquire(ring, q);
         const RowMeta m = ring.meta[s];
         if (m.kind < 0) {                       // stop record: hand the slot back (the ring may be shorter than
@@ -349,8 +356,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         const float2 *b2_sm = a2_sm + w.Np2;
         float *e2_sm = reinterpret_cast<float *>(const_cast<float2 *>(a2_sm));
         const UttInfo ui = utt_cached ? utt_sm[b] : utt[b];
-        const float sc = m.sc;                                               // :291-294 (fetched by the producer)
-        const float c = -m.lse;
+        // requested now, needed after the posteriors: their round trip hides behind the node loop
+        const float lse2 = __ldg(lse_all + (size_t)b * d.T + t);
+        const float sc = (gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss)) * gp.scale;      // :291-294
 
         float blank_part = 0.f;
         for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
@@ -393,6 +401,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             post_sm[u] = post * sc;
         }
         const float sc_soft = w.joint ? 2.f * sc : sc;                       // two losses, two softmax terms
+        const float c = -lse2;
         // softmax * sc in place, over the whole aligned span (what lies outside the row is never stored)
         float4 *row4 = reinterpret_cast<float4 *>(slotf);
 #pragma unroll 4

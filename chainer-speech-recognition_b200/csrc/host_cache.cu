@@ -79,6 +79,8 @@ const Knobs &knobs() {
         if (const char *e = getenv("B200CTC_LAT_STAGES")) k.lat_stages = atoi(e) < 2 ? 2 : atoi(e);
         if (const char *e = getenv("B200CTC_RING_KB")) k.ring_kb = atoi(e);
         if (const char *e = getenv("B200CTC_DBG_PROGRESS")) k.dbg_progress = atoi(e);
+        if (const char *e = getenv("B200CTC_LAT_K")) k.lat_k = atoi(e);
+        if (const char *e = getenv("B200CTC_LAT_CH")) k.lat_ch = atoi(e);
 #endif
     });
     return k;

@@ -643,9 +643,13 @@ cudaError_t launch_w(const LatticeParams &p, size_t smem, cudaStream_t stream) {
 // instantiated combinations: few warps -> 16-frame chunks; many warps -> shorter chunks (see kMaxStages)
 template <int K, bool GRAM>
 cudaError_t launch_one(const LatticeParams &p, int CH, size_t smem, cudaStream_t stream) {
-    if (p.W <= 3) return launch_w<K, GRAM, 3, 16>(p, smem, stream);
-    if (p.W <= 7) return CH == 16 ? launch_w<K, GRAM, 7, 16>(p, smem, stream) : launch_w<K, GRAM, 7, 8>(p, smem, stream);
-    return CH == 8 ? launch_w<K, GRAM, kMaxWarpsPerDir, 8>(p, smem, stream) : launch_w<K, GRAM, kMaxWarpsPerDir, 4>(p, smem, stream);
+    if (p.W <= 3)
+        return CH == 16 ? launch_w<K, GRAM, 3, 16>(p, smem, stream)
+                        : (CH == 8 ? launch_w<K, GRAM, 3, 8>(p, smem, stream) : launch_w<K, GRAM, 3, 4>(p, smem, stream));
+    if (p.W <= 7)
+        return CH == 16 ? launch_w<K, GRAM, 7, 16>(p, smem, stream)
+                        : (CH == 8 ? launch_w<K, GRAM, 7, 8>(p, smem, stream) : launch_w<K, GRAM, 7, 4>(p, smem, stream));
+    return CH >= 8 ? launch_w<K, GRAM, kMaxWarpsPerDir, 8>(p, smem, stream) : launch_w<K, GRAM, kMaxWarpsPerDir, 4>(p, smem, stream);
 }
 
 constexpr size_t kLatticeSmemBudget = 224 * 1024;
@@ -671,13 +675,18 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     *status = 0;
     const int kind = p.d.kind;
     const int Nmax = p.w.Nmax;
-    // nodes per lane: as few as possible (the recursion is issue-bound per warp), more only when the
-    // lattice would not fit 16 warps
+    // nodes per lane: two for the usual lattices (one recursion warp per SM sub-partition is the measured optimum at
+    // L = 80); four once the lattice would need more than eight warps (measured at L = 320, 11 warps: 1.51 -> 1.09 ms
+    // for the forward pass at T = 3200 with K = 4 and 4-frame chunks; K = 8 is slower again, profiles/r2_lattice_sweep.txt)
     int K;
-    if (kind == 0) K = (Nmax <= 32 * 2 * kMaxWarpsPerDir) ? 2 : 4;
+    if (kind == 0) K = (Nmax <= 32 * 2 * 8) ? 2 : 4;
     else K = (Nmax <= 32 * kGenericMaxWarps) ? 1 : ((Nmax <= 32 * 3 * kMaxWarpsPerDir) ? 3 : 6);
 #ifdef B200CTC_EXPERIMENT
     if (kind == 1 && knobs().gram_k3 && K == 1) K = 3;
+    if (knobs().lat_k > 0 && (Nmax + 32 * knobs().lat_k - 1) / (32 * knobs().lat_k) <= kMaxWarpsPerDir) {
+        if (kind == 0 && (knobs().lat_k == 2 || knobs().lat_k == 4 || knobs().lat_k == 8)) K = knobs().lat_k;
+        if (kind == 1 && (knobs().lat_k == 3 || knobs().lat_k == 6 || (knobs().lat_k == 1 && Nmax <= 32 * kGenericMaxWarps))) K = knobs().lat_k;
+    }
 #endif
     const int W = (Nmax + 32 * K - 1) / (32 * K);
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
@@ -688,7 +697,7 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     const int ahead = (concurrent && W <= 3) ? 2 : 3;
     const int want = W + ahead < kMaxStages ? W + ahead : kMaxStages;
     int CH = W <= 7 ? 16 : 8;
-    const int CHmin = W <= 3 ? 16 : (W <= 7 ? 8 : 4);
+    const int CHmin = W <= 3 ? 16 : 4;
     // next to the softmax/gather kernel every byte here is taken from that kernel's ring: stay below 64 KB if a
     // shorter chunk allows it
     const size_t budget = concurrent ? (size_t)64 * 1024 : kLatticeSmemBudget;
@@ -696,6 +705,7 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     int S = want;
 #ifdef B200CTC_EXPERIMENT
     if (knobs().lat_stages >= 2) S = knobs().lat_stages;
+    if (knobs().lat_ch == 16 || knobs().lat_ch == 8 || knobs().lat_ch == 4) CH = (W > 7 && knobs().lat_ch == 16) ? 8 : knobs().lat_ch;
 #endif
     while (S > 2 && plan_smem(p.w.W, W, S, PAD, CH).total > kLatticeSmemBudget) --S;
     const SmemPlan sp = plan_smem(p.w.W, W, S, PAD, CH);
@@ -711,7 +721,9 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
 #endif
     if (smem_out) *smem_out = smem;
     if (!launch) return cudaSuccess;
-    if (kind == 0) return K == 2 ? launch_one<2, false>(p, CH, smem, stream) : launch_one<4, false>(p, CH, smem, stream);
+    if (kind == 0)
+        return K == 2 ? launch_one<2, false>(p, CH, smem, stream)
+                      : (K == 4 ? launch_one<4, false>(p, CH, smem, stream) : launch_one<8, false>(p, CH, smem, stream));
     if (K == 1) return launch_one<1, true>(p, CH, smem, stream);
     return K == 3 ? launch_one<3, true>(p, CH, smem, stream) : launch_one<6, true>(p, CH, smem, stream);
 }

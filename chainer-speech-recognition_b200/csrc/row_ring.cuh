@@ -39,9 +39,7 @@ struct RowMeta {
     // per-row constants the producer fetches on the consumers' behalf (a dependent global load at the start of a
     // consumer's row is ~800 cycles during which the slot is held for nothing):
     int Lb;        // softmax/gather kernel: clamped label length of the utterance
-    float lse;     // gradient kernel: log2 normaliser of the frame
-    float sc;      // gradient kernel: upstream gradient * scale of the utterance
-    int pad_;
+    int pad_[3];
 };
 
 // bytes a slot needs for a row of V floats wherever it starts
@@ -56,7 +54,7 @@ struct RingLayout {
     int batch;             // frames per ticket (<= slots)
     int slots;             // R
     size_t slot_bytes;     // row (+ per-row extras), multiple of 128
-    size_t off_meta, off_full, off_empty, off_extra, total;
+    size_t off_meta, off_full, off_empty, off_next, off_extra, total;
 };
 
 inline size_t ring_budget() {
@@ -86,6 +84,7 @@ inline RingLayout make_ring(size_t slot_payload, size_t extra_bytes, size_t smem
     r.off_meta = o;  o += sizeof(RowMeta) * kMaxSlots;
     r.off_full = o;  o += 8 * kMaxSlots;
     r.off_empty = o; o += 8 * kMaxSlots;
+    r.off_next = o;  o += 16;
     r.off_extra = align_up(o, 128);
     r.total = r.off_extra + extra_bytes;
     return r;
@@ -97,6 +96,7 @@ struct Ring {
     unsigned char *base;
     RowMeta *meta;
     uint64_t *full, *empty;
+    unsigned *next;        // next row sequence number to hand to a consumer
     int slots;
     int nc;                // active consumers (<= slots)
     int batch;             // frames per ticket = min(kTicketBatch, slots): a batch never waits on its own rows
@@ -110,6 +110,7 @@ __device__ __forceinline__ Ring ring_setup(unsigned char *smem, const RingLayout
     r.meta = reinterpret_cast<RowMeta *>(smem + rl.off_meta);
     r.full = reinterpret_cast<uint64_t *>(smem + rl.off_full);
     r.empty = reinterpret_cast<uint64_t *>(smem + rl.off_empty);
+    r.next = reinterpret_cast<unsigned *>(smem + rl.off_next);
     r.slots = rl.slots;
     r.batch = rl.batch;
     r.nc = rl.consumers;
@@ -120,6 +121,7 @@ __device__ __forceinline__ Ring ring_setup(unsigned char *smem, const RingLayout
             mbar_init(&r.empty[i], 1);
             r.meta[i].seq = 0xffffffffu;
         }
+        *r.next = 0u;
         mbar_init_fence();
     }
     __syncthreads();
@@ -132,6 +134,15 @@ __device__ __forceinline__ int ring_claim(const Ring &r, unsigned q) {
     const unsigned n = q / (unsigned)r.slots;
     if (n > 0) mbar_wait(&r.empty[s], (n - 1) & 1u);
     return s;
+}
+
+// Consumer side (whole warp): take the next row, whichever it is.  Rows are NOT dealt out round-robin: a row that has
+// landed would then wait for "its" consumer while others idle -- at 66 % consumer utilisation that wait was as long
+// as the processing itself and kept a third of the ring's slots out of flight (tools/k1_roles.py).
+__device__ __forceinline__ unsigned ring_next_row(const Ring &r, int lane) {
+    unsigned q = 0;
+    if (lane == 0) q = atomicAdd(r.next, 1u);
+    return __shfl_sync(0xffffffffu, q, 0);
 }
 
 // Producer side, non-blocking: is the slot of row sequence number q free (its previous occupant released)?

@@ -270,6 +270,7 @@ constexpr int kK1Consumers = B200CTC_K1_CONSUMERS;
 constexpr int kK1Threads = 32 * (1 + kK1Consumers + 1);   // producer + consumers + signal warp
 constexpr int kGatherRegs = 4;                         // emitted ids per lane on the early-release path (<= 128 columns)
 constexpr int kFifoDepth = 4;
+constexpr int kLenCache = 2048;                        // utterances whose lengths the ring kernel keeps in shared memory
 struct SignalFifo {
     int2 entry[kK1Consumers][kFifoDepth];            // (b, t); b < 0 = this consumer is done
     unsigned head[kK1Consumers];                     // rows pushed by consumer c
@@ -370,6 +371,18 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     SignalFifo *fifo = reinterpret_cast<SignalFifo *>(smem_raw + rl.off_extra);
     const bool signalling = (d.progress & 1) != 0;
     if (threadIdx.x < kK1Consumers) { fifo->head[threadIdx.x] = 0u; fifo->tail[threadIdx.x] = 0u; }
+    // clamped lengths of every utterance, once per CTA: the producer then turns a ticket into copies without a round
+    // trip to L2 in between (that round trip, per batch of 8 rows, was 15 % of its time)
+    int *len_sm = reinterpret_cast<int *>(smem_raw + rl.off_extra + kFifoBytes);
+    const bool len_cached = d.B <= kLenCache;
+    if (len_cached) {
+        for (int i = threadIdx.x; i < d.B; i += blockDim.x) {
+            const int Tb = d.input_lengths ? __ldg(d.input_lengths + i) : d.T;
+            const int Lb = d.label_lengths ? __ldg(d.label_lengths + i) : d.Lmax;
+            len_sm[i] = max(0, min(Tb, d.T));
+            len_sm[d.B + i] = max(0, min(Lb, d.Lmax));
+        }
+    }
     __syncthreads();
     if (warp == kK1Consumers + 1) {                     // ===== signal warp =====
         if (signalling) signal_warp(fifo, ring.nc, lane, ws, w);
@@ -378,24 +391,25 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
 
     if (warp == 0) {
         // ===== producer (lane i owns frame i of the current batch) =====
-        unsigned q = 0, pend;
+        unsigned q = 0;
         long long r_wait0 = 0, r_wait1 = 0, r_rows = 0;
         const long long r_begin = K1_CLK();
-        ring_first_ticket(&hdr->k1_ticket, pend, lane, ring.batch);
-        for (;;) {
-            const long long c0 = K1_CLK();
-            const unsigned base = ring_take_batch(&hdr->k1_ticket, pend, lane, ring.batch, frames);
-            r_wait0 += K1_CLK() - c0;
-            if (base >= frames) break;
+        // one batch of tickets -> rows into the ring; returns false when the queue is exhausted
+        auto issue_batch = [&](unsigned base) -> bool {
+            if (base >= frames) return false;
             const unsigned f = base + (unsigned)lane;
             int b = 0, t = 0, Lb = 0;
             bool valid = false, need = false;
             if (lane < ring.batch && f < frames) {
                 frame_of_ticket(f, d.B, d.T, (d.progress & 2) != 0, b, t);
-                int Tb = d.input_lengths ? __ldg(d.input_lengths + b) : d.T;
-                Lb = d.label_lengths ? __ldg(d.label_lengths + b) : d.Lmax;
-                Tb = max(0, min(Tb, d.T));
-                Lb = max(0, min(Lb, d.Lmax));
+                int Tb;
+                if (len_cached) { Tb = len_sm[b]; Lb = len_sm[d.B + b]; }
+                else {
+                    Tb = d.input_lengths ? __ldg(d.input_lengths + b) : d.T;
+                    Lb = d.label_lengths ? __ldg(d.label_lengths + b) : d.Lmax;
+                    Tb = max(0, min(Tb, d.T));
+                    Lb = max(0, min(Lb, d.Lmax));
+                }
                 valid = t < Tb;
                 need = valid || ARGMAX;
             }
@@ -425,6 +439,25 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             }
             r_wait1 += K1_CLK() - c1;
             q += (unsigned)__popc(mask);
+            return true;
+        };
+        // Batches of rows are drawn from a global ticket counter (variable-length utterances balance themselves; dealing
+        // the batches round-robin instead was measured: the slowest CTA then finishes 8 % later).  Under a full-rate stream
+        // one atomic on that hot address takes ~5 us to come back, so two tickets are kept in flight: the one a batch
+        // needs was requested two batches ago.
+        unsigned pa = 0, pb = 0;
+        if (lane == 0) { pa = atomicAdd(&hdr->k1_ticket, (unsigned)ring.batch); pb = atomicAdd(&hdr->k1_ticket, (unsigned)ring.batch); }
+        for (;;) {
+            long long c0 = K1_CLK();
+            unsigned base = __shfl_sync(0xffffffffu, pa, 0);
+            if (lane == 0 && base < frames) pa = atomicAdd(&hdr->k1_ticket, (unsigned)ring.batch);
+            r_wait0 += K1_CLK() - c0;
+            if (!issue_batch(base)) break;
+            c0 = K1_CLK();
+            base = __shfl_sync(0xffffffffu, pb, 0);
+            if (lane == 0 && base < frames) pb = atomicAdd(&hdr->k1_ticket, (unsigned)ring.batch);
+            r_wait0 += K1_CLK() - c0;
+            if (!issue_batch(base)) break;
         }
         ring_stop(ring, q, lane);
         B200CTC_TL_K1(true);
@@ -444,7 +477,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     unsigned pushed = 0;
     long long c_wait = 0, c_proc = 0, c_rows = 0;
     const long long c_begin = K1_CLK();
-    for (unsigned q = (unsigned)(warp - 1);; q += (unsigned)ring.nc) {
+    for (;;) {
+        const unsigned q = ring_next_row(ring, lane);
         const long long c0 = K1_CLK();
         const int s = ring_acquire(ring, q);
         const long long c1 = K1_CLK();
@@ -455,6 +489,15 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
             if (lane == 0) mbar_arrive(&ring.empty[s]);
             break;
         }
+#ifdef B200CTC_EXPERIMENT
+        if (d.progress & 64) {                  // streaming-rate experiment: rows are dropped as they land (results are garbage)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[s]);
+            c_proc += K1_CLK() - c1;
+            ++c_rows;
+            continue;
+        }
+#endif
         float *slotf = reinterpret_cast<float *>(ring.slot(s));
         const float *row = slotf + m.off;                              // element v of the frame
         const float4 *row4 = reinterpret_cast<const float4 *>(slotf);  // the aligned span, float4 by float4
@@ -624,7 +667,7 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
     const long long frames = (long long)d.B * d.T;
     if (frames == 0) return cudaSuccess;
     unsigned char *wsb = static_cast<unsigned char *>(ws);
-    const RingLayout rl = make_ring(ring_row_bytes(d.V), kFifoBytes, smem_reserve, kK1Consumers);
+    const RingLayout rl = make_ring(ring_row_bytes(d.V), kFifoBytes + (d.B <= kLenCache ? 8 * (size_t)d.B : 0), smem_reserve, kK1Consumers);
     if (ring_usable(d.acts, d.stride_t, d.stride_b, d.V, rl) && !knobs().no_tma_k1) {
         long long ctas = (frames + kTicketBatch - 1) / kTicketBatch;
         if (ctas > sm_count()) ctas = sm_count();

@@ -33,10 +33,12 @@ def fast_ctc_problem(B, T, V, L, seed):
 # ---- long label sequences: every nodes-per-lane variant of the lattice kernel (csrc/lattice.cu, launch_lattice) ----
 LONG_CTC = [
     # B, T, V, L
-    (2, 1300, 16, 600),      # N = 1201: K=4
-    (1, 2100, 16, 1000),     # N = 2001: K=4, near the instantiated maximum (2048 nodes)
-    (2, 1100, 24, 500),      # N = 1001: the largest K=2 lattice
+    (2, 1300, 16, 600),      # N = 1201: four nodes per lane
+    (1, 2100, 16, 1000),     # N = 2001: near the instantiated maximum (2048 nodes)
+    (2, 1100, 24, 500),      # N = 1001
     (3, 900, 32, 400),
+    (2, 600, 32, 255),       # N = 511: the largest lattice with two nodes per lane (8 warps per direction)
+    (2, 600, 32, 256),       # N = 513: the smallest with four
 ]
 
 
