@@ -12,6 +12,12 @@ truncated to ``(x_length - repeats - 1) // 2`` ids.  Everything is assembled str
 so that a single asynchronous copy moves the labels, bigrams and both length vectors to the device (the
 reference issues four ``cuda.to_gpu`` calls per batch, asr/data/loaders/base.py:28-31).  Host-side code: there is
 nothing here for the GPU to do.
+
+``sort_by_length=True`` lays the batch out longest utterance first (stable) and also returns the permutation, which
+the caller applies to the feature batch: the lattice kernel starts its CTAs in batch order, so when a batch has
+more utterances than the GPU can hold lattice CTAs at once (B > ~2 x #SMs) the long ones start first and the short
+ones fill the tail (longest-processing-time-first).  The node -> vocabulary-slot tables of the gradient kernel are
+built on the device inside the forward call (csrc/prep.cuh), not here.
 """
 import numpy as np
 import torch
@@ -28,10 +34,11 @@ def _default_tokenizer(sentence):
 
 
 def labels_to_minibatch(sentences, x_length_batch, max_sentence_length, token_ids, id_blank, tokenizer=None,
-                        device=None, pin=True):
+                        device=None, pin=True, sort_by_length=False):
     """Returns ``(t_batch, bigram_batch, x_length_batch, t_length_batch)`` as int32 torch tensors -- views of one
     (pinned) host block, or of its device copy when ``device`` is given.  ``sentences``: transcriptions (strings, run
-    through ``tokenizer``) or ready lists of unigram tokens."""
+    through ``tokenizer``) or ready lists of unigram tokens.  With ``sort_by_length`` a fifth value follows: ``order``
+    (int64, host), row i of every output belongs to ``sentences[order[i]]``."""
     assert isinstance(token_ids, dict)                                 # :114
     assert isinstance(id_blank, int)                                   # :115
     tokenizer = tokenizer or _default_tokenizer
@@ -46,11 +53,13 @@ def labels_to_minibatch(sentences, x_length_batch, max_sentence_length, token_id
     t_len = host[2 * B * Lmax + B:]
     t_batch[...] = id_blank                                            # :125
     bigram_batch[...] = id_blank                                       # :126
-    for b, sentence in enumerate(sentences):
+    order = np.argsort(-np.asarray(x_length_batch, dtype=np.int64), kind="stable") if sort_by_length else np.arange(B)
+    for row, src in enumerate(order):
+        sentence = sentences[src]
         tokens = tokenizer(sentence) if isinstance(sentence, str) else list(sentence)      # :132
         unigram_ids = [token_ids[tok] for tok in tokens]               # :140-141
         bigram_ids = [-1] + [token_ids.get(first + second, -1) for first, second in zip(tokens[:-1], tokens[1:])]   # :139-146
-        x_length = int(x_length_batch[b])
+        x_length = int(x_length_batch[src])
         t_length = len(unigram_ids)
         # CTC feasibility (:159-166).  np.roll makes the neighbour test circular: id 0 is compared with the last id.
         repeats = int(np.count_nonzero(np.asarray(unigram_ids) == np.roll(unigram_ids, 1))) if t_length else 0
@@ -59,10 +68,11 @@ def labels_to_minibatch(sentences, x_length_batch, max_sentence_length, token_id
             unigram_ids = unigram_ids[:possible]                       # Python slice semantics, negative values included
             bigram_ids = bigram_ids[:possible]
             t_length = len(unigram_ids)
-        t_batch[b, :t_length] = unigram_ids                            # :168
-        bigram_batch[b, :t_length] = bigram_ids                        # :169
-        x_len[b] = x_length
-        t_len[b] = t_length
+        t_batch[row, :t_length] = unigram_ids                            # :168
+        bigram_batch[row, :t_length] = bigram_ids                        # :169
+        x_len[row] = x_length
+        t_len[row] = t_length
     out = block if device is None else block.to(device, non_blocking=True)
-    return (out[:B * Lmax].view(B, Lmax), out[B * Lmax:2 * B * Lmax].view(B, Lmax),
-            out[2 * B * Lmax:2 * B * Lmax + B], out[2 * B * Lmax + B:])
+    res = (out[:B * Lmax].view(B, Lmax), out[B * Lmax:2 * B * Lmax].view(B, Lmax),
+           out[2 * B * Lmax:2 * B * Lmax + B], out[2 * B * Lmax + B:])
+    return res + (torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64)),) if sort_by_length else res

@@ -62,7 +62,7 @@ struct WsLayout {
     int joint;         // 0 / 1
     int Nmax2, Np2;    // CTC lattice nodes for Lmax, padded like Np (its beta rows are stored one element up)
     size_t off_av2, off_bv2, off_utt2;
-    size_t off_hdr, off_utt, off_lse, off_lp, off_av, off_bv, off_usym, off_uoff, off_unode, off_bm, off_pc, total;
+    size_t off_hdr, off_utt, off_lse, off_lp, off_av, off_bv, off_usym, off_uoff, off_unode, off_urec, off_bm, off_pc, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -95,6 +95,7 @@ __host__ inline WsLayout make_layout(int kind, int B, int T, int V, int Lmax) {
     w.off_usym = o;  o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
     w.off_uoff = o;  o = align_up(o + sizeof(int) * (size_t)B * (w.Nmax + 1), 256);
     w.off_unode = o; o = align_up(o + sizeof(int) * (size_t)B * w.Nmax, 256);
+    w.off_urec = o;  o = align_up(o + 16 * (size_t)B * w.Nmax, 256);         // int4 per distinct id, see prep.cuh
     w.off_bm = o;    o = align_up(o + sizeof(unsigned) * (size_t)B * w.nwords, 256);
     w.off_pc = o;    o = align_up(o + sizeof(int) * (size_t)B * w.nwords, 256);
     w.off_prog = o;  o = align_up(o + sizeof(unsigned) * (size_t)B * w.nblk, 256);

@@ -238,12 +238,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const uint32_t span_max = (uint32_t)ring_row_bytes(d.V);             // where the alpha row starts in a slot
     const uint32_t ab_bytes = (uint32_t)w.Np * 8u;
     const uint32_t ab2_bytes = w.joint ? (uint32_t)w.Np2 * 8u : 0u;      // joint: + the plain-CTC lattice's alpha/beta rows
-    // extra region: [V + 4 floats of zeros][per consumer: Umax floats posterior]
+    // extra region: [V + 4 floats of zeros][utterance records]
     B200CTC_TL_K3(false);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
-    float *post_all = zero_row + ((d.V + 4 + 3) & ~3);
     // the utterance records, once per CTA: a consumer's row then starts without a round trip to L2
-    UttInfo *utt_sm = reinterpret_cast<UttInfo *>(post_all + (size_t)kRingConsumers * ((w.Umax + 3) & ~3));
+    UttInfo *utt_sm = reinterpret_cast<UttInfo *>(zero_row + ((d.V + 4 + 3) & ~3));
     const bool utt_cached = d.B <= kUttCache;
     for (int i = threadIdx.x; i < d.V + 4; i += blockDim.x) zero_row[i] = 0.f;
     if (utt_cached) {
@@ -330,10 +329,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
 
     // ===== consumers =====
     const float *lse_all = reinterpret_cast<const float *>(ws + w.off_lse);
-    const int *uoff_all = reinterpret_cast<const int *>(ws + w.off_uoff);
     const int *unode_all = reinterpret_cast<const int *>(ws + w.off_unode);
-    const int *usym_all = reinterpret_cast<const int *>(ws + w.off_usym);
-    float *post_sm = post_all + (size_t)(warp - 1) * ((w.Umax + 3) & ~3);
+    const int4 *urec_all = reinterpret_cast<const int4 *>(ws + w.off_urec);
+    constexpr int kRecBatch = 4;                          // id records per lane requested in one go
     const int per = d.kind == 0 ? 2 : 3;
     if (warp - 1 >= ring.nc) return;                      // short ring: fewer active consumers (row_ring.cuh)
     for (;;) {
@@ -359,6 +357,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
         // requested now, needed after the posteriors: their round trip hides behind the node loop
         const float lse2 = __ldg(lse_all + (size_t)b * d.T + t);
         const float sc = (gp.per_utterance ? __ldg(gp.grad_loss + b) : __ldg(gp.grad_loss)) * gp.scale;      // :291-294
+        const int4 *urec = urec_all + (size_t)b * w.Nmax;
+        int4 rec[kRecBatch];
+#pragma unroll
+        for (int k = 0; k < kRecBatch; ++k)
+            rec[k] = 32 * k + lane < ui.Ub ? __ldg(urec + 32 * k + lane) : make_int4(0, 0, 0, -1);
 
         float blank_part = 0.f;
         for (int j0 = 0; j0 < ui.Nb; j0 += 32) {
@@ -386,20 +389,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             }
         }
         blank_part = warp_sum(blank_part);
-        __syncwarp();
-        const int *uoff = uoff_all + (size_t)b * (w.Nmax + 1);
-        const int *unode = unode_all + (size_t)b * w.Nmax;
-        const int *usym = usym_all + (size_t)b * w.Nmax;
-        for (int u = lane; u < ui.Ub; u += 32) {                             // merge per emitted id (:180-217)
-            const int n0 = __ldg(uoff + u), n1 = __ldg(uoff + u + 1);
-            float post = (u == ui.ublank) ? blank_part : 0.f;
-            for (int n = n0; n < n1; ++n) {
-                const int j = __ldg(unode + n);
-                if (j < ui.Nb) post += e_sm[j];
-                post += joint_partner(e2_sm, j, Nb2);
-            }
-            post_sm[u] = post * sc;
-        }
         const float sc_soft = w.joint ? 2.f * sc : sc;                       // two losses, two softmax terms
         const float c = -lse2;
         // softmax * sc in place, over the whole aligned span (what lies outside the row is never stored)
@@ -414,7 +403,32 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             row4[i] = v;
         }
         __syncwarp();
-        for (int u = lane; u < ui.Ub; u += 32) row[__ldg(usym + u)] -= post_sm[u];     // distinct columns (:290)
+        // merge per emitted id (:180-217) and subtract at the id's column (distinct columns, :290): blank nodes from
+        // the strided sum above, the others in node order (fixed order => deterministic).  The records of the first
+        // 128 ids were requested at the start of the row; an id carried by one node needs nothing else.
+        const int *unode = unode_all + (size_t)b * w.Nmax;
+        for (int u0 = 0; u0 < ui.Ub; u0 += 32 * kRecBatch) {
+            if (u0 > 0) {
+#pragma unroll
+                for (int k = 0; k < kRecBatch; ++k) {
+                    const int u = u0 + 32 * k + lane;
+                    rec[k] = u < ui.Ub ? __ldg(urec + u) : make_int4(0, 0, 0, -1);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kRecBatch; ++k) {
+                const int u = u0 + 32 * k + lane;
+                if (u >= ui.Ub) continue;
+                float post = (u == ui.ublank) ? blank_part : 0.f;
+                int j = rec[k].w;
+                for (int n = 0; n < rec[k].z; ++n) {
+                    if (n > 0) j = __ldg(unode + rec[k].y + n);
+                    if (j < ui.Nb) post += e_sm[j];
+                    post += joint_partner(e2_sm, j, Nb2);
+                }
+                row[rec[k].x] -= post * sc;
+            }
+        }
         float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
         if (row_misalignment(dst) == m.off) {                                // warp-uniform
             fence_proxy_async_smem();
@@ -443,8 +457,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
     if (frames == 0) return cudaSuccess;
     unsigned char *wsb = const_cast<unsigned char *>(static_cast<const unsigned char *>(ws));
     const int b_major = g.gstride_b > g.gstride_t ? 1 : 0;
-    const size_t extra = sizeof(float) * ((size_t)((g.d.V + 4 + 3) & ~3) + (size_t)kRingConsumers * ((w.Umax + 3) & ~3)) +
-                         (g.d.B <= kUttCache ? sizeof(UttInfo) * (size_t)g.d.B : 0);
+    const size_t extra = sizeof(float) * (size_t)((g.d.V + 4 + 3) & ~3) + (g.d.B <= kUttCache ? sizeof(UttInfo) * (size_t)g.d.B : 0);
     const RingLayout rl = make_ring(ring_row_bytes(g.d.V) + sizeof(float) * (4 * (size_t)w.Np + (w.joint ? 4 * (size_t)w.Np2 : 0)), extra);
     if (ring_usable(g.d.acts, g.d.stride_t, g.d.stride_b, g.d.V, rl) &&
         ring_usable(g.grad_out, g.gstride_t, g.gstride_b, g.d.V, rl) && !knobs().no_tma_k3) {

@@ -12,6 +12,8 @@ namespace b200ctc {
 //   usym[u]            distinct emitted ids, sorted ascending, blank included (Ub of them)
 //   uoff[u]..uoff[u+1] range in unode[] listing the non-blank-type nodes that carry id usym[u]
 //                      (the blank-type nodes -- every 2nd / 3rd node -- are summed directly)
+//   urec[u]            {usym[u], uoff[u], node count, first node or -1}: one 16-byte load gives the gradient kernel all
+//                      it needs for an id carried by a single node (the common case) -- no chain of dependent loads
 //   bm[], pc[]         V-bit bitmap of emitted ids and, per 32-bit word, the number of set bits before it,
 //                      so that "posterior slot of column k" = pc[k/32] + popc(bm[k/32] & low bits).
 // ---------------------------------------------------------------------------------------------
@@ -104,6 +106,10 @@ __device__ __forceinline__ void prep_utterance(const ProblemDesc &d, const WsLay
         const int node = d.kind == 0 ? (2 * en + 1) : (3 * (en >> 1) + 1 + (en & 1));
         unode[uoff[erank[efirst[e]]] + epos[e]] = node;
     }
+    __syncthreads();
+    int4 *urec = reinterpret_cast<int4 *>(ws + w.off_urec) + (size_t)b * w.Nmax;
+    for (int u = threadIdx.x; u < s_U; u += blockDim.x)
+        urec[u] = make_int4(usym[u], uoff[u], cnt[u], cnt[u] > 0 ? unode[uoff[u]] : -1);
 }
 
 

@@ -61,3 +61,49 @@ def test_labels_match_reference_live():
                                                     tokenizer=vocab.convert_sentence_to_unigram_tokens)
         assert np.array_equal(t.numpy(), tb) and np.array_equal(big.numpy(), bb)
         assert tl.tolist() == list(tlb) and xl.tolist() == list(xlb)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_length_sorted_layout_is_a_row_permutation_of_the_reference(path):
+    """sort_by_length=True: longest utterance first (stable), every row still the reference's row for that sentence."""
+    g = np.load(path)
+    ids = {str(t): i for i, t in enumerate(g["inventory"])}
+    offs = g["offsets"]
+    sentences = [[str(t) for t in g["tokens"][offs[b]:offs[b + 1]]] for b in range(len(offs) - 1)]
+    t, big, xl, tl, order = mine().labels_to_minibatch(sentences, g["x_length"], int(g["Lmax"]), ids, 0,
+                                                       sort_by_length=True)
+    order = order.numpy()
+    assert sorted(order.tolist()) == list(range(len(sentences)))
+    assert np.all(np.diff(xl.numpy()) <= 0)
+    assert np.array_equal(order, np.argsort(-g["ref_x_length"].astype(np.int64), kind="stable"))
+    assert np.array_equal(t.numpy(), g["ref_t"][order])
+    assert np.array_equal(big.numpy(), g["ref_bigram"][order])
+    assert np.array_equal(tl.numpy(), g["ref_t_length"][order])
+    assert np.array_equal(xl.numpy(), g["ref_x_length"][order])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_device_block_feeds_the_loss(path):
+    """device=: the four arrays arrive on the GPU as views of ONE device block, equal to the reference's arrays, and go
+    into gram_ctc as they are; the length-sorted layout gives the same per-utterance losses, permuted."""
+    import torch
+    import b200ctc
+    g = np.load(path)
+    ids = {str(t): i for i, t in enumerate(g["inventory"])}
+    offs = g["offsets"]
+    sentences = [[str(t) for t in g["tokens"][offs[b]:offs[b + 1]]] for b in range(len(offs) - 1)]
+    dev = torch.device("cuda:0")
+    Lmax, B = int(g["Lmax"]), len(sentences)
+    t, big, xl, tl = mine().labels_to_minibatch(sentences, g["x_length"], Lmax, ids, 0, device=dev)
+    assert t.is_cuda and t.untyped_storage().data_ptr() == tl.untyped_storage().data_ptr()
+    assert np.array_equal(t.cpu().numpy(), g["ref_t"]) and np.array_equal(big.cpu().numpy(), g["ref_bigram"])
+    assert np.array_equal(tl.cpu().numpy(), g["ref_t_length"]) and np.array_equal(xl.cpu().numpy(), g["ref_x_length"])
+    T, V = int(g["x_length"].max()), len(ids)
+    x = torch.randn((T, B, V), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    loss = b200ctc.gram_ctc(x, t, big, 0, xl, tl, reduce="no")
+    ts, bs, xls, tls, order = mine().labels_to_minibatch(sentences, g["x_length"], Lmax, ids, 0, device=dev,
+                                                         sort_by_length=True)
+    loss_sorted = b200ctc.gram_ctc(x[:, order.to(dev)], ts, bs, 0, xls, tls, reduce="no")
+    assert torch.equal(loss_sorted, loss[order.to(dev)])
+    assert torch.isfinite(loss).all()

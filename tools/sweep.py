@@ -40,6 +40,7 @@ def configs():
     yield "cfg3 +ctc, 2 calls", "gram+ctc", 32, 600, 8000, 60      # joint training, run/gram_ctc/cnn/train.py:196-198
     yield "cfg3 +ctc, joint", "joint", 32, 600, 8000, 60           # the same objective from one pass (joint_ctc=True)
     yield "cfg4", "ctc", 512, 800, 3500, 80
+    yield "cfg4 length-sorted", "ctc", 512, 800, 3500, 80          # asr/data/processing.py sort_by_length=True
     for T in (200, 800, 1600, 3200):
         for V in (100, 3500):
             yield "cfg5 T=%d V=%d" % (T, V), "ctc", 64, T, V, T // 10
@@ -49,6 +50,9 @@ def run(name, kind, B, T, V, L, steps=20, warmup=5):
     dev = torch.device("cuda:0")
     rs = np.random.RandomState(0)
     in_len, lab_len = synth.make_lengths(rs, B, T, L)
+    if "sorted" in name:
+        order = np.argsort(-in_len, kind="stable")
+        in_len, lab_len = np.ascontiguousarray(in_len[order]), np.ascontiguousarray(lab_len[order])
     if kind == "ctc":
         labels = synth.make_ctc_labels(rs, B, L, V, lab_len)
         big = None
