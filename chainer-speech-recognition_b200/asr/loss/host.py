@@ -6,8 +6,8 @@ gradients.  Here the arithmetic still runs on the GPU: the batch is cut into utt
 three stages of a group -- activations host->device, loss forward + gradient, gradient device->host --
 run on three CUDA streams, so the PCIe transfers in both directions overlap each other and the kernels.
 Only valid frames cross PCIe, in both directions: padded frames are never read by the kernels, and their gradient rows
-are exactly zero (gram_ctc.py:296), so the host writes those itself -- on a small thread pool (a single-threaded memset
-of pinned memory is slower than the DMA it would replace; a few threads are not) while the copies are in flight.
+are exactly zero (gram_ctc.py:296), so the host clears those itself -- libc memset (streaming stores) on two helper
+threads while the copies are in flight (a NumPy slice assignment needed eight threads for the same work).
 Utterances are independent, so grouping changes no result bit-for-bit per utterance.
 
 Layout: host activations are (B,T,V) ("batch first", the decoder layout of asr/model/cnn.py:45-47), which makes
@@ -15,6 +15,7 @@ a group a contiguous slab of host memory; pass pinned tensors (``torch.Tensor.pi
 copies to be asynchronous.
 """
 import concurrent.futures
+import ctypes
 import os
 
 import numpy as np
@@ -35,7 +36,11 @@ def _zero_pool():
             n = len(os.sched_getaffinity(0))
         except Exception:
             n = os.cpu_count() or 2
-        _pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(8, n // 2)), thread_name_prefix="b200ctc-zero")
+        # two threads keep up with the DMA now that the rows are cleared by libc memset (one does, measured); more only
+        # fight the other ranks of a multi-GPU job for the memory system.  B200CTC_HOST_THREADS overrides.
+        want = os.environ.get("B200CTC_HOST_THREADS")
+        n = int(want) if want else min(2, n)
+        _pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(1, n), thread_name_prefix="b200ctc-zero")
     return _pool
 
 
@@ -91,6 +96,9 @@ def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length,
     assert 0 <= int(blank_symbol) < V
     if grad_out is None:
         grad_out = torch.empty((B, T, V), dtype=torch.float32, pin_memory=True)
+    elif not (isinstance(grad_out, torch.Tensor) and grad_out.dtype == torch.float32 and not grad_out.is_cuda and
+              tuple(grad_out.shape) == (B, T, V) and grad_out.is_contiguous()):
+        raise ValueError("grad_out must be a contiguous float32 host tensor of shape (B,T,V)")
     labels = _as_int32(labels, dev, "labels")
     bigrams = _as_int32(bigrams, dev, "label_bigram") if kind == _lib.KIND_GRAM else None
     il_host = None
@@ -113,10 +121,10 @@ def lattice_loss_host(kind, x_host, labels, bigrams, blank_symbol, input_length,
     zero_jobs = []
     if il_host is not None:
         # padded rows of the host gradient: zeroed by the pool while the DMA engines move the valid rows
-        g_np = grad_out.numpy()
+        g_base, row_bytes = grad_out.data_ptr(), V * 4
 
-        def zero_rows(b, n):
-            g_np[b, n:] = 0.0
+        def zero_rows(b, n):               # libc memset: streaming stores, and ctypes drops the GIL for the call
+            ctypes.memset(g_base + (b * T + n) * row_bytes, 0, (T - n) * row_bytes)
         pool = _zero_pool()
         for b in range(B):
             n = int(min(max(il_host[b], 0), T))
