@@ -340,24 +340,29 @@ def main():
     # all-reduce of the loss -- is issued after the gradient kernel has been enqueued, so no rank's backward ever
     # waits for a peer's forward.
     kw = {"batch_global": world * B} if world > 1 else {}
-    red = {"buf": torch.zeros((), dtype=torch.float32, device=dev), "work": None}
+    kDepth = 4                                       # all-reduces in flight per rank
+    red = {"buf": [torch.zeros((), dtype=torch.float32, device=dev) for _ in range(kDepth)], "work": [None] * kDepth, "n": 0}
 
     def reduce_loss(loss):
-        """The scalar all-reduce, asynchronous: the rank-local partial loss is copied into a buffer of its own and
-        NCCL reduces that buffer on its stream; the compute stream only waits for it when the buffer is about to be
-        reused (one step later) or read.  Nothing of the next step queues behind a peer."""
+        """The scalar all-reduce, asynchronous: the rank-local partial loss is copied into one of a few buffers of its
+        own and NCCL reduces that buffer on its stream; the compute stream only waits for it when the buffer is about
+        to be reused (kDepth steps later) or read.  Nothing of the next steps queues behind a peer, and a rank may run
+        up to kDepth steps ahead of the slowest one instead of meeting it after every step."""
         if world > 1:
-            if red["work"] is not None:
-                red["work"].wait()
-            red["buf"].copy_(loss.detach())
-            red["work"] = dist.all_reduce(red["buf"], op=dist.ReduceOp.SUM, group=group, async_op=True)
-            return red["buf"]
+            i = red["n"] % kDepth
+            red["n"] += 1
+            if red["work"][i] is not None:
+                red["work"][i].wait()
+            red["buf"][i].copy_(loss.detach())
+            red["work"][i] = dist.all_reduce(red["buf"][i], op=dist.ReduceOp.SUM, group=group, async_op=True)
+            return red["buf"][i]
         return loss
 
     def finish_reduce():
-        if red["work"] is not None:
-            red["work"].wait()
-            red["work"] = None
+        for i in range(kDepth):
+            if red["work"][i] is not None:
+                red["work"][i].wait()
+                red["work"][i] = None
 
     def step():
         x.grad = None

@@ -22,7 +22,7 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_committed_bench_lines_follow_the_contract():
-    for name, n in (("r1_bench_n1.json", 1), ("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4), ("r1_bench_n8.json", 8)):
+    for name, n in [("r%d_bench_n%d.json" % (r, n), n) for r in (1, 2) for n in (1, 2, 4, 8)]:
         path = os.path.join(ROOT, "profiles", name)
         with open(path) as f:
             d = json.loads(f.read())
@@ -37,3 +37,10 @@ def test_committed_bench_lines_follow_the_contract():
     with open(os.path.join(ROOT, "profiles", "r1_bench_n1.json")) as f:
         d = json.loads(f.read())
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    # round 2: the CPU baseline is the reference's own implementation, staged into oracle/_ref by build()
+    with open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")) as f:
+        d = json.loads(f.read())
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] == 1
+    with open(os.path.join(ROOT, "profiles", "r2_bench_reference_n1.json")) as f:
+        ref = json.loads(f.read())
+    assert ref["impl"] == "reference" and ref["config"] == d["config"] and ref["metric"] == d["metric"]
