@@ -216,17 +216,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) gradient_kernel(GradParams 
 // ---------------------------------------------------------------------------------------------
 // Store a row image that sits in shared memory at the same 16-byte phase as its destination: the aligned body as
 // one bulk copy, the <= 3 floats in front of and behind it with ordinary stores.  Called by one lane.
-__device__ __forceinline__ void store_row_image(float *dst, const float *src_sm, int V) {
+__device__ __forceinline__ void store_row_image(float *dst, const float *src_sm, int V, uint64_t policy, bool hint) {
     const int head = min(V, (4 - row_misalignment(dst)) & 3);
     const int body = (V - head) & ~3;
     for (int i = 0; i < head; ++i) dst[i] = src_sm[i];
     for (int i = head + body; i < V; ++i) dst[i] = src_sm[i];
-    if (body > 0) bulk_s2g(dst + head, src_sm + head, (uint32_t)body * 4u);
+    if (body > 0) {
+        if (hint) bulk_s2g_hint(dst + head, src_sm + head, (uint32_t)body * 4u, policy);
+        else bulk_s2g(dst + head, src_sm + head, (uint32_t)body * 4u);
+    }
     bulk_commit();
 }
 
 __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradParams gp, WsLayout w, unsigned char *ws,
-                                                                       int b_major, RingLayout rl) {
+                                                                       int b_major, RingLayout rl, int l2_hints) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ring ring = ring_setup(smem_raw, rl);
     const ProblemDesc &d = gp.d;
@@ -238,6 +241,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const uint32_t span_max = (uint32_t)ring_row_bytes(d.V);             // where the alpha row starts in a slot
     const uint32_t ab_bytes = (uint32_t)w.Np * 8u;
     const uint32_t ab2_bytes = w.joint ? (uint32_t)w.Np2 * 8u : 0u;      // joint: + the plain-CTC lattice's alpha/beta rows
+    const uint64_t l2pol = l2_policy_evict_first();
+    const bool l2hint = (l2_hints & 1) != 0;
     // extra region: [V + 4 floats of zeros][utterance records]
     B200CTC_TL_K3(false);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                 else { t = (int)(f / d.B); b = (int)(f % d.B); }
                 if (t >= (utt_cached ? utt_sm[b].Tb : utt[b].Tb)) {                  // :296 -- zeros, straight from smem
                     float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
-                    store_row_image(dst, zero_row + row_misalignment(dst), d.V);
+                    store_row_image(dst, zero_row + row_misalignment(dst), d.V, l2pol, l2hint);
                 } else {
                     need = true;
                 }
@@ -287,7 +292,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                     ring.meta[s].b = b; ring.meta[s].t = t; ring.meta[s].kind = 0; ring.meta[s].off = off;
                     ring_publish(ring, s, myq);
                     mbar_arrive_expect_tx(&ring.full[s], span + 2 * ab_bytes + 2 * ab2_bytes);
-                    bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
+                    if (l2hint) bulk_g2s_hint(ring.slot(s), src - off, span, &ring.full[s], l2pol);
+                    else bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
                     bulk_g2s(ring.slot(s) + span_max, av_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
                     bulk_g2s(ring.slot(s) + span_max + ab_bytes, bv_all + ((size_t)b * d.T + t) * w.Np, ab_bytes, &ring.full[s]);
                     if (w.joint) {
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                store_row_image(dst, row, d.V);
+                store_row_image(dst, row, d.V, l2pol, l2hint);
                 bulk_wait_read<0>();             // the TMA engine has read the slot: hand it back to the producer
                 mbar_arrive(&ring.empty[s]);
             }
@@ -466,7 +472,7 @@ cudaError_t launch_gradient(const GradParams &g, const WsLayout &w, const void *
         if (ctas < 1) ctas = 1;
         cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(gradient_ring_kernel), rl.total);
         if (e != cudaSuccess) return e;
-        gradient_ring_kernel<<<(int)ctas, kRingThreads, rl.total, stream>>>(g, w, wsb, b_major, rl);
+        gradient_ring_kernel<<<(int)ctas, kRingThreads, rl.total, stream>>>(g, w, wsb, b_major, rl, knobs().l2_hints);
         return cudaGetLastError();
     }
     const int per_warp = w.Np + ((w.Umax + 3) & ~3) + (w.joint ? w.Np2 : 0);

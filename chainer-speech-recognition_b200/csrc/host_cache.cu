@@ -81,6 +81,7 @@ const Knobs &knobs() {
         if (const char *e = getenv("B200CTC_DBG_PROGRESS")) k.dbg_progress = atoi(e);
         if (const char *e = getenv("B200CTC_LAT_K")) k.lat_k = atoi(e);
         if (const char *e = getenv("B200CTC_LAT_CH")) k.lat_ch = atoi(e);
+        if (const char *e = getenv("B200CTC_L2_HINTS")) k.l2_hints = atoi(e);
 #endif
     });
     return k;

@@ -360,9 +360,11 @@ __device__ __forceinline__ void fast_row_finish(float ref, float sl, float &la, 
 template <bool ARGMAX>
 __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(ProblemDesc d, WsLayout w,
                                                                               unsigned char *ws,
-                                                                              int64_t *argmax_out, RingLayout rl) {
+                                                                              int64_t *argmax_out, RingLayout rl, int l2_hints) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ring ring = ring_setup(smem_raw, rl);
+    const uint64_t l2pol = l2_policy_evict_first();
+    const bool l2hint = (l2_hints & 2) != 0;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws + w.off_hdr);
@@ -431,7 +433,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
                     ring.meta[s].Lb = Lb;
                     ring_publish(ring, s, myq);
                     mbar_arrive_expect_tx(&ring.full[s], span);
-                    bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
+                    if (l2hint) bulk_g2s_hint(ring.slot(s), src - off, span, &ring.full[s], l2pol);
+                    else bulk_g2s(ring.slot(s), src - off, span, &ring.full[s]);
                     pending = false;
                     issued = true;
                 }
@@ -676,11 +679,11 @@ cudaError_t launch_softmax_gather(const ProblemDesc &d, const WsLayout &w, void 
         if (argmax_out) {
             e = ensure_dynamic_smem(reinterpret_cast<const void *>(softmax_gather_ring_kernel<true>), rl.total);
             if (e != cudaSuccess) return e;
-            softmax_gather_ring_kernel<true><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, argmax_out, rl);
+            softmax_gather_ring_kernel<true><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, argmax_out, rl, knobs().l2_hints);
         } else {
             e = ensure_dynamic_smem(reinterpret_cast<const void *>(softmax_gather_ring_kernel<false>), rl.total);
             if (e != cudaSuccess) return e;
-            softmax_gather_ring_kernel<false><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, nullptr, rl);
+            softmax_gather_ring_kernel<false><<<(int)ctas, kK1Threads, rl.total, stream>>>(d, w, wsb, nullptr, rl, knobs().l2_hints);
         }
         return cudaGetLastError();
     }
