@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
     const uint32_t ab_bytes = (uint32_t)w.Np * 8u;
     const uint32_t ab2_bytes = w.joint ? (uint32_t)w.Np2 * 8u : 0u;      // joint: + the plain-CTC lattice's alpha/beta rows
     const uint64_t l2pol = l2_policy_evict_first();
-    const bool l2hint = (l2_hints & 1) != 0;
+    const bool l2hint = (l2_hints & 1) != 0;        // row loads
+    const bool l2hint_st = (l2_hints & 4) != 0;     // row stores
     // extra region: [V + 4 floats of zeros][utterance records]
     B200CTC_TL_K3(false);
     float *zero_row = reinterpret_cast<float *>(smem_raw + rl.off_extra);
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
                 else { t = (int)(f / d.B); b = (int)(f % d.B); }
                 if (t >= (utt_cached ? utt_sm[b].Tb : utt[b].Tb)) {                  // :296 -- zeros, straight from smem
                     float *dst = gp.grad_out + (int64_t)t * gp.gstride_t + (int64_t)b * gp.gstride_b;
-                    store_row_image(dst, zero_row + row_misalignment(dst), d.V, l2pol, l2hint);
+                    store_row_image(dst, zero_row + row_misalignment(dst), d.V, l2pol, l2hint_st);
                 } else {
                     need = true;
                 }
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gradient_ring_kernel(GradPara
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                store_row_image(dst, row, d.V, l2pol, l2hint);
+                store_row_image(dst, row, d.V, l2pol, l2hint_st);
                 bulk_wait_read<0>();             // the TMA engine has read the slot: hand it back to the producer
                 mbar_arrive(&ring.empty[s]);
             }
