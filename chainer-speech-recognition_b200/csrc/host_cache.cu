@@ -82,6 +82,7 @@ const Knobs &knobs() {
         if (const char *e = getenv("B200CTC_LAT_K")) k.lat_k = atoi(e);
         if (const char *e = getenv("B200CTC_LAT_CH")) k.lat_ch = atoi(e);
         if (const char *e = getenv("B200CTC_L2_HINTS")) k.l2_hints = atoi(e);
+        if (const char *e = getenv("B200CTC_LN_GROUP")) k.ln_group = atoi(e);
 #endif
     });
     return k;

@@ -40,7 +40,7 @@ cudaError_t ensure_dynamic_smem(const void *func, size_t bytes);
 struct Knobs {
     bool no_tma = false;
     bool no_tma_k1 = false, no_tma_k3 = false, gram_k3 = false, lat_nostore = false;
-    int lat_stages = 0, ring_kb = 0, dbg_progress = -1, lat_k = 0, lat_ch = 0;
+    int lat_stages = 0, ring_kb = 0, dbg_progress = -1, lat_k = 0, lat_ch = 0, ln_group = 0;
     int l2_hints = 2;          // bit 0: gradient kernel, bit 1: softmax/gather kernel mark their row streams evict-first in L2
                                // (measured: the forward pass gains 4 us, the gradient kernel loses 2 -- only the first is on)
 };

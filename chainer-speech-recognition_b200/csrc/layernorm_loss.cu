@@ -71,6 +71,7 @@ struct LnTileMeta {
 };
 
 constexpr int kLnFifo = 8;
+constexpr int kLnGroup = 4;              // 8-frame blocks with consecutive tickets: one 128-byte line of every row in flight together
 constexpr int kLnBlankChunks = 64;                         // 32-node chunks of the largest lattice (Nmax <= 2048)
 struct LnSignalFifo {                // forward: finished tiles on their way to the progress counters
     int4 entry[kLnFifo];             // (b, 16-frame block, valid frames, 0); b < 0: done
@@ -150,16 +151,25 @@ __device__ __forceinline__ void mbar_poll(uint64_t *bar, uint32_t parity, int si
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kLnWarps) : "memory"); }
 
 // ---- tile order ----
-// Tiles that share 128-byte lines of z (four consecutive 8-frame blocks of one utterance) get consecutive tickets,
-// so that the SMs working on them touch those lines at about the same time; groups of four walk the time axis from
+#ifdef B200CTC_EXPERIMENT
+inline int ln_group() { return knobs().ln_group > 0 ? knobs().ln_group : kLnGroup; }
+#else
+inline int ln_group() { return kLnGroup; }
+#endif
+// A tile takes 32 bytes out of every row of z, rows 4*T bytes apart: what DRAM sees depends on which tiles are in flight
+// TOGETHER.  Groups of G consecutive 8-frame blocks of one utterance get consecutive tickets, so the SMs working on them
+// touch 32*G contiguous bytes of every row at about the same time.  G = 4 (one 128-byte line) is the measured best:
+// 8 and 16 change nothing, 32 and whole rows are slower (B200CTC_LN_GROUP in the experiment build) -- longer groups
+// serve the lattice kernel in coarser lumps and balance the variable-length utterances worse.  Groups walk the time axis from
 // both ends (the alpha CTAs of the lattice kernel consume frames in ascending, the beta CTAs in descending order).
-__device__ __forceinline__ bool ln_tile_of_ticket(unsigned f, int B, int nTB, bool two_ended, int &b, int &tb) {
-    const int sub = (int)(f & 3u);
-    const unsigned q = f >> 2;
+__device__ __forceinline__ bool ln_tile_of_ticket(unsigned f, int B, int nTB, bool two_ended, int G, int &b, int &tb) {
+    const int sub = (int)(f % (unsigned)G);
+    const unsigned q = f / (unsigned)G;
     b = (int)(q % (unsigned)B);
     const int gs = (int)(q / (unsigned)B);
-    const int g = !two_ended ? gs : (gs & 1) ? ((nTB + 3) / 4 - 1 - (gs >> 1)) : (gs >> 1);
-    tb = 4 * g + sub;
+    const int ngroups = (nTB + G - 1) / G;
+    const int g = !two_ended ? gs : (gs & 1) ? (ngroups - 1 - (gs >> 1)) : (gs >> 1);
+    tb = G * g + sub;
     return tb < nTB;
 }
 
@@ -267,6 +277,7 @@ struct LnParams {
     int K;                          // boxes per tile = ceil(V / 240)
     int nTB;                        // 8-frame blocks = ceil(T / 8)
     int R;                          // ring slots
+    int group;                      // 8-frame blocks of one utterance that get consecutive tickets (ln_tile_of_ticket)
     // backward only
     const float *grad_loss;
     int per_utterance;
@@ -291,7 +302,8 @@ __device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const CUten
     LnTileMeta *metas = reinterpret_cast<LnTileMeta *>(smem + sm.off_meta);
     WsHeader *hdr = reinterpret_cast<WsHeader *>(p.ws + p.w.off_hdr);
     const UttInfo *utt = reinterpret_cast<const UttInfo *>(p.ws + p.w.off_utt);
-    const unsigned tiles = (unsigned)p.d.B * (unsigned)(((p.nTB + 3) / 4) * 4);
+    const int G = p.group;
+    const unsigned tiles = (unsigned)p.d.B * (unsigned)(((p.nTB + G - 1) / G) * G);
     const unsigned R = (unsigned)p.R;
     const int K = p.K;
     unsigned box = 0, seq = 0, n_ab = 0;             // boxes / tile records / alpha-beta loads issued by this CTA
@@ -303,7 +315,7 @@ __device__ __forceinline__ void ln_producer(const CUtensorMap *tmap, const CUten
     while (f < tiles) {
         const unsigned fnext = BACKWARD ? f + gridDim.x : atomicAdd(&hdr->k1_ticket, 1u);     // in flight while we issue
         int b, tb;
-        const bool real = ln_tile_of_ticket(f, p.d.B, p.nTB, !BACKWARD && (p.d.progress & 2) != 0, b, tb);
+        const bool real = ln_tile_of_ticket(f, p.d.B, p.nTB, !BACKWARD && (p.d.progress & 2) != 0, G, b, tb);
         f = fnext;
         if (!real) continue;
         const int t0 = tb * kLnTT;
@@ -525,9 +537,14 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
             else if (tid <= d.Lmax) sym = (tid - 1 < Lb) ? __ldg(d.labels + (size_t)m.b * d.Lmax + tid - 1) : -1;
             else sym = __ldg(d.bigrams + (size_t)m.b * d.Lmax + tid - 1 - d.Lmax);
         }
-        // ---- the tile into registers: rows 240k + 16w + r, frames 4h .. 4h+3 ----
+        // ---- the tile into registers: rows 240k + 16w + r, frames 4h .. 4h+3; the threads that own an emission column
+        //      pick up their symbol's row on the way.  Every box goes back to the loader as soon as this warp has read it:
+        //      the ring is a sliding window of boxes in flight ----
         float4 z[KMAX];
-        const SlotIter first = it;
+        float4 zs0 = make_float4(0.f, 0.f, 0.f, 0.f), zs1 = zs0;
+        if (!(sym >= 0 && sym < d.V)) sym = -1;
+        const int sym_box = sym >= 0 ? sym / kLnBoxRows : -1;
+        const uint32_t sym_off = sym >= 0 ? (uint32_t)((sym % kLnBoxRows) * 32) : 0u;
         {
             SlotIter s = it;
 #pragma unroll
@@ -535,7 +552,11 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
                 z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k < K) {
                     if (k > 0) mbar_spin(&full[s.slot], s.phase, 5);
-                    z[k] = lds128(ring + s.slot * kLnBoxBytes + lane_off);
+                    const uint32_t box = ring + s.slot * kLnBoxBytes;
+                    z[k] = lds128(box + lane_off);
+                    if (sym_box == k) { zs0 = lds128(box + sym_off); zs1 = lds128(box + sym_off + 16); }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s.slot]);
                     s.next(R);
                 }
             }
@@ -566,23 +587,10 @@ __global__ void __maxnreg__(104) ln_softmax_gather_kernel(const __grid_constant_
         int fih;
         const Moments mr = reduce_frames16(mo[0], mo[1], mo[2], mo[3], lane, merge_moments, fih);
         if (lane < 8) { const float v3[3] = {mr.n, mr.mean, mr.m2}; red_store<3>(red, 4 * h + fih, w, v3); }
-        // ---- the rows of the emitted symbols, then the boxes can be refilled ----
-        float4 zs0 = make_float4(0.f, 0.f, 0.f, 0.f), zs1 = zs0;
-        if (sym >= 0 && sym < d.V) {
-            unsigned sl = first.slot + (unsigned)(sym / kLnBoxRows);
-            if (sl >= R) sl -= R;
-            const uint32_t a = ring + sl * kLnBoxBytes + (uint32_t)((sym % kLnBoxRows) * 32);
-            zs0 = lds128(a);
-            zs1 = lds128(a + 16);
-        } else {
-            sym = -1;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            SlotIter s = first;
-            for (int k = 0; k < K; ++k) { mbar_arrive(&empty[s.slot]); s.next(R); }
-        }
         LN_T(2);
+#ifdef B200CTC_EXPERIMENT
+        if (d.progress & 64) continue;        // streaming-rate experiment: the tile is in registers, the boxes are free again -- next
+#endif
         bar_compute();
         LN_T(3);
         if (w < kLnTT) {
@@ -1039,6 +1047,7 @@ cudaError_t launch_ln_forward(const ProblemDesc &d, const LnLayout &ll, void *ws
         sm.R = 2 * p.K + 4;
     }
     p.R = sm.R;
+    p.group = ln_group();
     CUtensorMap map;
     if (!make_z_map(&map, z, d.B, d.T, d.V, zs_b, zs_v)) return cudaErrorInvalidValue;
     long long tiles = (long long)d.B * p.nTB;
@@ -1075,6 +1084,7 @@ cudaError_t launch_ln_backward(const GradParams &g, const LnLayout &ll, const vo
                                    kLnBoxBytes);
     if (sm.R < p.K + 2) { note_failure_site("shared-memory plan"); return cudaErrorInvalidConfiguration; }
     p.R = sm.R;
+    p.group = ln_group();
     CUtensorMap map, map_dz;
     if (!make_z_map(&map, z, d.B, d.T, d.V, zs_b, zs_v)) { note_failure_site("tensor map of z"); return cudaErrorInvalidValue; }
     if (!make_z_map(&map_dz, dz, d.B, d.T, d.V, dzs_b, dzs_v)) { note_failure_site("tensor map of dz"); return cudaErrorInvalidValue; }
