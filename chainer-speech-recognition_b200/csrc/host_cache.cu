@@ -71,6 +71,7 @@ const Knobs &knobs() {
     static std::once_flag once;
     std::call_once(once, [] {
         k.no_tma = getenv("B200CTC_NO_TMA") != nullptr;
+        if (const char *e = getenv("B200CTC_LN_GROUP")) k.ln_group = atoi(e) > 0 ? atoi(e) : 0;      // tile order of the fused-LN kernels
 #ifdef B200CTC_EXPERIMENT
         k.no_tma_k1 = getenv("B200CTC_NO_TMA_K1") != nullptr;
         k.no_tma_k3 = getenv("B200CTC_NO_TMA_K3") != nullptr;
@@ -82,7 +83,6 @@ const Knobs &knobs() {
         if (const char *e = getenv("B200CTC_LAT_K")) k.lat_k = atoi(e);
         if (const char *e = getenv("B200CTC_LAT_CH")) k.lat_ch = atoi(e);
         if (const char *e = getenv("B200CTC_L2_HINTS")) k.l2_hints = atoi(e);
-        if (const char *e = getenv("B200CTC_LN_GROUP")) k.ln_group = atoi(e);
 #endif
     });
     return k;

@@ -151,11 +151,7 @@ __device__ __forceinline__ void mbar_poll(uint64_t *bar, uint32_t parity, int si
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kLnWarps) : "memory"); }
 
 // ---- tile order ----
-#ifdef B200CTC_EXPERIMENT
 inline int ln_group() { return knobs().ln_group > 0 ? knobs().ln_group : kLnGroup; }
-#else
-inline int ln_group() { return kLnGroup; }
-#endif
 // A tile takes 32 bytes out of every row of z, rows 4*T bytes apart: what DRAM sees depends on which tiles are in flight
 // TOGETHER.  Groups of G consecutive 8-frame blocks of one utterance get consecutive tickets, so the SMs working on them
 // touch 32*G contiguous bytes of every row at about the same time.  G = 4 (one 128-byte line) is the measured best:
