@@ -229,11 +229,32 @@ __device__ __forceinline__ void store_results(const float2 (&outv)[K], float2 *o
             // slot 0 = node j (blank), slot 1 = node j-1; out points at slot 0's (shifted, odd) storage element
             if (store_mask & 1u) *reinterpret_cast<float4 *>(out - 1) = make_float4(outv[1].x, outv[1].y, outv[0].x, outv[0].y);
         }
+    } else if constexpr (!GRAM && K == 4) {
+        // four nodes = one 32-byte sector, written whole by ONE 256-bit store (STG.E.256): four predicated 8-byte stores
+        // made four partial-sector writes per lane and frame, and the long lattices this mapping is for ran four times
+        // slower per frame than the two-node mapping.  The reversed direction's groups are sector-aligned because its
+        // lanes are shifted by `rev_shift` phantom nodes (init_lane); slots of a group that hold no node land in the
+        // row padding.
+        if (store_mask != 0u) {
+            float2 *dst = REV ? out - 3 : out;
+            const float2 a = outv[REV ? 3 : 0], b = outv[REV ? 2 : 1], c = outv[REV ? 1 : 2], d = outv[REV ? 0 : 3];
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y),
+                         "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y)
+                         : "memory");
+        }
     } else {
 #pragma unroll
         for (int r = 0; r < K; ++r)
             if ((store_mask >> r) & 1u) out[REV ? -r : r] = outv[r];
     }
+}
+
+// Reversed direction of the four-node CTC mapping: number of phantom nodes in front of the lattice's first node, chosen
+// so that every lane's group of four storage elements (node j is stored at j + boff whatever the mapping) starts on a
+// 32-byte boundary: (Nb + shift + boff) % 4 == 0.  Even for CTC (Nb odd, boff 1), so blank/label parity is kept.
+template <int K, bool GRAM>
+__host__ __device__ inline int rev_shift(int Nb, int boff) {
+    return (!GRAM && K == 4) ? ((4 - ((Nb + boff) & 3)) & 3) : 0;
 }
 
 // one frame of the recursion for this lane
@@ -348,7 +369,7 @@ __device__ __forceinline__ void run_direction(LaneState<K, GRAM> &st, const DirP
     const uint32_t stage_bytes = row_bytes * CH;
     const uint32_t bnd_chunk_bytes = CH * PAD * 8u;
     const int gl = 32 * w + lane;                             // lane index within the direction
-    const int jbase = REV ? (c.Nb - 1 - K * gl + c.boff) : (K * gl);
+    const int jbase = REV ? (c.Nb - 1 + rev_shift<K, GRAM>(c.Nb, c.boff) - K * gl + c.boff) : (K * gl);
     const int64_t frame_step = REV ? -(int64_t)c.Np : (int64_t)c.Np;
     float2 *out_ptr = c.out_g + (size_t)f0 * c.Np + jbase;    // this lane's first node in frame f0
     // what this warp waits for before a chunk: warp 0 the emission rows, the others the warp before them (which
@@ -426,11 +447,12 @@ __device__ __forceinline__ void init_lane(LaneState<K, GRAM> &st, const ProblemD
     const int32_t *lab = d.labels + (size_t)b * d.Lmax;
     const int32_t *big = GRAM ? d.bigrams + (size_t)b * d.Lmax : nullptr;
     st.valid = 0u;
+    const int shift = rev ? rev_shift<K, GRAM>(Nb, GRAM ? 0 : 1) : 0;     // phantom nodes in front (reversed 4-node CTC mapping)
 #pragma unroll
     for (int r = 0; r < K; ++r) {
-        const int q = K * gl + r;
+        const int q = K * gl + r - shift;                // node index in this direction's coordinates
         const int j = rev ? Nb - 1 - q : q;              // forward node index
-        const bool ok = q < Nb;
+        const bool ok = q >= 0 && q < Nb;
         st.m[r] = (q == 0) ? 1.f : 0.f;                  // virtual state: all mass on the first node (gram_ctc.py:144)
         st.e[r] = (q == 0) ? 0.f : SENT;
         if (ok) st.valid |= (1u << r);
@@ -668,7 +690,7 @@ WsLayout ctc_view_of_joint(const WsLayout &w) {
 void lattice_set_debug(long long *p) { cudaMemcpyToSymbol(g_lat_dbg, &p, sizeof(p)); }
 #endif
 
-int lattice_max_nodes(int kind) { return kind == 0 ? 32 * 4 * kMaxWarpsPerDir : 32 * 6 * kMaxWarpsPerDir; }
+int lattice_max_nodes(int kind) { return kind == 0 ? 32 * 4 * kMaxWarpsPerDir - 3 : 32 * 6 * kMaxWarpsPerDir; }      // - 3: phantom nodes of the 4-node mapping
 
 cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bool concurrent, size_t *smem_out,
                            bool launch) {
@@ -688,7 +710,7 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
         if (kind == 1 && (knobs().lat_k == 3 || knobs().lat_k == 6 || (knobs().lat_k == 1 && Nmax <= 32 * kGenericMaxWarps))) K = knobs().lat_k;
     }
 #endif
-    const int W = (Nmax + 32 * K - 1) / (32 * K);
+    const int W = (Nmax + (kind == 0 && K == 4 ? 3 : 0) + 32 * K - 1) / (32 * K);      // + the reversed direction's phantom nodes
     if (W > kMaxWarpsPerDir) { *status = 2; return cudaSuccess; }
     const int PAD = kind == 0 ? 2 : 7;
     // chunk length: the longest one instantiated for this W whose ring of W + 3 stages fits
@@ -696,7 +718,9 @@ cudaError_t launch_lattice(LatticeParams p, cudaStream_t stream, int *status, bo
     // from that kernel's ring, and measured on the bench workload the shallower ring is the better trade)
     const int ahead = (concurrent && W <= 3) ? 2 : 3;
     const int want = W + ahead < kMaxStages ? W + ahead : kMaxStages;
-    int CH = W <= 7 ? 16 : 8;
+    // (a fully unrolled 16-frame chunk of a four-node step is ~48 KB of code: measured 309 cycles per frame against 154
+    // with 8-frame chunks -- instruction fetch, not arithmetic)
+    int CH = (W <= 7 && K <= 3) ? 16 : 8;
     const int CHmin = W <= 3 ? 16 : 4;
     // next to the softmax/gather kernel every byte here is taken from that kernel's ring: stay below 64 KB if a
     // shorter chunk allows it
