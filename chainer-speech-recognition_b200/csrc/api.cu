@@ -16,7 +16,7 @@ namespace {
 
 // zeroes the workspace header (ticket counters) and the frame-progress counters in stream order
 __global__ void zero_header_kernel(WsHeader *h, unsigned *prog, int nprog) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; h->k2b_done = 0u; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { h->k1_ticket = 0u; h->k3_ticket = 0u; h->k3_done = 0u; h->k2_done = 0u; h->k2b_done = 0u; h->stalled = 0u; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nprog; i += gridDim.x * blockDim.x) prog[i] = 0u;
 }
 

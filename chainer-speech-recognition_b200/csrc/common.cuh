@@ -42,6 +42,9 @@ struct WsHeader {
     unsigned int k3_done;      // gradient warps that ran out of work (last one re-arms the queue)
     unsigned int k2_done;      // lattice CTAs that have published their loss (last one reduces the batch)
     unsigned int k2b_done;     // same for the second (plain CTC) lattice of a joint Gram-CTC + CTC call
+    unsigned int stalled;      // a lattice CTA gave up waiting for emission rows of the softmax/gather kernel running next to
+                               // it (seconds: the two kernels are not co-resident -- never seen, but it must not hang the GPU);
+                               // the losses of the call are NaN then
 };
 
 // Workspace carve-up (all offsets in bytes from a 16-byte aligned base).

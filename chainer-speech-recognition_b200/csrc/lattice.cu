@@ -310,10 +310,16 @@ __device__ __forceinline__ void lattice_step(LaneState<K, GRAM> &st, int lane, b
 // The softmax/gather kernel may still be running (api.cu launches the two kernels concurrently): before a chunk's
 // rows are copied, the warp makes sure the 16-frame blocks the chunk touches are complete.  It keeps a watermark of
 // blocks known complete in its direction of travel and, when it has to look, checks 32 blocks with one round trip.
+// A wait that lasts seconds means the softmax/gather kernel is not running next to this one at all (something else
+// holds the SMs): give up, flag it (WsHeader::stalled; the call's losses become NaN) and run on with whatever is there --
+// a wrong result that the caller's NaN guard catches, not a hung GPU.
+constexpr unsigned kPollLimit = 1u << 24;         // x (128 ns nap + one L2 round trip): several seconds
 template <bool REV, int CH>
 __device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c, int f0, int n, int lane,
-                                             const unsigned char *ws, const WsLayout &wl, int b, bool poll) {
+                                             const unsigned char *ws, const WsLayout &wl, int b, bool poll,
+                                             volatile unsigned *stalled) {
     if (n <= 0) return;
+    unsigned idle = 0;
     const int S = c.S;
     const int nchunks = (n + CH - 1) / CH;
     const uint32_t row_bytes = (uint32_t)c.Wlp * 8u;
@@ -333,14 +339,14 @@ __device__ __forceinline__ void io_direction(const DirPipe &pp, const UttCtx &c,
             while (known < need) {
                 const int got = count_blocks_done(ws, wl, b, n, known, 1, lane);
                 known += got;
-                if (got == 0) __nanosleep(128);
+                if (got == 0) { __nanosleep(128); if (++idle > kPollLimit) { *stalled = 1u; break; } }
             }
         } else {
             const int need = flo / kProgBlock;                           // blocks [need, last] must be complete
             while (known > need) {
                 const int got = count_blocks_done(ws, wl, b, n, known - 1, -1, lane);
                 known -= got;
-                if (got == 0) __nanosleep(128);
+                if (got == 0) { __nanosleep(128); if (++idle > kPollLimit) { *stalled = 1u; break; } }
             }
         }
         if (lane == 0) {
@@ -577,8 +583,8 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         c.out_g = dir == 0 ? av : bv;
         c.Wlp = p.w.W; c.Np = p.w.Np; c.Nb = Nb; c.W = W; c.S = S; c.boff = p.w.boff;
         if (io) {
-            if (dir == 0) io_direction<false, CH>(pp, c, 0, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
-            else          io_direction<true, CH>(pp, c, Tb - 1, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0);
+            if (dir == 0) io_direction<false, CH>(pp, c, 0, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0, &hdr->stalled);
+            else          io_direction<true, CH>(pp, c, Tb - 1, Tb, lane, p.ws, p.w, b, (d.progress & 1) != 0, &hdr->stalled);
         } else {
             LaneState<K, GRAM> st;
             init_lane<K, GRAM>(st, d, b, Lb, Nb, dir == 1, 32 * w + lane);
@@ -632,6 +638,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
                 loss = 1e10f;                            // what the reference returns
             }
         }
+        if (*reinterpret_cast<volatile unsigned *>(&hdr->stalled) != 0u) loss = __int_as_float(0x7fc00000);      // see kPollLimit
         ui->Ph = Ph; ui->Pl = Pl; ui->loss = loss; ui->infeasible = feas ? 0 : 1;
         p.loss_per_utt[b] = p.second ? __ldcg(p.loss_per_utt + b) + loss : loss;     // joint: Gram-CTC loss + CTC loss
         // ---- the last CTA reduces the batch in a fixed order (gram_ctc.py:280-281) ----
@@ -646,6 +653,7 @@ __global__ void __launch_bounds__(32 * (MAXW + 1)) lattice_kernel(LatticeParams 
         for (int i = lane; i < d.B; i += 32) acc += (double)__ldcg(p.loss_per_utt + i);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (*reinterpret_cast<volatile unsigned *>(&hdr->stalled) != 0u) acc = (double)__int_as_float(0x7fc00000);
         if (lane == 0) *p.loss_reduced = (float)(acc * (double)p.loss_scale);
     }
     B200CTC_TL_K2(1, true);
