@@ -336,7 +336,7 @@ def main():
     in_len = torch.tensor(prob["input_length"], device=dev)
     lab_len = torch.tensor(prob["label_length"], device=dev)
     # Batch-sharded step: every rank scales its partial loss sum by 1/B_global in-kernel
-    # (batch_global), the gradient needs no communication, and the ONE collective of the path -- a scalar NCCL
+    # (batch_global), the gradient needs no communication, and the ONE collective of the path -- a small NCCL
     # all-reduce of the loss -- is issued after the gradient kernel has been enqueued, so no rank's backward ever
     # waits for a peer's forward.
     kw = {"batch_global": world * B} if world > 1 else {}
