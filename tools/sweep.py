@@ -3,6 +3,7 @@
   cfg1  CTC B=8,T=200,V=3500,L=40            cfg2  CTC B=64,T=800,V=3500,L=80 (the bench workload)
   cfg3  Gram-CTC B=32,T=600,V=8000,L=60      cfg4  CTC B=512,T=800,V=3500,L=80 on ONE GPU (its per-GPU share at 8 GPUs is cfg2)
   cfg5  CTC sweep T in {200,800,1600,3200} x V in {100,3500}, B=64, L=T/10
+  plus  cfg2 at B = 96, 128, 144 (the softmax/gather and lattice kernels still run side by side, two lattice CTAs per SM)
 
 For each: forward / backward / step time (CUDA events, inputs resident in HBM, 5 warm-up + 20 timed steps), padded
 frames per second and the fraction of the HBM roofline of the step's algorithmic bytes
@@ -39,6 +40,8 @@ def configs():
     yield "cfg3", "gram", 32, 600, 8000, 60
     yield "cfg3 +ctc, 2 calls", "gram+ctc", 32, 600, 8000, 60      # joint training, run/gram_ctc/cnn/train.py:196-198
     yield "cfg3 +ctc, joint", "joint", 32, 600, 8000, 60           # the same objective from one pass (joint_ctc=True)
+    for B in (96, 128, 144):                                       # between "every lattice CTA pair has an SM" and the serial schedule
+        yield "cfg2 B=%d" % B, "ctc", B, 800, 3500, 80
     yield "cfg4", "ctc", 512, 800, 3500, 80
     yield "cfg4 length-sorted", "ctc", 512, 800, 3500, 80          # asr/data/processing.py sort_by_length=True
     for T in (200, 800, 1600, 3200):
