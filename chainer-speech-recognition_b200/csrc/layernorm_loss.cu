@@ -139,12 +139,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 #ifdef B200CTC_EXPERIMENT
 #define LN_WATCHDOG(site, it_) do { if (++(it_) > (1ll << 25)) { printf("LN HANG site %d block %d thread %d\n", site, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
 #else
-#define LN_WATCHDOG(site, it_) ((void)0)
+#define LN_WATCHDOG(site, it_) ((void)(it_))
 #endif
 // For the lanes of the producer warp, which share ONE warp while running different loops: a suspending wait in one
 // lane would put the others to sleep with it, so these lanes only probe (test_wait returns at once) and nap.
 __device__ __forceinline__ void mbar_poll(uint64_t *bar, uint32_t parity, int site = 0) {
-    long long it_ = 0;
+    [[maybe_unused]] long long it_ = 0;
     (void)it_; (void)site;
     while (!mbar_test_wait(bar, parity)) { __nanosleep(40); LN_WATCHDOG(site, it_); }
 }
@@ -376,7 +376,7 @@ __device__ __forceinline__ void ln_signaller(const LnParams &p, unsigned char *s
     LnSignalFifo *ff = reinterpret_cast<LnSignalFifo *>(smem + sm.off_fifo);
     unsigned taken = 0;
     for (;;) {
-        long long it_ = 0;
+        [[maybe_unused]] long long it_ = 0;
         (void)it_;
         while (*reinterpret_cast<volatile unsigned *>(&ff->head) == taken) { __nanosleep(100); LN_WATCHDOG(2, it_); }
         __threadfence_block();
@@ -389,7 +389,7 @@ __device__ __forceinline__ void ln_signaller(const LnParams &p, unsigned char *s
     }
 }
 __device__ __forceinline__ void ln_signal_push(LnSignalFifo *ff, unsigned &pushed, int b, int blk, int n) {
-    long long it_ = 0;
+    [[maybe_unused]] long long it_ = 0;
     (void)it_;
     while (pushed - *reinterpret_cast<volatile unsigned *>(&ff->tail) >= (unsigned)kLnFifo) { __nanosleep(64); LN_WATCHDOG(3, it_); }
     ff->entry[pushed % kLnFifo] = make_int4(b, blk, n, 0);
@@ -411,7 +411,7 @@ __device__ __forceinline__ void ln_storer(const CUtensorMap *tmap_out, const LnP
     unsigned slot = 0;
     for (unsigned n = 0;; ++n) {
         bool stop = false;
-        long long it_ = 0;
+        [[maybe_unused]] long long it_ = 0;
         (void)it_;
         while (!mbar_test_wait(outbar, n & 1u)) {
             if (*total == n + 1u) { stop = true; break; }
@@ -449,7 +449,7 @@ struct SlotIter {
     __device__ __forceinline__ void next(unsigned R) { if (++slot == R) { slot = 0; phase ^= 1u; } }
 };
 __device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity, int site = 0) {
-    long long it_ = 0;
+    [[maybe_unused]] long long it_ = 0;
     (void)it_; (void)site;
 #ifdef B200CTC_EXPERIMENT
     while (!mbar_test_wait(bar, parity)) { LN_WATCHDOG(site, it_); }     // watchdog build: probe, count, report

@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
         unsigned q = 0;
         long long r_wait0 = 0, r_wait1 = 0, r_rows = 0;
         const long long r_begin = K1_CLK();
+        (void)r_begin;
         // one batch of tickets -> rows into the ring; returns false when the queue is exhausted
         auto issue_batch = [&](unsigned base) -> bool {
             if (base >= frames) return false;
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) softmax_gather_ring_kernel(Prob
     unsigned pushed = 0;
     long long c_wait = 0, c_proc = 0, c_rows = 0;
     const long long c_begin = K1_CLK();
+    (void)c_begin;
     for (;;) {
         const unsigned q = ring_next_row(ring, lane);
         const long long c0 = K1_CLK();
