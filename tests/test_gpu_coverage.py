@@ -71,6 +71,18 @@ def test_long_label_gram(pkg, shape, trained):
     assert_parity(loss, grad, loss_ref, grad_ref, "long gram %r" % (shape,))
 
 
+@pytest.mark.parametrize("lab_len", [[300, 1, 0, 157], [299, 2, 3, 158]])
+def test_short_labels_inside_a_long_label_batch(pkg, lab_len):
+    """Lmax = 300 selects the four-nodes-per-lane mapping (256-bit stores, reversed direction shifted by phantom nodes so
+    that its groups are sector-aligned): label lengths 0, 1, 2, 3 and both parities of Nb + shift must come out right."""
+    prob = synth().ctc_problem(4, 700, 50, 300, seed=45)
+    prob["label_length"] = np.asarray(lab_len, np.int32)
+    prob["input_length"] = np.asarray([700, 650, 40, 700], np.int32)
+    loss, grad, _ = run_cuda(pkg, prob, "ctc")
+    loss_ref, grad_ref, _ = run_oracle(prob, "ctc")
+    assert_parity(loss, grad, loss_ref, grad_ref, "short labels, long Lmax %r" % (lab_len,))
+
+
 def test_lattice_size_limit_is_reported_not_crashed(pkg):
     import torch
     x = torch.zeros(2100, 1, 8, device="cuda:0")
