@@ -476,17 +476,11 @@ def main():
             del loss                                    # drop the eager autograd graph (its AccumulateGrad node is bound to
             x.grad = None                               # the default stream, which would invalidate the capture)
             gkw = {"batch_global": world * B} if world > 1 else {}
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean", **gkw).backward()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            x.grad = None
-            with torch.cuda.graph(graph, **({"capture_error_mode": "thread_local"} if world > 1 else {})):
-                gloss = b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean", **gkw)
-                gloss.backward()
+            # the package's own helper (asr/loss/graphed.py): what a training loop with fixed shapes would use
+            gstep = b200ctc.GraphedStep(
+                lambda: b200ctc.connectionist_temporal_classification(x, labels, 0, in_len, lab_len, reduce="mean", **gkw),
+                [x], warmup=1, capture_error_mode="thread_local" if world > 1 else None)
+            graph, gloss = gstep.graph, gstep.loss
         except Exception as exc:                                   # capture unsupported: the eager number stands
             sys.stderr.write("bench.py: CUDA graph capture skipped (%s)\n" % exc)
             captured = 0.0

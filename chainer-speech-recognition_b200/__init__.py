@@ -15,12 +15,12 @@ from . import _lib, distributed, synth
 from ._build import build
 from .asr.loss import (gram_ctc, joint_gram_ctc, GramCTC, connectionist_temporal_classification, ctc,
                        ConnectionistTemporalClassification, greedy_argmax, ctc_host, gram_ctc_host,
-                       layernorm_ctc, layernorm_gram_ctc)
+                       layernorm_ctc, layernorm_gram_ctc, GraphedStep)
 
 from .asr.data import labels_to_minibatch
 from .asr.error import (compute_minibatch_error, compute_character_error_rate, build_expansion_table,
                         minibatch_error_details)
 
-__all__ = ["layernorm_ctc", "layernorm_gram_ctc", "labels_to_minibatch", "joint_gram_ctc", "compute_minibatch_error", "compute_character_error_rate", "build_expansion_table", "minibatch_error_details",
+__all__ = ["GraphedStep", "layernorm_ctc", "layernorm_gram_ctc", "labels_to_minibatch", "joint_gram_ctc", "compute_minibatch_error", "compute_character_error_rate", "build_expansion_table", "minibatch_error_details",
            "gram_ctc", "GramCTC", "connectionist_temporal_classification", "ctc",
            "ConnectionistTemporalClassification", "greedy_argmax", "ctc_host", "gram_ctc_host", "build", "distributed", "synth"]

@@ -5,3 +5,4 @@ from .ctc import connectionist_temporal_classification, ctc, ConnectionistTempor
 from ._function import greedy_argmax                                         # noqa: F401
 from .host import ctc_host, gram_ctc_host                                   # noqa: F401
 from .layernorm_loss import layernorm_ctc, layernorm_gram_ctc                         # noqa: F401
+from .graphed import GraphedStep                                             # noqa: F401

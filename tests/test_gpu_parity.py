@@ -333,3 +333,31 @@ def test_concurrent_and_serial_forward_agree_bitwise(pkg, monkeypatch):
     monkeypatch.setenv("B200CTC_NO_CONCURRENT", "1")
     b = run_cuda(pkg, prob, "ctc")
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
+def test_graphed_step_replays_the_eager_step(pkg):
+    """GraphedStep (asr/loss/graphed.py): one captured forward + backward, replayed on new data copied into the captured
+    tensors, gives the eager call's loss and gradient bit for bit."""
+    import importlib
+    import torch
+    s = importlib.import_module("chainer-speech-recognition_b200.synth")
+    dev = torch.device("cuda:0")
+    probs = [s.ctc_problem(6, 90, 130, 12, seed=51), s.ctc_problem(6, 90, 130, 12, seed=52)]
+    x = torch.tensor(probs[0]["x"], device=dev, requires_grad=True)
+    lab = torch.tensor(probs[0]["labels"], device=dev)
+    il = torch.tensor(probs[0]["input_length"], device=dev)
+    ll = torch.tensor(probs[0]["label_length"], device=dev)
+    step = pkg.GraphedStep(lambda: pkg.ctc(x, lab, 0, il, ll, reduce="mean"), [x])
+    for prob in probs + probs[:1]:
+        with torch.no_grad():
+            x.copy_(torch.tensor(prob["x"], device=dev)); lab.copy_(torch.tensor(prob["labels"], device=dev))
+            il.copy_(torch.tensor(prob["input_length"], device=dev)); ll.copy_(torch.tensor(prob["label_length"], device=dev))
+        loss = step.replay()
+        torch.cuda.synchronize()
+        got_loss, got_grad = float(loss.detach()), x.grad.clone()
+        xe = torch.tensor(prob["x"], device=dev, requires_grad=True)
+        le = pkg.ctc(xe, lab, 0, il, ll, reduce="mean")
+        le.backward()
+        assert got_loss == float(le.detach())
+        assert torch.equal(got_grad, xe.grad)
